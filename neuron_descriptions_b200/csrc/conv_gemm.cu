@@ -1,0 +1,405 @@
+// tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h for the contract).
+//
+// CTA = 6 warps, persistent over output tiles (static round-robin):
+//   warp 0      : TMA producer  (A boxes per tap / k-block, B weight tiles) -> smem ring, mbarrier full/empty
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer -> fp32 accumulators in TMEM (2 buffers)
+//   warps 2..5  : epilogue: tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo split or fp32 -> global
+// The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "conv_gemm.h"
+#include "ptx.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace milan {
+
+namespace {
+
+constexpr int kNumThreads = 192;
+constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KiB, one A plane per stage
+
+template <int BLOCK_N, bool SPLIT>
+struct SmemLayout {
+  static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
+  static constexpr int kPlanes = SPLIT ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
+};
+
+template <int BLOCK_N, bool SPLIT, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using L = SmemLayout<BLOCK_N, SPLIT>;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; power of two (128 or 256)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int pl = 0; pl < 4; ++pl) {
+      tma_prefetch_desc(&p.tmap_a[0][pl]);
+      if (SPLIT) tma_prefetch_desc(&p.tmap_a[1][pl]);
+    }
+    tma_prefetch_desc(&p.tmap_b[0]);
+    if (SPLIT) tma_prefetch_desc(&p.tmap_b[1]);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int cin_blocks = p.cin / kGemmBlockK;
+  const int num_kb = p.num_taps * cin_blocks;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = L::kPlanes * (p.a_box_bytes + L::kBBytes);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.box_w, h0 = th * p.box_h, n0 = tn * p.box_n;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int plane = p.tap_plane[tap];
+          const int cw = w0 + p.tap_dw[tap];
+          const int ch = h0 + p.tap_dh[tap];
+          for (int cb = 0; cb < cin_blocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * L::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+            if (SPLIT) tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+            uint8_t* sb = st + L::kPlanes * kABytes;
+            const int kcoord = (tap * cin_blocks + cb) * kGemmBlockK;
+            tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+            if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_hi = a_hi + L::kPlanes * kABytes;
+          const uint64_t da_hi = make_smem_desc_sw128(a_hi);
+          const uint64_t db_hi = make_smem_desc_sw128(b_hi);
+          const uint64_t da_lo = make_smem_desc_sw128(a_hi + kABytes);
+          const uint64_t db_lo = make_smem_desc_sw128(b_hi + L::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
+            umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+              umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    const int box_hw = p.box_w * p.box_h;
+    const int dn = row / box_hw;
+    const int rem = row - dn * box_hw;
+    const int dh = rem / p.box_w;
+    const int dw = rem - dh * p.box_w;
+    const bool row_in_box = row < box_hw * p.box_n;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      const int th = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int w = tw * p.box_w + dw, h = th * p.box_h + dh, n = tn * p.box_n + dn;
+      const bool valid = row_in_box && w < p.out_w && h < p.out_h && n < p.out_n;
+      const long long pix = (static_cast<long long>(n) * p.out_h + h) * p.out_w + w;
+
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c0, acc);
+        tmem_ld_wait();
+        const int col0 = n_tile * BLOCK_N + c0;
+        if (valid && col0 < p.cout) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (EPI == EPI_BF16) {
+            const long long off = pix * p.ldc + col0;
+            if (p.res_hi != nullptr) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r = __ldg(r4 + j);
+                v[8 * j + 0] += bf16_lo_to_f32(r.x); v[8 * j + 1] += bf16_hi_to_f32(r.x);
+                v[8 * j + 2] += bf16_lo_to_f32(r.y); v[8 * j + 3] += bf16_hi_to_f32(r.y);
+                v[8 * j + 4] += bf16_lo_to_f32(r.z); v[8 * j + 5] += bf16_hi_to_f32(r.z);
+                v[8 * j + 6] += bf16_lo_to_f32(r.w); v[8 * j + 7] += bf16_hi_to_f32(r.w);
+              }
+              if (SPLIT && p.res_lo != nullptr) {
+                const uint4* q4 = reinterpret_cast<const uint4*>(p.res_lo + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 r = __ldg(q4 + j);
+                  v[8 * j + 0] += bf16_lo_to_f32(r.x); v[8 * j + 1] += bf16_hi_to_f32(r.x);
+                  v[8 * j + 2] += bf16_lo_to_f32(r.y); v[8 * j + 3] += bf16_hi_to_f32(r.y);
+                  v[8 * j + 4] += bf16_lo_to_f32(r.z); v[8 * j + 5] += bf16_hi_to_f32(r.z);
+                  v[8 * j + 6] += bf16_lo_to_f32(r.w); v[8 * j + 7] += bf16_hi_to_f32(r.w);
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(v[2 * j], h0, l0);
+              split_bf16(v[2 * j + 1], h1, l1);
+              hi[j] = pack_bf16x2(h0, h1);
+              lo[j] = pack_bf16x2(l0, l1);
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(p.out_hi + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            if (SPLIT) {
+              uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          } else {  // EPI_F32
+            float* o = p.out_f32 + pix * p.ldc + col0;
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (col0 + 32 <= p.cout) {
+              float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.cout) o[j] = v[j];
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[as]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+std::atomic<long long> g_launches{0};
+
+template <int BLOCK_N, bool SPLIT, int EPI>
+int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, SPLIT>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI>;
+  static bool configured = false;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured = true;
+    }
+  }
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  if (total_tiles <= 0) return 0;
+  const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+  kernel<<<grid, kNumThreads, L::kTotalBytes, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+long long conv_gemm_launch_count() { return g_launches.load(); }
+
+int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
+                     cudaStream_t stream) {
+#define MILAN_DISPATCH(BN, SP, EP) \
+  if (block_n == BN && (split != 0) == SP && epilogue == EP) return launch_impl<BN, SP, EP>(p, num_sms, stream);
+  MILAN_DISPATCH(128, true, EPI_BF16)
+  MILAN_DISPATCH(128, false, EPI_BF16)
+  MILAN_DISPATCH(64, true, EPI_BF16)
+  MILAN_DISPATCH(64, false, EPI_BF16)
+  MILAN_DISPATCH(128, true, EPI_F32)
+  MILAN_DISPATCH(128, false, EPI_F32)
+#undef MILAN_DISPATCH
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+// ---------------------------------------------------------------- tensor maps
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+char g_tmap_err[256] = "";
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+}  // namespace
+
+const char* tmap_last_error() { return g_tmap_err; }
+
+int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n,
+                 uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
+                 uint32_t box_h, uint32_t box_n) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled entry point unavailable");
+    return -1;
+  }
+  cuuint64_t dims[4] = {c, w, h, n};
+  cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kGemmBlockK), box_w, box_h, box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tmap_err, sizeof g_tmap_err,
+             "cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+             "box=(64,%u,%u,%u) base=%p",
+             static_cast<int>(r), (unsigned long long)c, (unsigned long long)w, (unsigned long long)h,
+             (unsigned long long)n, (unsigned long long)stride_w_bytes, (unsigned long long)stride_h_bytes,
+             (unsigned long long)stride_n_bytes, box_w, box_h, box_n, base);
+    return static_cast<int>(r);
+  }
+  return 0;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes,
+                 uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled entry point unavailable");
+    return -1;
+  }
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tmap_err, sizeof g_tmap_err,
+             "cuTensorMapEncodeTiled(2d) failed: %d dims=(%llu,%llu) pitch=%llu box=(64,%u) base=%p",
+             static_cast<int>(r), (unsigned long long)k, (unsigned long long)rows,
+             (unsigned long long)pitch_bytes, box_rows, base);
+    return static_cast<int>(r);
+  }
+  return 0;
+}
+
+void choose_box(int W, int H, int N, int* bw, int* bh, int* bn) {
+  long long best_tiles = -1;
+  int bbw = 1, bbh = 1, bbn = 1;
+  for (int w = 1; w <= W && w <= kGemmBlockM; ++w) {
+    for (int h = 1; h <= H && w * h <= kGemmBlockM; ++h) {
+      int n = kGemmBlockM / (w * h);
+      if (n > N) n = N;
+      if (n > 256) n = 256;
+      if (n < 1) continue;
+      const long long tiles =
+          static_cast<long long>((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
+      // Prefer fewer tiles; on ties prefer wider rows (longer contiguous runs in memory).
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && w > bbw)) {
+        best_tiles = tiles;
+        bbw = w; bbh = h; bbn = n;
+      }
+    }
+  }
+  *bw = bbw; *bh = bbh; *bn = bbn;
+}
+
+}  // namespace milan

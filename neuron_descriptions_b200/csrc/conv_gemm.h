@@ -1,0 +1,107 @@
+// Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// One kernel covers every matrix product on the MILAN hot path:
+//   * ResNet-101 1x1 / 3x3, stride 1 / 2 convolutions of the pyramid encoder
+//     (reference: torchvision resnet101 called at src/milan/encoders.py:298),
+//   * the 7x7 stem as a GEMM over an im2col matrix,
+//   * the decoder / LM linear layers (src/milan/decoders.py:612-621, src/milan/lms.py:85-87).
+//
+// A (activations) is NHWC bf16, addressed through 4-D TMA boxes (c, w, h, n); each filter tap is the same box
+// shifted by (dw, dh), with out-of-bounds pixels zero-filled by TMA (= conv padding). Stride-2 convs read one of
+// four parity planes of the input (same memory, doubled strides) so every load stays a unit-stride box.
+// B (weights) is [Cout][taps*Cin] bf16, K-major.
+//
+// Precision: in SPLIT mode every fp32 operand is carried as a (hi, lo) bf16 pair and each k-block issues
+// hi*hi + lo*hi + hi*lo into the fp32 TMEM accumulator (~2^-16 relative operand error, i.e. fp32-class results
+// on the bf16 tensor pipe). In FAST mode only the hi planes are used (plain bf16).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace milan {
+
+constexpr int kMaxTaps = 9;
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 64;
+
+enum EpilogueKind : int {
+  EPI_BF16 = 0,  // out_hi(/out_lo) bf16 NHWC, + bias, + residual, optional ReLU
+  EPI_F32 = 1,   // out_f32 row-major [pixel][ldc], + bias
+};
+
+struct alignas(64) ConvGemmParams {
+  CUtensorMap tmap_a[2][4];  // [hi|lo][parity plane]
+  CUtensorMap tmap_b[2];     // [hi|lo]
+  int box_w, box_h, box_n;   // M tile = box_w*box_h*box_n (<=128) output pixels
+  int tiles_w, tiles_h, tiles_n;
+  int out_w, out_h, out_n;   // output extents (pixels / images)
+  int n_tiles;               // ceil(cout / BLOCK_N)
+  int cout;
+  int cin;                   // channels per tap (multiple of 64)
+  int num_taps;
+  int8_t tap_plane[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
+  uint32_t a_box_bytes;      // bytes one A box delivers
+  const float* bias;         // [cout] or nullptr
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;
+  long long ldc;             // row pitch (elements) of the output / residual
+  int relu;
+};
+
+// block_n: 64 or 128. split: hi/lo planes (1) or hi only (0). Returns cudaError_t as int.
+int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
+                     cudaStream_t stream);
+// Number of kernel launches performed through launch_conv_gemm since process start (for gpu_launches).
+long long conv_gemm_launch_count();
+
+// Host helpers to build tensor maps (driver entry point resolved at runtime; no libcuda link dependency).
+// 4-D bf16 map: dims (c, w, h, n), byte strides for w/h/n, box (64, bw, bh, bn), 128B swizzle, zero OOB fill.
+int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n,
+                 uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
+                 uint32_t box_h, uint32_t box_n);
+// 2-D bf16 map: dims (k, rows), row pitch bytes, box (64, box_rows).
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes,
+                 uint32_t box_rows);
+const char* tmap_last_error();
+
+// Pick an M-tile box (bw, bh, bn) with bw*bh*bn <= 128 minimising the number of tiles for a WxHxN output.
+void choose_box(int W, int H, int N, int* bw, int* bh, int* bn);
+
+}  // namespace milan
+
+namespace milan {
+
+// Geometry of one convolution (pad = ksize/2, NHWC activations, weights [Cout][ksize*ksize*Cin]).
+// ksize 1 with stride 1 is a plain GEMM over M = N*H*W rows (also used for the decoder linears with H=W=1).
+struct ConvDesc {
+  int N, H, W;   // input extents
+  int Cin, Cout;
+  int ksize;     // 1 or 3
+  int stride;    // 1 or 2
+};
+
+struct ConvIO {
+  const __nv_bfloat16* in_hi;
+  const __nv_bfloat16* in_lo;   // nullptr in FAST mode
+  const __nv_bfloat16* w_hi;    // [Cout][ksize*ksize*Cin]
+  const __nv_bfloat16* w_lo;
+  const float* bias;            // padded to a multiple of 128 floats, or nullptr
+  const __nv_bfloat16* res_hi;  // same shape as the output, or nullptr
+  const __nv_bfloat16* res_lo;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;               // EPI_F32 only
+  long long ldc;                // output row pitch in elements (0 -> Cout)
+  int relu;
+};
+
+// Fills `p` (tensor maps, tiling, taps) for the convolution; returns 0 on success. *block_n receives the
+// N-tile width the kernel must be launched with.
+int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n);
+
+}  // namespace milan

@@ -1,0 +1,112 @@
+// Host-side planning for conv_gemm: tensor maps, M-tile boxes and filter-tap tables per convolution.
+#include "conv_gemm.h"
+
+#include <cstdio>
+#include <cstring>
+
+namespace milan {
+
+int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n) {
+  memset(p, 0, sizeof(*p));
+  if (d.Cin % kGemmBlockK != 0) return -2;
+  if (!(d.ksize == 1 || d.ksize == 3) || !(d.stride == 1 || d.stride == 2)) return -3;
+  if (d.stride == 2 && ((d.H | d.W) & 1)) return -4;
+  const int Ho = d.H / d.stride, Wo = d.W / d.stride;
+  const int bn_tile = (d.Cout <= 64) ? 64 : 128;
+  *block_n = bn_tile;
+  const uint64_t esz = 2;
+  const int nplanes_hi_lo = split ? 2 : 1;
+  const __nv_bfloat16* in_planes[2] = {io.in_hi, io.in_lo};
+  const __nv_bfloat16* w_planes[2] = {io.w_hi, io.w_lo};
+
+  p->cin = d.Cin;
+  p->cout = d.Cout;
+  p->n_tiles = (d.Cout + bn_tile - 1) / bn_tile;
+  p->bias = io.bias;
+  p->res_hi = io.res_hi;
+  p->res_lo = io.res_lo;
+  p->out_hi = io.out_hi;
+  p->out_lo = io.out_lo;
+  p->out_f32 = io.out_f32;
+  p->ldc = io.ldc > 0 ? io.ldc : d.Cout;
+  p->relu = io.relu;
+
+  int rc = 0;
+  if (d.ksize == 1 && d.stride == 1) {
+    // Flat GEMM: rows = all pixels.
+    const long long M = static_cast<long long>(d.N) * d.H * d.W;
+    p->box_w = kGemmBlockM; p->box_h = 1; p->box_n = 1;
+    p->tiles_w = static_cast<int>((M + kGemmBlockM - 1) / kGemmBlockM);
+    p->tiles_h = 1; p->tiles_n = 1;
+    p->out_w = static_cast<int>(M); p->out_h = 1; p->out_n = 1;
+    p->num_taps = 1;
+    p->tap_plane[0] = 0; p->tap_dw[0] = 0; p->tap_dh[0] = 0;
+    for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
+      const uint64_t pitch = static_cast<uint64_t>(d.Cin) * esz;
+      rc = make_tmap_4d(&p->tmap_a[hl][0], in_planes[hl], d.Cin, M, 1, 1, pitch, pitch * M, pitch * M,
+                        kGemmBlockM, 1, 1);
+      if (rc) return rc;
+      for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];
+    }
+  } else {
+    int bw, bh, bn;
+    choose_box(Wo, Ho, d.N, &bw, &bh, &bn);
+    p->box_w = bw; p->box_h = bh; p->box_n = bn;
+    p->tiles_w = (Wo + bw - 1) / bw;
+    p->tiles_h = (Ho + bh - 1) / bh;
+    p->tiles_n = (d.N + bn - 1) / bn;
+    p->out_w = Wo; p->out_h = Ho; p->out_n = d.N;
+    const uint64_t cpitch = static_cast<uint64_t>(d.Cin) * esz;
+    const uint64_t img = cpitch * d.W * d.H;
+    if (d.stride == 1) {
+      for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
+        rc = make_tmap_4d(&p->tmap_a[hl][0], in_planes[hl], d.Cin, d.W, d.H, d.N, cpitch, cpitch * d.W, img, bw, bh, bn);
+        if (rc) return rc;
+        for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];
+      }
+    } else {
+      // Parity planes: pixel (h, w) = (2*h2 + ph, 2*w2 + pw) lives in plane ph*2+pw at (h2, w2).
+      for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int pw = 0; pw < 2; ++pw) {
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(in_planes[hl]) +
+                                  (static_cast<uint64_t>(ph) * d.W + pw) * cpitch;
+            rc = make_tmap_4d(&p->tmap_a[hl][ph * 2 + pw], base, d.Cin, d.W / 2, d.H / 2, d.N, 2 * cpitch,
+                              2 * cpitch * d.W, img, bw, bh, bn);
+            if (rc) return rc;
+          }
+        }
+      }
+    }
+    int t = 0;
+    for (int r = 0; r < d.ksize; ++r) {
+      for (int s = 0; s < d.ksize; ++s, ++t) {
+        const int oh = r - d.ksize / 2, ow = s - d.ksize / 2;  // input offset relative to stride*out
+        if (d.stride == 1) {
+          p->tap_plane[t] = 0; p->tap_dh[t] = static_cast<int8_t>(oh); p->tap_dw[t] = static_cast<int8_t>(ow);
+        } else {
+          // input row = 2*out + oh  ->  parity = oh & 1, plane row = out + floor(oh / 2)
+          const int ph = oh & 1, pw = ow & 1;
+          const int fh = (oh - ph) / 2, fw = (ow - pw) / 2;
+          p->tap_plane[t] = static_cast<int8_t>(ph * 2 + pw);
+          p->tap_dh[t] = static_cast<int8_t>(fh);
+          p->tap_dw[t] = static_cast<int8_t>(fw);
+        }
+      }
+    }
+    p->num_taps = t;
+  }
+  p->a_box_bytes = static_cast<uint32_t>(p->box_w) * p->box_h * p->box_n * kGemmBlockK * 2;
+  const uint64_t ktot = static_cast<uint64_t>(p->num_taps) * d.Cin;
+  for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
+    rc = make_tmap_2d(&p->tmap_b[hl], w_planes[hl], ktot, d.Cout, ktot * esz, bn_tile);
+    if (rc) return rc;
+  }
+  if (!split) {
+    p->tmap_b[1] = p->tmap_b[0];
+    for (int pl = 0; pl < 4; ++pl) p->tmap_a[1][pl] = p->tmap_a[0][pl];
+  }
+  return 0;
+}
+
+}  // namespace milan

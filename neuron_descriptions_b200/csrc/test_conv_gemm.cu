@@ -1,0 +1,224 @@
+// Standalone check of the tcgen05 conv/GEMM kernel against a double-precision CPU convolution.
+// Build: make -C neuron_descriptions_b200/csrc test_conv_gemm ; run on a B200 (gpurun).
+#include "conv_gemm.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+using namespace milan;
+
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) {                                                         \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                       \
+    }                                                                                \
+  } while (0)
+
+static uint16_t f2bf(float f) {  // round-to-nearest-even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static void split(const std::vector<float>& x, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  hi.resize(x.size());
+  lo.resize(x.size());
+  for (size_t i = 0; i < x.size(); ++i) {
+    hi[i] = f2bf(x[i]);
+    lo[i] = f2bf(x[i] - bf2f(hi[i]));
+  }
+}
+template <class T>
+static T* upload(const std::vector<T>& v) {
+  T* d;
+  CK(cudaMalloc(&d, v.size() * sizeof(T) + 256));
+  CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+struct Case {
+  const char* name;
+  int N, H, W, Cin, Cout, ks, stride, relu, residual, split, f32out;
+};
+
+static int run_case(const Case& c, int num_sms) {
+  std::mt19937 rng(1234 + c.Cin * 7 + c.Cout + c.H);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  const int Ho = c.H / c.stride, Wo = c.W / c.stride;
+  const size_t in_elems = static_cast<size_t>(c.N) * c.H * c.W * c.Cin;
+  const int taps = c.ks * c.ks;
+  const size_t w_elems = static_cast<size_t>(c.Cout) * taps * c.Cin;
+  const size_t out_elems = static_cast<size_t>(c.N) * Ho * Wo * c.Cout;
+  std::vector<float> x(in_elems), w(w_elems), bias((c.Cout + 127) / 128 * 128, 0.f), res(out_elems);
+  for (auto& v : x) v = nd(rng);
+  const float wscale = 1.0f / std::sqrt(static_cast<float>(taps * c.Cin));
+  for (auto& v : w) v = nd(rng) * wscale;
+  for (int i = 0; i < c.Cout; ++i) bias[i] = nd(rng) * 0.1f;
+  for (auto& v : res) v = nd(rng);
+  std::vector<uint16_t> xh, xl, wh, wl, rh, rl;
+  split(x, xh, xl);
+  split(w, wh, wl);
+  split(res, rh, rl);
+  // The CPU reference uses exactly the values the GPU sees.
+  std::vector<float> xe(in_elems), we(w_elems), re(out_elems);
+  for (size_t i = 0; i < in_elems; ++i) xe[i] = c.split ? bf2f(xh[i]) + bf2f(xl[i]) : bf2f(xh[i]);
+  for (size_t i = 0; i < w_elems; ++i) we[i] = c.split ? bf2f(wh[i]) + bf2f(wl[i]) : bf2f(wh[i]);
+  for (size_t i = 0; i < out_elems; ++i) re[i] = c.split ? bf2f(rh[i]) + bf2f(rl[i]) : bf2f(rh[i]);
+
+  uint16_t *dxh = upload(xh), *dxl = upload(xl), *dwh = upload(wh), *dwl = upload(wl), *drh = upload(rh),
+           *drl = upload(rl);
+  float* dbias = upload(bias);
+  uint16_t *doh, *dol;
+  float* dof;
+  CK(cudaMalloc(&doh, out_elems * 2 + 256));
+  CK(cudaMalloc(&dol, out_elems * 2 + 256));
+  CK(cudaMalloc(&dof, out_elems * 4 + 256));
+  CK(cudaMemset(doh, 0xFF, out_elems * 2));
+  CK(cudaMemset(dol, 0xFF, out_elems * 2));
+  CK(cudaMemset(dof, 0xFF, out_elems * 4));
+
+  ConvDesc d{c.N, c.H, c.W, c.Cin, c.Cout, c.ks, c.stride};
+  ConvIO io{};
+  io.in_hi = reinterpret_cast<__nv_bfloat16*>(dxh);
+  io.in_lo = reinterpret_cast<__nv_bfloat16*>(dxl);
+  io.w_hi = reinterpret_cast<__nv_bfloat16*>(dwh);
+  io.w_lo = reinterpret_cast<__nv_bfloat16*>(dwl);
+  io.bias = dbias;
+  if (c.residual) {
+    io.res_hi = reinterpret_cast<__nv_bfloat16*>(drh);
+    io.res_lo = reinterpret_cast<__nv_bfloat16*>(drl);
+  }
+  io.out_hi = reinterpret_cast<__nv_bfloat16*>(doh);
+  io.out_lo = reinterpret_cast<__nv_bfloat16*>(dol);
+  io.out_f32 = dof;
+  io.relu = c.relu;
+  ConvGemmParams p;
+  int block_n = 0;
+  int rc = build_conv_params(&p, d, io, c.split, &block_n);
+  if (rc) {
+    printf("[%s] build_conv_params failed rc=%d: %s\n", c.name, rc, tmap_last_error());
+    return 1;
+  }
+  if (c.f32out) block_n = 128;
+  if (c.f32out && c.Cout <= 64) { printf("[%s] bad case\n", c.name); return 1; }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  rc = launch_conv_gemm(p, block_n, c.split, c.f32out ? EPI_F32 : EPI_BF16, num_sms, 0);
+  if (rc) { printf("[%s] launch failed rc=%d\n", c.name, rc); return 1; }
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) { printf("[%s] kernel failed: %s\n", c.name, cudaGetErrorString(se)); return 1; }
+  const int reps = 5;
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < reps; ++i) launch_conv_gemm(p, block_n, c.split, c.f32out ? EPI_F32 : EPI_BF16, num_sms, 0);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= reps;
+
+  std::vector<uint16_t> oh(out_elems), ol(out_elems);
+  std::vector<float> of(out_elems);
+  CK(cudaMemcpy(oh.data(), doh, out_elems * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ol.data(), dol, out_elems * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(of.data(), dof, out_elems * 4, cudaMemcpyDeviceToHost));
+
+  // CPU reference (sampled if large).
+  const int pad = c.ks / 2;
+  double max_err = 0, max_ref = 0;
+  size_t checked = 0, bad = 0;
+  const size_t stride_check = out_elems > 4000000 ? 97 : 1;
+  for (size_t idx = 0; idx < out_elems; idx += stride_check) {
+    const int co = idx % c.Cout;
+    size_t pix = idx / c.Cout;
+    const int ow = pix % Wo;
+    const int oh_ = (pix / Wo) % Ho;
+    const int n = pix / (static_cast<size_t>(Wo) * Ho);
+    double acc = bias[co];
+    for (int r = 0; r < c.ks; ++r) {
+      const int ih = oh_ * c.stride + r - pad;
+      if (ih < 0 || ih >= c.H) continue;
+      for (int s = 0; s < c.ks; ++s) {
+        const int iw = ow * c.stride + s - pad;
+        if (iw < 0 || iw >= c.W) continue;
+        const float* xp = &xe[((static_cast<size_t>(n) * c.H + ih) * c.W + iw) * c.Cin];
+        const float* wp = &we[(static_cast<size_t>(co) * taps + r * c.ks + s) * c.Cin];
+        for (int ci = 0; ci < c.Cin; ++ci) acc += static_cast<double>(xp[ci]) * wp[ci];
+      }
+    }
+    if (c.residual && !c.f32out) acc += re[idx];
+    if (c.relu) acc = acc > 0 ? acc : 0;
+    double got;
+    if (c.f32out) got = of[idx];
+    else got = c.split ? static_cast<double>(bf2f(oh[idx])) + bf2f(ol[idx]) : bf2f(oh[idx]);
+    const double err = std::fabs(got - acc);
+    if (!(err <= 1e30)) { ++bad; }
+    if (err > max_err) max_err = err;
+    if (std::fabs(acc) > max_ref) max_ref = std::fabs(acc);
+    ++checked;
+  }
+  const double tol = c.split ? 2e-4 : 6e-2;
+  const double flops = 2.0 * out_elems * taps * c.Cin;
+  const bool ok = bad == 0 && max_err <= tol * (max_ref > 1 ? max_ref : 1);
+  printf("[%s] N=%d %dx%d Cin=%d Cout=%d k=%d s=%d split=%d f32=%d box=(%d,%d,%d) tiles=%d bn=%d : max_err=%.3e "
+         "(max_ref=%.2f, nan=%zu, checked=%zu) %.3f ms %.1f TFLOP/s %s\n",
+         c.name, c.N, c.H, c.W, c.Cin, c.Cout, c.ks, c.stride, c.split, c.f32out, p.box_w, p.box_h, p.box_n,
+         p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles, block_n, max_err, max_ref, bad, checked, ms,
+         flops / ms * 1e-9, ok ? "OK" : "FAIL");
+  cudaFree(dxh); cudaFree(dxl); cudaFree(dwh); cudaFree(dwl); cudaFree(drh); cudaFree(drl);
+  cudaFree(dbias); cudaFree(doh); cudaFree(dol); cudaFree(dof);
+  return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  int dev = 0;
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
+  const int sms = prop.multiProcessorCount;
+  std::vector<Case> cases = {
+      // name            N   H   W  Cin  Cout ks st relu res split f32
+      {"gemm_small",     1,  1, 128,  64,  128, 1, 1, 0, 0, 0, 0},
+      {"gemm_small_sp",  1,  1, 128,  64,  128, 1, 1, 0, 0, 1, 0},
+      {"gemm_k256",      1,  1, 300, 256,  128, 1, 1, 0, 0, 1, 0},
+      {"gemm_f32_tail",  1,  1, 200, 512,  300, 1, 1, 0, 0, 1, 1},
+      {"c1x1_56",        2, 56,  56,  64,  256, 1, 1, 1, 1, 1, 0},
+      {"c1x1_cout64",    2, 56,  56, 256,   64, 1, 1, 1, 0, 1, 0},
+      {"c3x3_56",        3, 56,  56,  64,   64, 3, 1, 1, 0, 1, 0},
+      {"c3x3_28",        5, 28,  28, 128,  128, 3, 1, 1, 0, 1, 0},
+      {"c3x3_14",        7, 14,  14, 256,  256, 3, 1, 1, 0, 1, 0},
+      {"c3x3_7",         9,  7,   7, 512,  512, 3, 1, 1, 0, 1, 0},
+      {"c3x3_s2_56",     3, 56,  56, 128,  128, 3, 2, 1, 0, 1, 0},
+      {"c3x3_s2_14",     5, 14,  14, 512,  512, 3, 2, 1, 0, 1, 0},
+      {"c1x1_s2_56",     3, 56,  56, 256,  512, 1, 2, 0, 0, 1, 0},
+      {"c3x3_28_fast",   5, 28,  28, 128,  128, 3, 1, 1, 1, 0, 0},
+      // throughput-sized (sampled check)
+      {"perf_l3_1x1",  240, 14,  14, 1024, 256, 1, 1, 1, 0, 1, 0},
+      {"perf_l3_3x3",  240, 14,  14, 256,  256, 3, 1, 1, 0, 1, 0},
+      {"perf_l3_1x1b", 240, 14,  14, 256, 1024, 1, 1, 1, 1, 1, 0},
+      {"perf_l3_3x3f", 240, 14,  14, 256,  256, 3, 1, 1, 0, 0, 0},
+      {"perf_l1_3x3",  240, 56,  56,  64,   64, 3, 1, 1, 0, 1, 0},
+  };
+  int only = argc > 1 ? atoi(argv[1]) : -1;
+  int fails = 0;
+  for (size_t i = 0; i < cases.size(); ++i) {
+    if (only >= 0 && static_cast<int>(i) != only) continue;
+    fails += run_case(cases[i], sms);
+    fflush(stdout);
+  }
+  printf("%s (%d failures)\n", fails ? "SOME FAILED" : "ALL OK", fails);
+  return fails ? 1 : 0;
+}
