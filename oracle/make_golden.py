@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference) on CPU.
+
+Run in the build container only (`python -m oracle.make_golden`); the GPU box has no /root/reference.
+Weights and inputs are regenerated from seeds by `neuron_descriptions_b200.synthetic`, so only outputs are
+stored. The beam search inside the reference's `Decoder.forward` is `oracle.beam_search.BeamSearch`
+(allennlp is not installed; see that file's header) — every other line executed is the reference's own.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from neuron_descriptions_b200 import synthetic  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+VARIANTS = {  # name -> (sharpen, stop_bias)
+    'flat': (1.0, 0.0),     # default nn init: near-uniform logits, top-k order is rounding-sensitive
+    'sharp': (12.0, 0.0),   # well separated, full-length beams
+    'stop': (12.0, 2.0),    # beams end with <stop> at varied lengths (forced-stop path), T = 15
+    'early': (8.0, 2.0),    # every beam ends early -> early exit, T < 15
+}
+ENC_NEURONS, DEC_NEURONS, K = 2, 6, 15
+
+
+def build_reference_decoder(milan, lang, sd, vocab, with_encoder=True):
+    indexer = lang.Indexer(lang.Vocab(tuple(vocab)), tokenize=None, start=True, stop=True, pad=True, unk=True)
+    encoder = milan.encoders.PyramidConvEncoder('resnet101', pretrained=False)
+    lm = milan.lms.LanguageModel(indexer)
+    decoder = milan.decoders.Decoder(indexer, encoder, lm=lm)
+    missing, unexpected = decoder.load_state_dict(sd, strict=False)
+    if with_encoder:
+        assert not missing and not unexpected, (missing, unexpected)
+    else:
+        assert all(k.startswith('encoder.') for k in missing) and not unexpected, (missing, unexpected)
+    return decoder.eval()
+
+
+def synthetic_features(n, k, seed):
+    """Feature tensors with the sparsity/magnitude of masked-pooled ResNet activations."""
+    gen = torch.Generator().manual_seed(seed + 4242)
+    feats = torch.randn(n, k, synthetic.FEATURE_SIZE, generator=gen).abs() * 0.5
+    feats[:, :, :64] = torch.randn(n, k, 64, generator=gen) * 0.3  # raw conv1 block can be negative
+    feats[0, 1] = 0.0  # an all-zero-mask exemplar
+    return feats
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    milan, lang = ref_import.import_reference()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    vocab = synthetic.synthetic_vocab(5000)
+
+    # ---- encoder golden: reference PyramidConvEncoder('resnet101') on seeded exemplars.
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=3.0)
+    decoder = build_reference_decoder(milan, lang, sd, vocab)
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(ENC_NEURONS, K, seed=0, zero_mask_fraction=0.1)
+    masks_u8[0, 0] = 0  # guarantee one all-zero mask
+    masks_u8[1, 3, :, 100:102, 50:52] = 0
+    scale = torch.tensor(1.0 / 255.0, dtype=torch.float64).to(torch.float32)
+    images = images_u8.float().mul(scale)  # TopImagesDataset contract, src/milannotations/datasets.py:191-197
+    masks = masks_u8.float()
+    with torch.no_grad():
+        features = decoder.encode(images, masks)
+        out_greedy = decoder(images, masks, strategy='greedy', mi=False)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'encoder_resnet101.npz'),
+                        features=features.numpy(), greedy_tokens=out_greedy.tokens.numpy(),
+                        greedy_scores=out_greedy.scores.numpy(),
+                        meta=np.array([ENC_NEURONS, K, 0], dtype=np.int64))
+    print('encoder golden: features', tuple(features.shape), 'abs mean', features.abs().mean().item(),
+          'max', features.abs().max().item())
+
+    # ---- decoder goldens, three logit regimes, from seeded features.
+    feats = synthetic_features(DEC_NEURONS, K, seed=0)
+    for name, (sharpen, stop_bias) in VARIANTS.items():
+        sd = synthetic.synthetic_state_dict(seed=0, sharpen=sharpen, stop_bias=stop_bias, with_encoder=False)
+        decoder = build_reference_decoder(milan, lang, sd, vocab, with_encoder=False)
+        stop_index = decoder.indexer.stop_index
+        with torch.no_grad():
+            state = decoder.init_state(feats, lm=False)
+            start = torch.full((DEC_NEURONS,), decoder.indexer.start_index, dtype=torch.long)
+            first = decoder.step(feats, start, state)
+            greedy = decoder(feats, strategy='greedy', mi=False)
+            greedy_mi = decoder(feats, strategy='greedy', mi=True)
+            beam = decoder(feats, strategy='beam', mi=False, beam_size=50)
+            rerank = decoder(feats, strategy='rerank', beam_size=50)
+            small_beam = decoder(feats, strategy='rerank', beam_size=7, length=9)
+            inputs_lm = torch.cat([torch.full((DEC_NEURONS * 50, 1), decoder.indexer.start_index, dtype=torch.long),
+                                   beam.beam_tokens.view(DEC_NEURONS * 50, -1)], dim=-1)
+            lm_scores = decoder.lm(inputs_lm, reduce=True)
+        top_v, top_i = first.predictions.topk(8, dim=-1)
+        np.savez_compressed(
+            os.path.join(GOLDEN_DIR, f'decoder_{name}.npz'),
+            init_h=state.h.numpy(), init_c=state.c.numpy(),
+            step0_attn=first.attentions.numpy(), step0_h=first.state.h.numpy(), step0_c=first.state.c.numpy(),
+            step0_top_values=top_v.numpy(), step0_top_indices=top_i.numpy(),
+            step0_logsumexp=first.predictions.logsumexp(-1).numpy(),
+            greedy_tokens=greedy.tokens.numpy(), greedy_scores=greedy.scores.numpy(),
+            greedy_attn=greedy.attentions.numpy(),
+            greedy_chosen_logp=greedy.predictions.gather(2, greedy.tokens.unsqueeze(-1)).squeeze(-1).numpy(),
+            greedy_mi_tokens=greedy_mi.tokens.numpy(), greedy_mi_scores=greedy_mi.scores.numpy(),
+            beam_tokens=beam.beam_tokens.numpy(), beam_scores=beam.beam_scores.numpy(),
+            rerank_tokens=rerank.tokens.numpy(), rerank_scores=rerank.scores.numpy(),
+            small_beam_tokens=small_beam.beam_tokens.numpy(), small_beam_scores=small_beam.beam_scores.numpy(),
+            small_rerank_tokens=small_beam.tokens.numpy(), small_rerank_scores=small_beam.scores.numpy(),
+            lm_scores=lm_scores.numpy(),
+            captions=np.array(rerank.captions), greedy_captions=np.array(greedy.captions),
+            meta=np.array([DEC_NEURONS, K, stop_index], dtype=np.int64))
+        print(f'decoder golden [{name}]: beam T={beam.beam_tokens.shape[-1]} rerank[0]={rerank.captions[0]!r} '
+              f'greedy score {greedy.scores[0].item():.4f} beam top {beam.beam_scores[0, 0].item():.4f}')
+
+
+if __name__ == '__main__':
+    main()
