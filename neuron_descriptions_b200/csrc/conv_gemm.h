@@ -104,4 +104,10 @@ struct ConvIO {
 // N-tile width the kernel must be launched with.
 int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n);
 
+// Plain GEMM out[M][ldc] (fp32) = A[M][K] * W[N][K]^T + bias, A given as bf16 hi/lo planes with row pitch
+// a_pitch (elements), W contiguous [N][K]. K must be a multiple of 64. Launch with block_n = 128, EPI_F32.
+int build_gemm_params(ConvGemmParams* p, long long M, int K, int N, const __nv_bfloat16* a_hi,
+                      const __nv_bfloat16* a_lo, long long a_pitch, const __nv_bfloat16* w_hi,
+                      const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split);
+
 }  // namespace milan

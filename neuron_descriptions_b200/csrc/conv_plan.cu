@@ -109,4 +109,40 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
   return 0;
 }
 
+int build_gemm_params(ConvGemmParams* p, long long M, int K, int N, const __nv_bfloat16* a_hi,
+                      const __nv_bfloat16* a_lo, long long a_pitch, const __nv_bfloat16* w_hi,
+                      const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split) {
+  memset(p, 0, sizeof(*p));
+  if (K % kGemmBlockK != 0 || M <= 0) return -2;
+  const int bn_tile = 128;
+  p->cin = K;
+  p->cout = N;
+  p->n_tiles = (N + bn_tile - 1) / bn_tile;
+  p->bias = bias;
+  p->out_f32 = out;
+  p->ldc = ldc;
+  p->box_w = kGemmBlockM; p->box_h = 1; p->box_n = 1;
+  p->tiles_w = static_cast<int>((M + kGemmBlockM - 1) / kGemmBlockM);
+  p->tiles_h = 1; p->tiles_n = 1;
+  p->out_w = static_cast<int>(M); p->out_h = 1; p->out_n = 1;
+  p->num_taps = 1;
+  p->a_box_bytes = kGemmBlockM * kGemmBlockK * 2;
+  const __nv_bfloat16* a_planes[2] = {a_hi, a_lo};
+  const __nv_bfloat16* w_planes[2] = {w_hi, w_lo};
+  const int np = split ? 2 : 1;
+  for (int hl = 0; hl < np; ++hl) {
+    const uint64_t pitch = static_cast<uint64_t>(a_pitch) * 2;
+    int rc = make_tmap_4d(&p->tmap_a[hl][0], a_planes[hl], K, M, 1, 1, pitch, pitch * M, pitch * M, kGemmBlockM, 1, 1);
+    if (rc) return rc;
+    for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];
+    rc = make_tmap_2d(&p->tmap_b[hl], w_planes[hl], K, N, static_cast<uint64_t>(K) * 2, bn_tile);
+    if (rc) return rc;
+  }
+  if (!split) {
+    p->tmap_b[1] = p->tmap_b[0];
+    for (int pl = 0; pl < 4; ++pl) p->tmap_a[1][pl] = p->tmap_a[0][pl];
+  }
+  return 0;
+}
+
 }  // namespace milan

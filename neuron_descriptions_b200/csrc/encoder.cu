@@ -1,0 +1,273 @@
+// Non-GEMM kernels of the pyramid encoder (reference: PyramidConvEncoder.forward, src/milan/encoders.py:286-320).
+//   stem_im2col      : normalise (encoders.py:294-295) + im2col of the 7x7/2 stem -> bf16 hi/lo GEMM operand
+//   mask_pyramid     : bilinear (align_corners=False) mask downsample to the 5 retained resolutions +
+//                      per-image sum-normalisation with the all-zero exception (encoders.py:303-314)
+//   masked_pool      : weighted spatial sum of a retained NHWC map (encoders.py:317)
+//   bn_relu_maxpool  : bn1 + ReLU + 3x3/2 max-pool after the stem (torchvision resnet forward)
+// All are HBM/L2-bound streaming kernels: coalesced along channels, 128-bit where the layout allows.
+#include "encoder.h"
+#include "ptx.cuh"
+
+#include <cstdint>
+
+namespace milan {
+
+namespace {
+
+constexpr int kImg = 224;
+constexpr int kStemOut = 112;
+constexpr int kStemK = 192;  // 7*7*3 = 147 padded to 3 x 64
+
+template <typename T>
+__device__ __forceinline__ float load_pixel(const T* p);
+template <>
+__device__ __forceinline__ float load_pixel<uint8_t>(const uint8_t* p) {
+  // TopImagesDataset: images.float() * fp32(1/255)  (src/milannotations/datasets.py:191-197,
+  // src/deps/netdissect/renormalize.py:118-139)
+  return __fmul_rn(static_cast<float>(*p), 0.00392156862745098f);  // no FMA contraction with the mean subtract
+}
+template <>
+__device__ __forceinline__ float load_pixel<float>(const float* p) {
+  return *p;
+}
+
+// One warp per output pixel; lane l writes k = 6l .. 6l+5 of the 192-wide row.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const T* __restrict__ images, int n_images,
+                                                          __nv_bfloat16* __restrict__ a_hi,
+                                                          __nv_bfloat16* __restrict__ a_lo, float3 mean, float3 stdv,
+                                                          int split) {
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(n_images) * kStemOut * kStemOut;
+  if (warp_global >= total) return;
+  const int ow = warp_global % kStemOut;
+  const int oh = (warp_global / kStemOut) % kStemOut;
+  const int n = warp_global / (kStemOut * kStemOut);
+  const T* img = images + static_cast<long long>(n) * 3 * kImg * kImg;
+  const float m[3] = {mean.x, mean.y, mean.z};
+  const float s[3] = {stdv.x, stdv.y, stdv.z};
+  uint32_t hi[3], lo[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    __nv_bfloat16 h2[2], l2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = lane * 6 + j * 2 + e;
+      float v = 0.0f;
+      if (k < 147) {
+        const int r = k / 21, rem = k - r * 21, ss = rem / 3, c = rem - ss * 3;
+        const int ih = oh * 2 + r - 3, iw = ow * 2 + ss - 3;
+        if (ih >= 0 && ih < kImg && iw >= 0 && iw < kImg) {
+          const float x = load_pixel<T>(img + (static_cast<long long>(c) * kImg + ih) * kImg + iw);
+          v = __fdiv_rn(__fsub_rn(x, m[c]), s[c]);
+        }
+      }
+      split_bf16(v, h2[e], l2[e]);
+    }
+    hi[j] = pack_bf16x2(h2[0], h2[1]);
+    lo[j] = pack_bf16x2(l2[0], l2[1]);
+  }
+  const long long off = warp_global * kStemK + lane * 6;  // 12-byte aligned -> 4-byte stores
+  uint32_t* ph = reinterpret_cast<uint32_t*>(a_hi + off);
+  ph[0] = hi[0]; ph[1] = hi[1]; ph[2] = hi[2];
+  if (split) {
+    uint32_t* pl = reinterpret_cast<uint32_t*>(a_lo + off);
+    pl[0] = lo[0]; pl[1] = lo[1]; pl[2] = lo[2];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float load_mask(const T* p) { return static_cast<float>(*p); }
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.0f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = red[0];
+  const int nw = blockDim.x >> 5;
+  for (int i = 1; i < nw; ++i) t = fmaxf(t, red[i]);
+  return t;
+}
+
+// One CTA per image: all 5 levels.
+template <typename T>
+__global__ void __launch_bounds__(256) mask_pyramid_kernel(const T* __restrict__ masks, float* __restrict__ wts) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const T* m = masks + static_cast<long long>(n) * kImg * kImg;
+  float* out = wts + static_cast<long long>(n) * kMaskPyramidSize;
+  int off = 0;
+  for (int level = 0; level < 5; ++level) {
+    const int S = kStemOut >> level;  // 112, 56, 28, 14, 7
+    const int scale = kImg / S;
+    const int c0 = scale / 2 - 1;
+    float local_sum = 0.0f, local_max = 0.0f;
+    for (int p = threadIdx.x; p < S * S; p += blockDim.x) {
+      const int i = p / S, j = p - i * S;
+      const T* q = m + (i * scale + c0) * kImg + j * scale + c0;
+      // upsample_bilinear2d: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
+      const float top = 0.5f * load_mask(q) + 0.5f * load_mask(q + 1);
+      const float bot = 0.5f * load_mask(q + kImg) + 0.5f * load_mask(q + kImg + 1);
+      const float v = 0.5f * top + 0.5f * bot;
+      out[off + p] = v;
+      local_sum += v;
+      local_max = fmaxf(local_max, fabsf(v));
+    }
+    const float total = block_reduce_sum(local_sum, red);
+    const float amax = block_reduce_max(local_max, red);
+    // valid = ~isclose(ms, 0).all(): |v| <= 1e-8 everywhere -> leave un-normalised (encoders.py:311-314)
+    if (amax > 1e-8f) {
+      for (int p = threadIdx.x; p < S * S; p += blockDim.x) out[off + p] = out[off + p] / total;
+    }
+    off += S * S;
+    __syncthreads();
+  }
+}
+
+// pooled[n][c] = sum_p w[n][p] * (hi + lo)[n][p][c]. CTA = (image, 64-channel group); 8 warps stride pixels,
+// lane = 2 channels (one 4-byte load per plane, 128 B per warp per pixel). Zero-weight pixels are skipped.
+__global__ void __launch_bounds__(256) masked_pool_kernel(const __nv_bfloat16* __restrict__ hi,
+                                                          const __nv_bfloat16* __restrict__ lo,
+                                                          const float* __restrict__ wts, int wts_stride, int P, int C,
+                                                          float* __restrict__ out, int out_stride) {
+  __shared__ float2 acc_s[8][32];
+  const int n = blockIdx.x;
+  const int cg = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* w = wts + static_cast<long long>(n) * wts_stride;
+  const long long base = static_cast<long long>(n) * P * C + cg * 64 + lane * 2;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int p = warp; p < P; p += 8) {
+    const float wp = __ldg(w + p);
+    if (wp == 0.0f) continue;
+    const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + base + static_cast<long long>(p) * C));
+    float x0 = bf16_lo_to_f32(h), x1 = bf16_hi_to_f32(h);
+    if (lo != nullptr) {
+      const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + base + static_cast<long long>(p) * C));
+      x0 += bf16_lo_to_f32(l);
+      x1 += bf16_hi_to_f32(l);
+    }
+    acc.x = fmaf(wp, x0, acc.x);
+    acc.y = fmaf(wp, x1, acc.y);
+  }
+  acc_s[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float2 t = acc_s[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { t.x += acc_s[i][lane].x; t.y += acc_s[i][lane].y; }
+    float* o = out + static_cast<long long>(n) * out_stride + cg * 64 + lane * 2;
+    o[0] = t.x;
+    o[1] = t.y;
+  }
+}
+
+// y[n][oh][ow][c] = max_{3x3, stride 2, pad 1} relu(alpha[c] * x + beta[c]);  C = 64, thread = 2 channels.
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ x_hi,
+                                                              const __nv_bfloat16* __restrict__ x_lo,
+                                                              const float* __restrict__ alpha,
+                                                              const float* __restrict__ beta, int n_images,
+                                                              __nv_bfloat16* __restrict__ y_hi,
+                                                              __nv_bfloat16* __restrict__ y_lo) {
+  constexpr int C = 64, IN = 112, OUT = 56;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_images) * OUT * OUT * (C / 2);
+  if (idx >= total) return;
+  const int c2 = idx % (C / 2);
+  const long long pix = idx / (C / 2);
+  const int ow = pix % OUT;
+  const int oh = (pix / OUT) % OUT;
+  const int n = pix / (OUT * OUT);
+  const float a0 = alpha[2 * c2], a1 = alpha[2 * c2 + 1], b0 = beta[2 * c2], b1 = beta[2 * c2 + 1];
+  float m0 = 0.0f, m1 = 0.0f;  // relu output >= 0 and every window holds >= 1 valid pixel
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * 2 + r - 1;
+    if (ih < 0 || ih >= IN) continue;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * 2 + s - 1;
+      if (iw < 0 || iw >= IN) continue;
+      const long long off = ((static_cast<long long>(n) * IN + ih) * IN + iw) * C + 2 * c2;
+      const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(x_hi + off));
+      float v0 = bf16_lo_to_f32(h), v1 = bf16_hi_to_f32(h);
+      if (x_lo != nullptr) {
+        const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(x_lo + off));
+        v0 += bf16_lo_to_f32(l);
+        v1 += bf16_hi_to_f32(l);
+      }
+      m0 = fmaxf(m0, fmaf(v0, a0, b0));
+      m1 = fmaxf(m1, fmaf(v1, a1, b1));
+    }
+  }
+  __nv_bfloat16 h0, l0, h1, l1;
+  split_bf16(m0, h0, l0);
+  split_bf16(m1, h1, l1);
+  const long long o = pix * C + 2 * c2;
+  *reinterpret_cast<uint32_t*>(y_hi + o) = pack_bf16x2(h0, h1);
+  if (y_lo != nullptr) *reinterpret_cast<uint32_t*>(y_lo + o) = pack_bf16x2(l0, l1);
+}
+
+}  // namespace
+
+int launch_stem_im2col(const void* images, int dtype, int n_images, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                       const float mean[3], const float stdv[3], int split, cudaStream_t stream) {
+  const long long warps = static_cast<long long>(n_images) * kStemOut * kStemOut;
+  const int threads = 256;
+  const long long blocks = (warps * 32 + threads - 1) / threads;
+  const float3 m = make_float3(mean[0], mean[1], mean[2]);
+  const float3 s = make_float3(stdv[0], stdv[1], stdv[2]);
+  if (dtype == 0) {
+    stem_im2col_kernel<uint8_t><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        static_cast<const uint8_t*>(images), n_images, a_hi, a_lo, m, s, split);
+  } else {
+    stem_im2col_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        static_cast<const float*>(images), n_images, a_hi, a_lo, m, s, split);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_mask_pyramid(const void* masks, int dtype, int n_images, float* wts, cudaStream_t stream) {
+  if (dtype == 0) {
+    mask_pyramid_kernel<uint8_t><<<n_images, 256, 0, stream>>>(static_cast<const uint8_t*>(masks), wts);
+  } else {
+    mask_pyramid_kernel<float><<<n_images, 256, 0, stream>>>(static_cast<const float*>(masks), wts);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_masked_pool(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const float* wts, int wts_stride,
+                       int n_images, int P, int C, float* out, int out_stride, cudaStream_t stream) {
+  dim3 grid(n_images, C / 64);
+  masked_pool_kernel<<<grid, 256, 0, stream>>>(hi, lo, wts, wts_stride, P, C, out, out_stride);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_bn_relu_maxpool(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const float* alpha,
+                           const float* beta, int n_images, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
+                           cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_images) * 56 * 56 * 32;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  bn_relu_maxpool_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x_hi, x_lo, alpha, beta, n_images,
+                                                                               y_hi, y_lo);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace milan

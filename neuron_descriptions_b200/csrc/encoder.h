@@ -1,0 +1,22 @@
+// Launchers for the non-GEMM encoder kernels (encoder.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace milan {
+
+// Per-image size of the 5-level mask pyramid: 112^2 + 56^2 + 28^2 + 14^2 + 7^2.
+constexpr int kMaskPyramidSize = 12544 + 3136 + 784 + 196 + 49;
+constexpr int kMaskLevelOffset[5] = {0, 12544, 15680, 16464, 16660};
+
+// dtype: 0 = uint8, 1 = float32. images NCHW (n,3,224,224); masks (n,1,224,224).
+int launch_stem_im2col(const void* images, int dtype, int n_images, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                       const float mean[3], const float stdv[3], int split, cudaStream_t stream);
+int launch_mask_pyramid(const void* masks, int dtype, int n_images, float* wts, cudaStream_t stream);
+int launch_masked_pool(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const float* wts, int wts_stride,
+                       int n_images, int P, int C, float* out, int out_stride, cudaStream_t stream);
+int launch_bn_relu_maxpool(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const float* alpha,
+                           const float* beta, int n_images, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
+                           cudaStream_t stream);
+
+}  // namespace milan

@@ -1,0 +1,441 @@
+"""Facade of `src/milan/decoders.py`: the reference's `Decoder` surface (constructor, `forward`, `encode`,
+`init_state`, `step`, `predict`, checkpoint `load`/`save`) driving the CUDA engine through the C ABI.
+
+Same names, argument meaning and error behaviour as the reference; tensors only cross at the boundary.
+There is no CPU path: a `Decoder` must be moved to a CUDA device (`.to('cuda')`) before it can compute.
+"""
+import collections
+from typing import Any, Dict, Mapping, NamedTuple, Optional, Sequence, Tuple, Union
+
+import torch
+
+from neuron_descriptions_b200.engine import Engine
+from neuron_descriptions_b200.milan import encoders, lang, lms
+
+StrSequence = Sequence[str]
+
+
+class DecoderState(NamedTuple):
+    """`src/milan/decoders.py:84-99`."""
+    h: torch.Tensor
+    c: torch.Tensor
+    h_lm: Optional[torch.Tensor]
+    c_lm: Optional[torch.Tensor]
+
+
+class DecoderStep(NamedTuple):
+    """`src/milan/decoders.py:102-117`."""
+    predictions: torch.Tensor
+    attentions: torch.Tensor
+    state: DecoderState
+
+
+class DecoderOutput(NamedTuple):
+    """`src/milan/decoders.py:120-150`."""
+    captions: StrSequence
+    scores: torch.Tensor
+    tokens: torch.Tensor
+    predictions: Optional[torch.Tensor]
+    attentions: Optional[torch.Tensor]
+    beam_captions: Optional[Sequence[StrSequence]]
+    beam_scores: Optional[torch.Tensor]
+    beam_tokens: Optional[torch.Tensor]
+
+
+class _LazyBeamCaptions(collections.abc.Sequence):
+    """`beam_captions` (`decoders.py:486-487`) detokenised on first use: 50 strings per neuron are rarely read."""
+
+    def __init__(self, indexer, tokens: torch.Tensor):
+        self._indexer, self._tokens, self._value = indexer, tokens, None
+
+    def _materialise(self):
+        if self._value is None:
+            self._value = tuple(map(self._indexer.reconstruct, self._tokens.tolist()))
+        return self._value
+
+    def __len__(self):
+        return len(self._tokens)
+
+    def __getitem__(self, index):
+        return self._materialise()[index]
+
+
+Strategy = Union[torch.Tensor, str]
+STRATEGY_GREEDY = 'greedy'
+STRATEGY_SAMPLE = 'sample'
+STRATEGY_BEAM = 'beam'
+STRATEGY_RERANK = 'rerank'
+STRATEGIES = (STRATEGY_GREEDY, STRATEGY_SAMPLE, STRATEGY_BEAM, STRATEGY_RERANK)
+
+
+class Decoder:
+    """`src/milan/decoders.py:224-1109` (inference surface)."""
+
+    def __init__(self,
+                 indexer: lang.Indexer,
+                 encoder: encoders.Encoder,
+                 lm: Optional[lms.LanguageModel] = None,
+                 embedding_size: int = 128,
+                 hidden_size: int = 512,
+                 attention_hidden_size: Optional[int] = None,
+                 dropout: float = .5,
+                 length: int = 15,
+                 strategy: Optional[str] = None,
+                 temperature: float = .2,
+                 beam_size: int = 50,
+                 precision: str = 'split',
+                 max_neurons: int = 32):
+        if lm is not None:
+            my_vocab, lm_vocab = indexer.vocab.unique, lm.indexer.vocab.unique
+            if my_vocab != lm_vocab:
+                raise ValueError('lm and decoder have different vocabs;'
+                                 f'lm missing {my_vocab - lm_vocab} and decoder missing {lm_vocab - my_vocab}')
+        if strategy is None:
+            strategy = STRATEGY_BEAM if lm is None else STRATEGY_RERANK
+        self.indexer = indexer
+        self.encoder = encoder
+        self.lm = lm
+        self.embedding_size = embedding_size
+        self.hidden_size = hidden_size
+        self.attention_hidden_size = attention_hidden_size
+        self.dropout = dropout
+        self.length = length
+        self.strategy = strategy
+        self.temperature = temperature
+        self.beam_size = beam_size
+        self.training = False
+        self.precision = precision
+        self.max_neurons = max_neurons
+        self._state_dict: Dict[str, torch.Tensor] = {}
+        self._engine: Optional[Engine] = None
+
+    # ------------------------------------------------------------------ module-ish plumbing
+    @property
+    def feature_size(self) -> int:
+        return self.encoder.feature_shape[-1]
+
+    @property
+    def vocab_size(self) -> int:
+        return len(self.indexer)
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            raise RuntimeError('this Decoder is not on a CUDA device: call .to("cuda") first '
+                               '(milan_b200 is CUDA-only, there is no CPU fallback)')
+        return self._engine
+
+    def state_dict(self) -> Mapping[str, torch.Tensor]:
+        return collections.OrderedDict(self._state_dict)
+
+    def load_state_dict(self, state_dict: Mapping[str, torch.Tensor], strict: bool = False):
+        self._state_dict = {k: v.detach().cpu() for k, v in state_dict.items()}
+        if self._engine is not None:
+            device = self._engine.device
+            self._engine.close()
+            self._engine = None
+            self.to(device)
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError('milan_b200 is an inference engine; training (Decoder.fit) is out of scope')
+        self.training = False
+        return self
+
+    def to(self, device):
+        """Create (or move) the engine. Mirrors `nn.Module.to` for the `predict(device=...)` call path."""
+        if device is None:
+            return self
+        device = torch.device(device)
+        if device.type != 'cuda':
+            if self._engine is not None:
+                self._engine.close()
+                self._engine = None
+            return self
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        if self._engine is not None and self._engine.device.index == index:
+            return self
+        if not self._state_dict:
+            raise RuntimeError('Decoder has no weights: load a checkpoint or call load_state_dict first')
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = Engine(self._state_dict, vocab_size=self.vocab_size, device=torch.device('cuda', index),
+                              embedding_size=self.embedding_size, hidden_size=self.hidden_size,
+                              attention_size=self.attention_hidden_size, feature_size=self.feature_size,
+                              lm_embedding_size=self.lm.embedding_size if self.lm else 128,
+                              lm_hidden_size=self.lm.hidden_size if self.lm else 512, precision=self.precision,
+                              max_neurons=self.max_neurons, max_beam=max(50, self.beam_size),
+                              max_length=max(15, self.length))
+        if hasattr(self.encoder, 'bind'):
+            self.encoder.bind(self._engine)
+        if self.lm is not None:
+            self.lm.bind(self._engine)
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device('cuda', device) if device is not None else 'cuda')
+
+    def __call__(self, *args, **kwargs) -> DecoderOutput:
+        return self.forward(*args, **kwargs)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self,
+                images_or_features: torch.Tensor,
+                masks: Optional[torch.Tensor] = None,
+                encode: Optional[bool] = None,
+                length: Optional[int] = None,
+                strategy: Optional[Strategy] = None,
+                mi: Optional[bool] = None,
+                temperature: Optional[float] = None,
+                beam_size: Optional[int] = None,
+                group_size: Optional[int] = None) -> DecoderOutput:
+        """`Decoder.forward`, `src/milan/decoders.py:335-523`.
+
+        `group_size` is an extension: when several reference batches are decoded in one call, the reference's
+        batch-level early exit (and the LM mask that depends on it) is reproduced per group of that many rows.
+        """
+        if encode is None:
+            encode = masks is not None
+        if length is None:
+            length = self.length
+        if strategy is None:
+            strategy = self.strategy
+        if mi is None:
+            mi = self.lm is not None and not self.training
+            mi &= not isinstance(strategy, str) or strategy != STRATEGY_RERANK
+        if temperature is None:
+            temperature = self.temperature
+        if beam_size is None:
+            beam_size = self.beam_size
+        batch_size = len(images_or_features)
+
+        if mi and isinstance(strategy, str) and strategy == STRATEGY_RERANK:
+            raise ValueError('cannot set `mi=` decoding when reranking')
+        if (mi or (isinstance(strategy, str) and strategy == STRATEGY_RERANK)) and self.lm is None:
+            raise ValueError('cannot use MI/rerank decoding without an LM')
+        if (mi or (isinstance(strategy, str) and strategy == STRATEGY_RERANK)) and self.training:
+            raise ValueError('cannot use MI/rerank decoding while training')
+        if isinstance(strategy, str) and strategy not in STRATEGIES:
+            raise ValueError(f'unknown strategy: {strategy}')
+        if isinstance(strategy, torch.Tensor):
+            if strategy.dim() != 2:
+                raise ValueError(f'strategy must be 2D, got {strategy.dim()}')
+            if strategy.shape[-1] != length:
+                raise ValueError(f'strategy must have length {length}, got {strategy.shape[-1]}')
+
+        engine = self.engine
+        features = self.encode(images_or_features, masks=masks) if encode else images_or_features
+        features = features.to(engine.device, torch.float32)
+
+        predictions = attentions = beam_captions = beam_scores = beam_tokens = None
+        if isinstance(strategy, torch.Tensor) or strategy == STRATEGY_GREEDY:
+            forced = strategy if isinstance(strategy, torch.Tensor) else None
+            tokens, scores, predictions, attentions = engine.decode_greedy(features, length, mi, temperature, forced)
+        elif strategy == STRATEGY_SAMPLE:
+            tokens, scores, predictions, attentions = self._sample(features, length, mi, temperature)
+        else:
+            if mi:
+                raise NotImplementedError("MI beam decoding (strategy='beam' with an LM and mi=True) is a SURVEY 8(f) "
+                                          "'next' row; pass mi=False or use strategy='rerank'")
+            rerank = strategy == STRATEGY_RERANK
+            beam_tokens, beam_scores, steps, tokens, scores, _ = engine.decode_beam(
+                features, length, beam_size, rerank, temperature, group_size=group_size or batch_size)
+            if group_size is None or group_size >= batch_size:
+                # the reference returns only the T <= length columns produced before its early exit
+                T = int(steps[0].item())
+                beam_tokens, tokens = beam_tokens[..., :T], tokens[..., :T]
+            beam_captions = _LazyBeamCaptions(self.indexer, beam_tokens)
+        return DecoderOutput(
+            captions=self.indexer.reconstruct(tokens.tolist()),
+            tokens=tokens,
+            scores=scores,
+            predictions=predictions,
+            attentions=attentions,
+            beam_captions=beam_captions,
+            beam_scores=beam_scores,
+            beam_tokens=beam_tokens,
+        )
+
+    def _sample(self, features, length, mi, temperature):
+        """strategy='sample' (`decoders.py:448-453`): per-step multinomial draw over the CUDA step's output."""
+        batch_size = len(features)
+        state = self.init_state(features, lm=mi)
+        currents = torch.full((batch_size,), self.indexer.start_index, dtype=torch.long, device=features.device)
+        tokens = currents.new_zeros(batch_size, length)
+        scores = features.new_zeros(batch_size)
+        predictions = features.new_zeros(batch_size, length, self.vocab_size)
+        attentions = features.new_zeros(batch_size, length, features.shape[1])
+        for time in range(length):
+            outputs = self.step(features, currents, state, temperature=temperature)
+            currents = torch.multinomial(torch.exp(outputs.predictions), 1).view(batch_size)
+            predictions[:, time] = outputs.predictions
+            attentions[:, time] = outputs.attentions
+            tokens[:, time] = currents
+            state = outputs.state
+            scores += outputs.predictions.gather(1, currents.view(-1, 1)).view(batch_size)
+        return tokens, scores, predictions, attentions
+
+    def encode(self, images: torch.Tensor, masks: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`Decoder.encode`, `src/milan/decoders.py:525-546`."""
+        batch_size = len(images)
+        images = images.view(-1, *images.shape[-3:])
+        if masks is not None:
+            masks = masks.view(-1, *masks.shape[-3:])
+        features = self.encoder(images, masks=masks)
+        return features.view(batch_size, -1, self.feature_size)
+
+    def init_state(self, features: torch.Tensor, lm: bool = True) -> DecoderState:
+        """`Decoder.init_state`, `src/milan/decoders.py:548-574`."""
+        h, c = self.engine.init_state(features)
+        h_lm = c_lm = None
+        if self.lm is not None and lm:
+            h_lm = h.new_zeros(self.lm.layers, len(features), self.lm.hidden_size)
+            c_lm = c.new_zeros(self.lm.layers, len(features), self.lm.hidden_size)
+        return DecoderState(h, c, h_lm, c_lm)
+
+    def step(self, features: torch.Tensor, tokens: torch.Tensor, state: DecoderState,
+             temperature: Optional[float] = None) -> DecoderStep:
+        """`Decoder.step`, `src/milan/decoders.py:576-634`."""
+        h, c, h_lm, c_lm = state
+        if (h_lm is None) != (c_lm is None):
+            raise ValueError('state must have both h_lm and c_lm or neither')
+        if h_lm is not None and self.lm is None:
+            raise ValueError('state has h_lm or c_lm, but decoder has no lm')
+        temperature = self.temperature if temperature is None else temperature
+        predictions, attentions, h, c, h_lm, c_lm = self.engine.step(features, tokens, h, c, h_lm, c_lm, temperature)
+        return DecoderStep(predictions=predictions, attentions=attentions,
+                           state=DecoderState(h=h, c=c, h_lm=h_lm, c_lm=c_lm))
+
+    # ------------------------------------------------------------------ predict
+    def predict(self,
+                dataset,
+                mask: bool = True,
+                image_index: int = 2,
+                mask_index: int = 3,
+                batch_size: int = 16,
+                features=None,
+                num_workers: int = 0,
+                device=None,
+                display_progress_as: Optional[str] = 'predict captions',
+                **kwargs: Any) -> StrSequence:
+        """`Decoder.predict`, `src/milan/decoders.py:809-871`.
+
+        Several reference batches are fused into one engine call (`group_size=batch_size` keeps the reference's
+        per-batch early-exit semantics); datasets exposing `batch_u8(lo, hi)` are fed as uint8 (4x less H2D).
+        """
+        del num_workers
+        if device is not None:
+            self.to(device)
+        engine = self.engine
+        source = dataset if features is None else features
+        total = len(source)
+        chunk = max(batch_size, (engine.cfg.max_neurons // batch_size) * batch_size)
+        chunk = min(chunk, engine.cfg.max_neurons) if engine.cfg.max_neurons < batch_size else chunk
+        ranges = range(0, total, chunk)
+        if display_progress_as is not None:
+            try:
+                from tqdm.auto import tqdm
+                ranges = tqdm(ranges, desc=display_progress_as)
+            except ImportError:
+                pass
+        captions = []
+        for lo in ranges:
+            hi = min(lo + chunk, total)
+            group = batch_size if chunk > batch_size else None
+            with torch.no_grad():
+                if features is not None:
+                    feats = torch.stack([torch.as_tensor(features[i][0]) for i in range(lo, hi)])
+                    output = self(feats, group_size=group, **kwargs)
+                else:
+                    if hasattr(dataset, 'batch_u8'):
+                        images, masks = dataset.batch_u8(lo, hi)
+                    else:
+                        samples = [dataset[i] for i in range(lo, hi)]
+                        images = torch.stack([torch.as_tensor(s[image_index]) for s in samples])
+                        masks = torch.stack([torch.as_tensor(s[mask_index]) for s in samples])
+                    images = images.to(engine.device, non_blocking=True)
+                    masks = masks.to(engine.device, non_blocking=True) if mask else None
+                    if masks is None:
+                        output = self(images, encode=True, group_size=group, **kwargs)
+                    else:
+                        output = self(images, masks, group_size=group, **kwargs)
+            captions += output.captions
+        return tuple(captions)
+
+    def fit(self, *args, **kwargs):
+        raise NotImplementedError('training (src/milan/decoders.py:873-1070) is out of scope for this engine')
+
+    # ------------------------------------------------------------------ checkpoints
+    def properties(self) -> Mapping[str, Any]:
+        """`src/milan/decoders.py:1072-1086`."""
+        return {
+            'indexer': self.indexer, 'encoder': self.encoder, 'lm': self.lm,
+            'embedding_size': self.embedding_size, 'hidden_size': self.hidden_size,
+            'attention_hidden_size': self.attention_hidden_size, 'dropout': self.dropout, 'length': self.length,
+            'strategy': self.strategy, 'temperature': self.temperature, 'beam_size': self.beam_size,
+        }
+
+    def serialize(self) -> Mapping[str, Any]:
+        """Reference payload layout (`src/utils/serialize.py:80-118,188-203`), tokenizer omitted."""
+        def indexer_payload(indexer):
+            props = {'vocab': {'properties': {'tokens': tuple(indexer.vocab.tokens)}, 'children': {}},
+                     'tokenize': None, 'start': indexer.start, 'stop': indexer.stop, 'pad': indexer.pad,
+                     'unk': indexer.unk, 'length': indexer.length}
+            return {'properties': props, 'children': {}}
+
+        props = dict(self.properties())
+        props['indexer'] = indexer_payload(self.indexer)
+        props['encoder'] = {'properties': dict(self.encoder.properties()), 'children': {}}
+        if self.lm is not None:
+            lm_props = dict(self.lm.properties())
+            lm_props['indexer'] = indexer_payload(self.lm.indexer)
+            props['lm'] = {'properties': lm_props, 'children': {}}
+        return {'properties': props, 'children': {'encoder': encoders.key(self.encoder)},
+                'state_dict': self.state_dict()}
+
+    def save(self, file, **kwargs: Any) -> None:
+        torch.save(self.serialize(), file, **kwargs)
+
+    @classmethod
+    def deserialize(cls, payload: Mapping[str, Any], **overrides: Any) -> 'Decoder':
+        """Rebuild from a reference checkpoint payload (`serialize.py:121-163,221-253`; `decoders.py:1095-1109`)
+        without spaCy or a network: the tokenizer is dropped and `pretrained=False` is implied."""
+        props = dict(payload['properties'])
+        children = dict(payload.get('children', {}))
+        encoder_key = children.get('encoder')
+        if encoder_key is None:
+            raise ValueError('serialized decoder missing encoder')
+        indexer = lang.indexer_from_payload(props['indexer'])
+        encoder_props = dict(props['encoder']['properties'])
+        encoder = encoders.parse(encoder_key)(**encoder_props)
+        lm = None
+        if props.get('lm') is not None:
+            lm_props = dict(props['lm']['properties'])
+            lm_indexer = lang.indexer_from_payload(lm_props.pop('indexer'))
+            lm = lms.LanguageModel(lm_indexer, **lm_props)
+        kwargs = {key: props[key] for key in ('embedding_size', 'hidden_size', 'attention_hidden_size', 'dropout',
+                                              'length', 'strategy', 'temperature', 'beam_size') if key in props}
+        kwargs.update(overrides)
+        decoder = cls(indexer, encoder, lm=lm, **kwargs)
+        state_dict = payload.get('state_dict')
+        if state_dict is not None:
+            decoder.load_state_dict(state_dict, strict=False)
+        return decoder.eval()
+
+    @classmethod
+    def load(cls, file, **kwargs: Any) -> 'Decoder':
+        """`SerializableModule.load`, `src/utils/serialize.py:255-269`; kwargs go to `torch.load`."""
+        overrides = {key: kwargs.pop(key) for key in ('precision', 'max_neurons') if key in kwargs}
+        kwargs.setdefault('map_location', 'cpu')
+        kwargs.setdefault('weights_only', False)
+        payload = torch.load(file, **kwargs)
+        return cls.deserialize(payload, **overrides)
+
+
+def decoder(*args, **kwargs):
+    raise NotImplementedError('Decoder training factory (src/milan/decoders.py:1214) is out of scope')

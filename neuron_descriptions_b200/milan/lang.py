@@ -1,0 +1,192 @@
+"""Host-side vocabulary / detokenisation mirror of `src/utils/lang.py` (only what decoding needs).
+
+`Indexer.reconstruct` / `unindex` follow `src/utils/lang.py:573-612,678-730`; special ids follow `:242-260`.
+Tokenisation (`Indexer.__call__`, needs spaCy) is out of scope for the describe-neurons path:
+an `Indexer` built with `tokenize=None` raises if asked to index text.
+"""
+import collections
+import dataclasses
+import functools
+from typing import Any, Callable, Mapping, Optional, Sequence, Tuple, Union
+
+START_TOKEN = '<start>'
+STOP_TOKEN = '<stop>'
+PAD_TOKEN = '<pad>'
+UNK_TOKEN = '<unk>'
+
+
+@dataclasses.dataclass(frozen=True)
+class Vocab:
+    """`src/utils/lang.py:93-178`."""
+
+    tokens: Tuple[str, ...]
+
+    def __post_init__(self):
+        object.__setattr__(self, 'tokens', tuple(self.tokens))
+
+    @functools.cached_property
+    def ids(self) -> Mapping[str, int]:
+        return {token: index for index, token in enumerate(self.tokens)}
+
+    @functools.cached_property
+    def unique(self):
+        return frozenset(self.ids)
+
+    def __getitem__(self, token):
+        if isinstance(token, (int, slice)):
+            return self.tokens[token]
+        return self.ids[token]
+
+    def __len__(self) -> int:
+        return len(self.tokens)
+
+    def __contains__(self, token) -> bool:
+        if isinstance(token, int):
+            return 0 <= token < len(self)
+        return token in self.unique
+
+    def properties(self):
+        return {'tokens': self.tokens}
+
+
+@dataclasses.dataclass(frozen=True)
+class Indexer:
+    """`src/utils/lang.py:230-747`: ids <-> text with the four special tokens after the vocabulary."""
+
+    vocab: Vocab
+    tokenize: Optional[Callable[..., Any]] = None
+    start: bool = False
+    stop: bool = False
+    pad: bool = False
+    unk: bool = False
+    length: Optional[int] = None
+
+    @functools.cached_property
+    def start_index(self) -> int:
+        return len(self.vocab)
+
+    @functools.cached_property
+    def stop_index(self) -> int:
+        return len(self.vocab) + 1
+
+    @functools.cached_property
+    def pad_index(self) -> int:
+        return len(self.vocab) + 2
+
+    @functools.cached_property
+    def unk_index(self) -> int:
+        return len(self.vocab) + 3
+
+    @functools.cached_property
+    def specials(self) -> Mapping[int, str]:
+        return collections.OrderedDict((
+            (self.start_index, START_TOKEN),
+            (self.stop_index, STOP_TOKEN),
+            (self.pad_index, PAD_TOKEN),
+            (self.unk_index, UNK_TOKEN),
+        ))
+
+    @functools.cached_property
+    def tokens(self) -> Tuple[str, ...]:
+        return tuple(list(self.vocab.tokens) + list(self.specials.values()))
+
+    @functools.cached_property
+    def ids(self) -> Mapping[str, int]:
+        ids = dict(self.vocab.ids)
+        for index, token in self.specials.items():
+            ids[token] = index
+        return ids
+
+    @functools.cached_property
+    def unique(self):
+        return frozenset(self.ids)
+
+    def __getitem__(self, token):
+        if isinstance(token, (int, slice)):
+            return self.tokens[token]
+        return self.ids[token]
+
+    def __len__(self) -> int:
+        return len(self.vocab) + len(self.specials)
+
+    def __contains__(self, token) -> bool:
+        if isinstance(token, int):
+            return 0 <= token < len(self)
+        return token in self.unique
+
+    def __call__(self, *args, **kwargs):
+        raise NotImplementedError(
+            'text -> ids indexing needs the spaCy tokenizer of the reference (src/utils/lang.py:460-515); '
+            'it is outside the describe-neurons hot path this engine covers')
+
+    def unindex(self, indexed, specials: bool = True, start: bool = True, stop: bool = True, pad: bool = True,
+                unk: bool = True):
+        """`src/utils/lang.py:573-612`."""
+        if not indexed:
+            return ()
+        singleton = isinstance(indexed[0], int)
+        unindexed = []
+        for indices in [indexed] if singleton else indexed:
+            tokens = []
+            for index in indices:
+                if index < len(self.vocab):
+                    tokens.append(self.vocab[index])
+                    continue
+                for (special, token), keep in zip(self.specials.items(), (start, stop, pad, unk)):
+                    if index == special:
+                        if specials and keep:
+                            tokens.append(token)
+                        break
+                else:
+                    raise ValueError(f'unknown index: {index}')
+            unindexed.append(tuple(tokens))
+        return unindexed[0] if singleton else tuple(unindexed)
+
+    def reconstruct(self, inputs: Union[Sequence[int], Sequence[Sequence[int]], Sequence[str],
+                                        Sequence[Sequence[str]]]):
+        """`src/utils/lang.py:678-730`."""
+        if not inputs:
+            raise ValueError('must provide at least one seq')
+        for index, item in enumerate(inputs):
+            if not isinstance(item, (int, str)) and not item:
+                raise ValueError(f'input seq {index} is empty')
+        if isinstance(inputs[0], str):
+            tokenized = [inputs]
+        elif isinstance(inputs[0], int):
+            tokenized = [self.unindex(inputs)]
+        elif isinstance(inputs[0][0], str):
+            tokenized = inputs
+        else:
+            assert isinstance(inputs[0][0], int), 'unknown input type'
+            tokenized = self.unindex(inputs)
+        special_tokens = set(self.specials.values())
+        texts = []
+        for tokens in tokenized:
+            tokens = list(tokens)
+            if STOP_TOKEN in tokens:
+                tokens = tokens[:tokens.index(STOP_TOKEN)]
+            text = ' '.join(token for token in tokens if token not in special_tokens)
+            for token in ('.', ',', ';', ':'):
+                text = text.replace(' ' + token, token)
+            for token in ('-',):
+                text = text.replace(' %s' % token, token)
+                text = text.replace('%s ' % token, token)
+            text = '. '.join(sentence.strip().capitalize() for sentence in text.split('.')).strip()
+            texts.append(text)
+        return texts[0] if isinstance(inputs[0], (str, int)) else tuple(texts)
+
+    def properties(self):
+        return {'vocab': self.vocab, 'tokenize': self.tokenize, 'start': self.start, 'stop': self.stop,
+                'pad': self.pad, 'unk': self.unk, 'length': self.length}
+
+
+def indexer_from_payload(payload: Mapping[str, Any]) -> Indexer:
+    """Rebuild an `Indexer` from a reference `Serializable` payload (`src/utils/serialize.py:121-163`) without
+    spaCy: the tokenizer child is kept as its raw payload (decoding never tokenises)."""
+    props = dict(payload['properties'])
+    vocab = props['vocab']
+    if isinstance(vocab, Mapping):
+        vocab = Vocab(tuple(vocab['properties']['tokens']))
+    return Indexer(vocab=vocab, tokenize=None, start=bool(props.get('start', False)),
+                   stop=bool(props.get('stop', False)), pad=bool(props.get('pad', False)),
+                   unk=bool(props.get('unk', False)), length=props.get('length'))

@@ -1,0 +1,93 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/milan_b200.h declares; the host-side
+logic that needs no GPU behaves like the reference."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    header = open(os.path.join(ROOT, 'include', 'milan_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    return sorted(set(re.findall(r'\b(milan_[a-z_0-9]+)\s*\(', header)))
+
+
+def test_library_exports_every_declared_symbol():
+    from neuron_descriptions_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/milan_b200.h but not exported'
+        assert name in _lib.SIGNATURES, f'{name} has no ctypes signature'
+    assert lib.milan_version().startswith(b'milan_b200')
+
+
+def test_config_struct_matches_header():
+    from neuron_descriptions_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'milan_b200.h')).read()
+    body = header[header.index('typedef struct MilanConfig {'):header.index('} MilanConfig;')]
+    fields = re.findall(r'int32_t\s+([a-z_]+);', body)
+    assert fields == [name for name, _ in _lib.MilanConfig._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the loud failure without a GPU')
+def test_product_path_fails_loudly_without_gpu():
+    from neuron_descriptions_b200 import synthetic
+    from neuron_descriptions_b200.engine import Engine
+    sd = synthetic.synthetic_state_dict(seed=0, with_encoder=False)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Engine(sd, vocab_size=5004, device='cuda:0')
+
+
+def test_facade_host_logic():
+    from neuron_descriptions_b200 import milan, synthetic
+    from neuron_descriptions_b200.milan import lang
+    vocab = synthetic.synthetic_vocab(50)
+    indexer = lang.Indexer(lang.Vocab(vocab), start=True, stop=True, pad=True, unk=True)
+    assert (indexer.start_index, indexer.stop_index, indexer.pad_index, indexer.unk_index) == (50, 51, 52, 53)
+    assert len(indexer) == 54
+    assert indexer.reconstruct([10, 1, 11, 0, 14, 2, 10, 51, 11]) == 'Dog, cat. Top-dog'
+    assert indexer.reconstruct([[10], [51, 10]]) == ('Dog', '')
+    with pytest.raises(ValueError):
+        indexer.reconstruct([])
+    with pytest.raises(ValueError):
+        indexer.unindex([999])
+    with pytest.raises(ValueError, match='encoder not supported'):
+        milan.PyramidConvEncoder('vgg16')
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer))
+    assert decoder.strategy == 'rerank' and decoder.vocab_size == 54 and decoder.feature_size == 3904
+    assert milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101')).strategy == 'beam'
+    with pytest.raises(RuntimeError, match='CUDA'):
+        decoder(torch.zeros(1, 15, 3904))
+    with pytest.raises(KeyError):
+        milan.pretrained('not-a-model')
+    with pytest.raises(FileNotFoundError):
+        milan.pretrained('base', path='/nonexistent/base.pth')
+
+
+def test_checkpoint_round_trip(tmp_path):
+    """Reference payload layout {'properties','children','state_dict'} (src/utils/serialize.py:188-253)."""
+    from neuron_descriptions_b200 import milan, synthetic
+    from neuron_descriptions_b200.milan import lang
+    vocab = synthetic.synthetic_vocab(30)
+    indexer = lang.Indexer(lang.Vocab(vocab), start=True, stop=True, pad=True, unk=True)
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer), beam_size=7, temperature=.3)
+    sd = synthetic.synthetic_state_dict(seed=0, vocab_size=30, with_encoder=False)
+    decoder.load_state_dict(sd)
+    path = tmp_path / 'milan.pth'
+    decoder.save(path)
+    payload = torch.load(path, weights_only=False)
+    assert set(payload) == {'properties', 'children', 'state_dict'}
+    assert payload['children'] == {'encoder': 'PyramidConvEncoder'}
+    loaded = milan.Decoder.load(path)
+    assert loaded.beam_size == 7 and loaded.temperature == .3 and loaded.lm is not None
+    assert loaded.indexer.vocab.tokens == tuple(vocab)
+    assert set(loaded.state_dict()) == set(sd)
+    via_hub = milan.pretrained('base', path=path)
+    assert via_hub.vocab_size == 34

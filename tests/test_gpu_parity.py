@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference-generated goldens.
+
+Tolerances (north_star): identical greedy token ids; beam / greedy log-prob sums within 1e-3 (fp32);
+encoder features within 1e-3 relative to the feature scale (the convs run as bf16 hi/lo split products with
+fp32 accumulation; measured error is ~1e-5).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neuron_descriptions_b200 import synthetic
+from oracle import milan_oracle as O
+from oracle.make_golden import VARIANTS, synthetic_features
+
+pytestmark = pytest.mark.gpu
+
+VOCAB = synthetic.synthetic_vocab(5000)
+V = len(VOCAB) + 4
+STOP = len(VOCAB) + 1
+LOGP_TOL = 1e-3
+
+
+def _engine(sd, **kwargs):
+    from neuron_descriptions_b200.engine import Engine
+    return Engine(sd, vocab_size=V, device='cuda:0', **kwargs)
+
+
+@pytest.fixture(scope='module')
+def full_sd():
+    return synthetic.synthetic_state_dict(seed=0, sharpen=3.0)
+
+
+@pytest.fixture(scope='module')
+def full_engine(full_sd):
+    engine = _engine(full_sd, max_neurons=16)
+    yield engine
+    engine.close()
+
+
+def _golden_inputs():
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(2, 15, seed=0, zero_mask_fraction=0.1)
+    masks_u8[0, 0] = 0
+    masks_u8[1, 3, :, 100:102, 50:52] = 0
+    return images_u8, masks_u8
+
+
+def test_encoder_matches_reference_golden(full_engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'encoder_resnet101.npz'))
+    images_u8, masks_u8 = _golden_inputs()
+    feats = full_engine.encode(images_u8.view(-1, 3, 224, 224), masks_u8.view(-1, 1, 224, 224)).cpu().view(2, 15, -1)
+    ref = torch.from_numpy(g['features'])
+    scale = ref.abs().max().item()
+    err = (feats - ref).abs().max().item()
+    print(f'encoder max abs err {err:.3e} (feature scale {scale:.3f})')
+    assert err <= 1e-3 * scale, f'encoder features differ from the reference golden: {err} (scale {scale})'
+    torch.testing.assert_close(feats, ref, rtol=2e-3, atol=1e-3 * scale)
+    # all-zero mask -> exactly zero features (reference tests/milan/encoders_test.py:59-77)
+    assert feats[0, 0].abs().max().item() == 0.0
+    assert feats[0, 1].abs().max().item() > 0.0
+
+
+def test_encoder_float_and_uint8_inputs_agree(full_engine):
+    images_u8, masks_u8 = _golden_inputs()
+    images_u8, masks_u8 = images_u8[:1].reshape(-1, 3, 224, 224), masks_u8[:1].reshape(-1, 1, 224, 224)
+    images_f, masks_f = O.to_float_inputs(images_u8, masks_u8)
+    a = full_engine.encode(images_u8, masks_u8)
+    b = full_engine.encode(images_f, masks_f)
+    assert torch.equal(a, b), (a - b).abs().max()
+    # masks=None == all-ones masks (src/milan/encoders.py:292-293)
+    c = full_engine.encode(images_u8[:3], None)
+    d = full_engine.encode(images_u8[:3], torch.ones_like(masks_u8[:3]))
+    assert torch.equal(c, d)
+
+
+def test_encoder_matches_oracle_on_fresh_inputs(full_engine, full_sd):
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(1, 6, seed=5)
+    images_f, masks_f = O.to_float_inputs(images_u8, masks_u8)
+    with torch.no_grad():
+        ref = O.encode(images_f, masks_f, full_sd)
+    got = full_engine.encode(images_u8.view(-1, 3, 224, 224), masks_u8.view(-1, 1, 224, 224)).cpu().view(1, 6, -1)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 1e-3 * scale
+
+
+@pytest.fixture(scope='module', params=sorted(VARIANTS))
+def variant(request, golden_dir):
+    name = request.param
+    sharpen, stop_bias = VARIANTS[name]
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=sharpen, stop_bias=stop_bias, with_encoder=False)
+    engine = _engine(sd, max_neurons=16)
+    g = np.load(os.path.join(golden_dir, f'decoder_{name}.npz'))
+    yield name, sd, engine, g
+    engine.close()
+
+
+def _tokens_match(got, ref, got_scores, ref_scores, what):
+    """Token ids must be identical except where the reference itself is within rounding of a tie."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    if np.array_equal(got, ref):
+        return
+    bad = np.argwhere((got != ref).any(axis=-1))
+    for idx in bad:
+        idx = tuple(idx)
+        assert abs(float(got_scores[idx]) - float(ref_scores[idx])) <= LOGP_TOL, (
+            f'{what}: sequence {idx} differs and scores are not tied: {got[idx]} vs {ref[idx]} '
+            f'({got_scores[idx]} vs {ref_scores[idx]})')
+    frac = len(bad) / max(1, int(np.prod(got.shape[:-1])))
+    assert frac <= 0.02, f'{what}: {len(bad)} sequences differ (near-ties), too many'
+
+
+def test_decoder_init_and_first_step(variant):
+    name, sd, engine, g = variant
+    n, k, _ = g['meta'].tolist()
+    feats = synthetic_features(n, k, seed=0)
+    h, c = engine.init_state(feats)
+    np.testing.assert_allclose(h.cpu().numpy(), g['init_h'], atol=2e-5)
+    np.testing.assert_allclose(c.cpu().numpy(), g['init_c'], atol=2e-5)
+    start = torch.full((n,), len(VOCAB), dtype=torch.long)
+    pred, attn, h1, c1, _, _ = engine.step(feats, start, h, c)
+    np.testing.assert_allclose(attn.cpu().numpy(), g['step0_attn'], atol=2e-5)
+    np.testing.assert_allclose(h1.cpu().numpy(), g['step0_h'], atol=2e-5)
+    np.testing.assert_allclose(c1.cpu().numpy(), g['step0_c'], atol=5e-5)
+    np.testing.assert_allclose(pred.logsumexp(-1).cpu().numpy(), g['step0_logsumexp'], atol=1e-4)
+    top_v, top_i = pred.cpu().topk(8, dim=-1)
+    np.testing.assert_allclose(top_v.numpy(), g['step0_top_values'], atol=2e-4)
+    if name != 'flat':
+        np.testing.assert_array_equal(top_i.numpy(), g['step0_top_indices'])
+
+
+def test_decoder_greedy(variant):
+    name, sd, engine, g = variant
+    n, k, _ = g['meta'].tolist()
+    feats = synthetic_features(n, k, seed=0)
+    tokens, scores, predictions, attentions = engine.decode_greedy(feats, 15, mi=False, temperature=0.2)
+    if name == 'flat':  # near-uniform logits: argmax is rounding-sensitive, scores are still pinned
+        _tokens_match(tokens.cpu().numpy(), g['greedy_tokens'], scores.cpu().numpy(), g['greedy_scores'], 'greedy')
+    else:
+        np.testing.assert_array_equal(tokens.cpu().numpy(), g['greedy_tokens'])
+        np.testing.assert_allclose(scores.cpu().numpy(), g['greedy_scores'], atol=LOGP_TOL)
+        np.testing.assert_allclose(attentions.cpu().numpy(), g['greedy_attn'], atol=1e-4)
+        chosen = predictions.gather(2, tokens.unsqueeze(-1)).squeeze(-1)
+        np.testing.assert_allclose(chosen.cpu().numpy(), g['greedy_chosen_logp'], atol=LOGP_TOL)
+    # MI greedy (the reference default for strategy='greedy' when the decoder has an LM, decoders.py:385-387)
+    tokens_mi, scores_mi, _, _ = engine.decode_greedy(feats, 15, mi=True, temperature=0.2)
+    if name != 'flat':
+        np.testing.assert_array_equal(tokens_mi.cpu().numpy(), g['greedy_mi_tokens'])
+        np.testing.assert_allclose(scores_mi.cpu().numpy(), g['greedy_mi_scores'], atol=LOGP_TOL)
+
+
+def test_decoder_beam_and_rerank(variant):
+    name, sd, engine, g = variant
+    n, k, _ = g['meta'].tolist()
+    feats = synthetic_features(n, k, seed=0)
+    beam_tokens, beam_scores, steps, tokens, scores, lm_scores = engine.decode_beam(feats, 15, 50, True, 0.2)
+    T = int(steps[0].item())
+    assert T == g['beam_tokens'].shape[-1], f'early-exit length {T} vs reference {g["beam_tokens"].shape[-1]}'
+    np.testing.assert_allclose(beam_scores.cpu().numpy(), g['beam_scores'], atol=LOGP_TOL)
+    if name != 'flat':
+        _tokens_match(beam_tokens[..., :T].cpu().numpy(), g['beam_tokens'], beam_scores.cpu().numpy(), g['beam_scores'],
+                      'beam')
+        np.testing.assert_allclose(lm_scores.view(-1).cpu().numpy(), g['lm_scores'], atol=LOGP_TOL)
+        np.testing.assert_array_equal(tokens[..., :T].cpu().numpy(), g['rerank_tokens'])
+    np.testing.assert_allclose(scores.cpu().numpy(), g['rerank_scores'], atol=LOGP_TOL)
+    assert (tokens[..., T:] == STOP).all()
+    # smaller beam / shorter length
+    bt, bs, steps, tok, sc, _ = engine.decode_beam(feats, 9, 7, True, 0.2)
+    T = int(steps[0].item())
+    assert T == g['small_beam_tokens'].shape[-1]
+    np.testing.assert_allclose(bs.cpu().numpy(), g['small_beam_scores'], atol=LOGP_TOL)
+    np.testing.assert_allclose(sc.cpu().numpy(), g['small_rerank_scores'], atol=LOGP_TOL)
+    if name != 'flat':
+        np.testing.assert_array_equal(bt[..., :T].cpu().numpy(), g['small_beam_tokens'])
+        np.testing.assert_array_equal(tok[..., :T].cpu().numpy(), g['small_rerank_tokens'])
+
+
+def test_lm_score_matches_oracle(variant):
+    name, sd, engine, g = variant
+    gen = torch.Generator().manual_seed(3)
+    inputs = torch.randint(0, len(VOCAB), (37, 12), generator=gen)
+    inputs[:, 0] = len(VOCAB)
+    inputs[3, 4] = STOP
+    inputs[5, 1] = STOP
+    inputs[7, 11] = STOP
+    inputs[9, 5:] = STOP
+    ref = O.lm_forward(inputs, sd, STOP)
+    got = engine.lm_score(inputs).cpu()
+    torch.testing.assert_close(got, ref, atol=LOGP_TOL, rtol=0)
+
+
+def test_beam_properties_full_size():
+    """Size-independent properties at BASELINE size (16 neurons x beam 50 x 15 steps, V = 5004)."""
+    sd = synthetic.synthetic_state_dict(seed=1, sharpen=12.0, stop_bias=2.0, with_encoder=False)
+    engine = _engine(sd, max_neurons=32)
+    feats = synthetic_features(32, 15, seed=9)
+    bt, bs, steps, tok, sc, lm = engine.decode_beam(feats, 15, 50, True, 0.2, group_size=16)
+    assert (bs[:, :-1] >= bs[:, 1:]).all(), 'beam scores must be sorted descending'
+    # every beam score equals the forced-decode log-prob sum of its sequence (tokens after the first <stop> cost 0)
+    for j in (0, 17, 49):
+        seq = bt[:, j]
+        _, _, pred, _ = engine.decode_greedy(feats, 15, mi=False, temperature=0.2, forced=seq)
+        chosen = pred.gather(2, seq.unsqueeze(-1)).squeeze(-1)
+        after = ((seq == STOP).long().cumsum(-1) - (seq == STOP).long()) > 0
+        total = chosen.masked_fill(after, 0.0).sum(-1)
+        torch.testing.assert_close(total, bs[:, j], atol=LOGP_TOL, rtol=0)
+    # rerank score = beam score - T * lm score at the chosen index (decoders.py:507)
+    combined = bs - 0.2 * lm
+    torch.testing.assert_close(sc, combined.max(dim=1).values, atol=1e-5, rtol=0)
+    # grouping: decoding the second group alone gives the same sequences (neurons are independent)
+    bt2, bs2, _, _, _, _ = engine.decode_beam(feats[16:], 15, 50, False, 0.2)
+    assert torch.equal(bt2, bt[16:]) and torch.allclose(bs2, bs[16:], atol=1e-5)
+    # beam_size = 1 reproduces greedy up to the first <stop>
+    b1, _, _, _, _, _ = engine.decode_beam(feats, 15, 1, False, 0.2)
+    gt, _, _, _ = engine.decode_greedy(feats, 15, mi=False, temperature=0.2)
+    for row_b, row_g in zip(b1[:, 0].tolist(), gt.tolist()):
+        cut = row_g.index(STOP) + 1 if STOP in row_g else len(row_g)
+        assert row_b[:cut] == row_g[:cut]
+    engine.close()
+
+
+def test_describe_host_end_to_end(full_engine, full_sd):
+    """milan_describe_host (host uint8 in, token ids out) vs the oracle's predict on the same exemplars."""
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(3, 15, seed=11)
+    images_f, masks_f = O.to_float_inputs(images_u8, masks_u8)
+    with torch.no_grad():
+        feats = O.encode(images_f, masks_f, full_sd)
+        ref = O.decode(feats, full_sd, VOCAB, strategy='rerank', beam_size=50)
+        ref_greedy = O.decode(feats, full_sd, VOCAB, strategy='greedy', mi=False)
+    tokens, scores, steps = full_engine.describe_host(images_u8, masks_u8, strategy='rerank')
+    T = ref.tokens.shape[-1]
+    assert int(steps[0]) == T
+    torch.testing.assert_close(scores, ref.scores, atol=LOGP_TOL, rtol=0)
+    _tokens_match(tokens[:, :T].numpy(), ref.tokens.numpy(), scores.numpy(), ref.scores.numpy(), 'describe/rerank')
+    tokens_g, scores_g, _ = full_engine.describe_host(images_u8, masks_u8, strategy='greedy', mi=False)
+    torch.testing.assert_close(scores_g, ref_greedy.scores, atol=LOGP_TOL, rtol=0)
+    _tokens_match(tokens_g.numpy(), ref_greedy.tokens.numpy(), scores_g.numpy(), ref_greedy.scores.numpy(),
+                  'describe/greedy')
+
+
+def test_facade_matches_reference_surface(full_sd):
+    """Decoder facade: predict() on a dataset of TopImages-like samples, forward kwargs and error behaviour."""
+    from neuron_descriptions_b200 import milan
+    from neuron_descriptions_b200.milan import lang
+    indexer = lang.Indexer(lang.Vocab(VOCAB), start=True, stop=True, pad=True, unk=True)
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer), max_neurons=16)
+    decoder.load_state_dict(full_sd)
+    with pytest.raises(RuntimeError):
+        decoder(torch.zeros(1, 15, 3904))  # not on a CUDA device: no CPU fallback
+    decoder.to('cuda:0')
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(3, 15, seed=11)
+    images_f, masks_f = O.to_float_inputs(images_u8, masks_u8)
+    dataset = [('layer', i, images_f[i], masks_f[i]) for i in range(3)]
+    captions = decoder.predict(dataset, strategy='rerank', temperature=.2, beam_size=50, device='cuda:0',
+                               display_progress_as=None)
+    with torch.no_grad():
+        ref = O.describe(images_f, masks_f, full_sd, VOCAB, strategy='rerank', beam_size=50)
+    assert len(captions) == 3 and all(isinstance(c, str) for c in captions)
+    assert list(captions) == list(ref)
+    out = decoder(images_f, masks_f, strategy='greedy', mi=False)
+    assert out.tokens.shape == (3, 15) and out.predictions.shape == (3, 15, V) and out.attentions.shape == (3, 15, 15)
+    with pytest.raises(ValueError, match='unknown strategy'):
+        decoder(images_f, masks_f, strategy='nope')
+    with pytest.raises(ValueError, match='cannot set `mi=` decoding when reranking'):
+        decoder(images_f, masks_f, strategy='rerank', mi=True)
+    with pytest.raises(ValueError, match='strategy must have length'):
+        decoder(images_f, masks_f, strategy=torch.zeros(3, 4, dtype=torch.long))
