@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the MILAN describe-neurons hot path on B200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference [--steps K] [--warmup W]           reference arm: the CPU oracle port
+
+A "step" = describing one batch of synthetic neurons (k = 15 exemplars of 3x224x224 + mask, beam = 50, LM/PMI
+rerank, length 15): ResNet-101 pyramid encode -> attention-LSTM beam search -> LM rerank -> token ids.
+  value : neurons/s with the uint8 exemplars already resident in HBM when the timed region starts
+  e2e   : the same through `milan_describe_host` with HOST (pinned) buffers: H2D of the exemplars and D2H of the
+          token ids / scores inside the timed region
+Weak scaling: every rank describes its own shard of neurons; the only collective is an all-gather of the final
+token ids + scores (NCCL), inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'neurons described/sec (k=15, beam=50)'
+UNIT = 'neurons/s'
+K_EXEMPLARS, BEAM, LENGTH, GROUP = 15, 50, 15, 16
+CONV_FLOP_PER_NEURON = 2.0 * 7.79935744e9 * K_EXEMPLARS  # 104 convs through layer4
+WORKLOAD = ('alexnet/imagenet 1k neurons, k=15, beam=50 + PMI rerank (synthetic exemplars of that shape, '
+            'random-init MILAN resnet101 encoder + attention-LSTM decoder + LSTM LM, V=5004)')
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as handle:
+            peaks = json.load(handle)
+        return peaks, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        clocks, maxes, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                clocks.append(float(parts[1]))
+                maxes.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        if not clocks:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        clocks.sort()
+        return {'sm_mhz': clocks[len(clocks) // 2], 'sm_max_mhz': max(maxes), 'reasons': sorted(reasons),
+                'samples': len(clocks)}
+
+
+def cpu_oracle_neurons_per_s(n_neurons, threads):
+    """The reference's CPU path (oracle port, torch fp32) on a bounded sample of the same workload."""
+    from neuron_descriptions_b200 import synthetic
+    from oracle import milan_oracle as O
+    torch.set_num_threads(threads)
+    vocab = synthetic.synthetic_vocab(5000)
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0)
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(n_neurons, K_EXEMPLARS, seed=123)
+    images, masks = O.to_float_inputs(images_u8, masks_u8)
+    start = time.perf_counter()
+    with torch.no_grad():
+        O.describe(images, masks, sd, vocab, batch_size=GROUP, strategy='rerank', beam_size=BEAM, length=LENGTH,
+                   temperature=0.2)
+    elapsed = time.perf_counter() - start
+    return n_neurons / elapsed, elapsed
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_oracle_neurons_per_s(1, threads)
+    times = []
+    for _ in range(args.steps):
+        nps, elapsed = cpu_oracle_neurons_per_s(sample, threads)
+        times.append(elapsed)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'neurons_per_step': sample, 'device': 'cpu'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': f'{sample} neurons per step x {len(times)} steps, oracle port of the reference '
+                                   f'PyTorch path (torch fp32, {threads} threads), batch 16, rerank beam 50'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=6)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='ours', choices=('ours', 'reference'))
+    parser.add_argument('--neurons-per-step', type=int, default=64)
+    parser.add_argument('--precision', default='split', choices=('split', 'fast'))
+    parser.add_argument('--no-cpu-baseline', action='store_true')
+    args = parser.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from neuron_descriptions_b200 import _lib, synthetic
+    from neuron_descriptions_b200.engine import Engine
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the milan_b200 engine has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    nb = args.neurons_per_step
+
+    vocab = synthetic.synthetic_vocab(5000)
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0)
+    engine = Engine(sd, vocab_size=len(vocab) + 4, device=device, precision=args.precision, max_neurons=nb)
+    lib = _lib.load()
+
+    # Two distinct host batches per rank, alternated, so consecutive steps never see the same bytes; each step moves
+    # nb*15*(3+1)*224*224 B (193 MB at nb=64) of inputs and GBs of activations: far beyond the 126 MB L2.
+    host = []
+    for i in range(2):
+        images_u8, masks_u8 = synthetic.synthetic_exemplars(nb, K_EXEMPLARS, seed=1000 * rank + i)
+        host.append((images_u8.pin_memory(), masks_u8.pin_memory()))
+    dev = [(im.to(device), mk.to(device)) for im, mk in host]
+    gathered_tokens = torch.empty(world, nb, LENGTH, dtype=torch.long, device=device) if world > 1 else None
+    gathered_scores = torch.empty(world, nb, dtype=torch.float32, device=device) if world > 1 else None
+
+    def step_resident(i):
+        images, masks = dev[i % 2]
+        feats = engine.encode(images.view(-1, 3, 224, 224), masks.view(-1, 1, 224, 224)).view(nb, K_EXEMPLARS, -1)
+        _, _, _, tokens, scores, _ = engine.decode_beam(feats, LENGTH, BEAM, True, 0.2, group_size=GROUP)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered_tokens, tokens)
+            dist.all_gather_into_tensor(gathered_scores, scores)
+        return tokens
+
+    def step_e2e(i):
+        images, masks = host[i % 2]
+        tokens, scores, _ = engine.describe_host(images, masks, strategy='rerank', length=LENGTH, beam=BEAM,
+                                                 group_size=GROUP, temperature=0.2)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered_tokens, tokens.to(device, non_blocking=True))
+            dist.all_gather_into_tensor(gathered_scores, scores.to(device, non_blocking=True))
+        return tokens
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(fn, profile):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        engine.set_profiling(profile)
+        launches0 = lib.milan_launch_count()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        start.record()
+        for i in range(steps):
+            fn(warmup + i)
+        end.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = start.elapsed_time(end)
+        launches = lib.milan_launch_count() - launches0
+        prof = engine.get_profile() if profile else None
+        engine.set_profiling(False)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof, clocks
+
+    ms_res, launches, prof, clocks = timed(step_resident, True)
+    ms_e2e, _, _, clocks_e2e = timed(step_e2e, False)
+
+    total_neurons = nb * steps * world
+    value = total_neurons / (ms_res / 1e3)
+    e2e_value = total_neurons / (ms_e2e / 1e3)
+    peaks, peak_kind = measured_peaks()
+    conv_ms = prof['conv_ms']
+    conv_launches = max(1, prof['conv_launches'])
+    achieved = CONV_FLOP_PER_NEURON * nb * steps / (conv_ms / 1e3) / 1e12  # algorithmic TFLOP/s while convs run
+    peak = peaks['bf16_tflops_sustained']
+    traffic_path = os.path.join(ROOT, 'profiles', 'conv_traffic.json')
+    traffic = None
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as handle:
+            traffic = json.load(handle).get('dram_bytes_per_launch')
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': ms_res / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16x3' if args.precision == 'split' else 'bf16', 'data': 'synthetic',
+        'config': {
+            'workload': WORKLOAD, 'neurons_per_step_per_gpu': nb, 'k': K_EXEMPLARS, 'beam': BEAM, 'length': LENGTH,
+            'strategy': 'rerank', 'reference_batch_size': GROUP, 'parallelism': f'neuron-sharded x{world}',
+            'precision': ('bf16 hi/lo split operands, 3 tcgen05 MMAs per k-block, fp32 TMEM accumulation (fp32-class '
+                          'results; parity-tested)' if args.precision == 'split' else 'plain bf16 operands'),
+            'l2': 'inputs larger than L2: 193 MB of fresh exemplars + >10 GB of activations per step vs 126 MB L2',
+        },
+        'roofline': {
+            'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+            'traffic': traffic, 'kernel': 'conv_gemm_kernel (104 encoder convolutions per step)',
+            'peak_kind': f'{peak_kind} bf16 sustained (kernel timed inside a long step)',
+            'algorithmic_flop_per_launch': CONV_FLOP_PER_NEURON * nb * steps / conv_launches,
+            'avg_launch_ms': conv_ms / conv_launches, 'conv_share_of_step': conv_ms / ms_res,
+            'mma_flop_multiplier': 3 if args.precision == 'split' else 1,
+        },
+        'phases_ms_per_step': {'encoder_convs': conv_ms / steps, 'step_total': ms_res / steps},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nb * K_EXEMPLARS * 4 * 224 * 224,
+                'd2h_bytes_per_step': nb * (LENGTH * 8 + 4 + 4), 'ms_per_step': ms_e2e / steps},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'clocks_e2e': clocks_e2e,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 4
+        nps, elapsed = cpu_oracle_neurons_per_s(sample, threads)
+        line['cpu_baseline'] = {'value': nps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': f'{sample} neurons (60 exemplars) through the oracle port of the reference '
+                                          f'PyTorch CPU path, rerank beam 50, {elapsed:.1f} s'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 }
 
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_all_launches{0};
 
 template <int BLOCK_N, bool SPLIT, int EPI>
 int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
@@ -287,12 +288,15 @@ int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   kernel<<<grid, kNumThreads, L::kTotalBytes, stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_all_launches.fetch_add(1, std::memory_order_relaxed);
   return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
 
 long long conv_gemm_launch_count() { return g_launches.load(); }
+long long total_launch_count() { return g_all_launches.load(); }
+void note_launch(int n) { g_all_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream) {

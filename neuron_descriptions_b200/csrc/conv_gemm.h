@@ -56,8 +56,10 @@ struct alignas(64) ConvGemmParams {
 // block_n: 64 or 128. split: hi/lo planes (1) or hi only (0). Returns cudaError_t as int.
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream);
-// Number of kernel launches performed through launch_conv_gemm since process start (for gpu_launches).
-long long conv_gemm_launch_count();
+// Kernel launches performed by this library since process start (for bench.py's gpu_launches).
+long long conv_gemm_launch_count();   // tcgen05 conv/GEMM kernel only
+long long total_launch_count();       // every kernel of the library
+void note_launch(int n = 1);
 
 // Host helpers to build tensor maps (driver entry point resolved at runtime; no libcuda link dependency).
 // 4-D bf16 map: dims (c, w, h, n), byte strides for w/h/n, box (64, bw, bh, bn), 128B swizzle, zero OOB fill.

@@ -1,6 +1,7 @@
 // Non-GEMM kernels of the decoder / beam search / LM rerank (see decoder.h). All arithmetic is fp32; operands
 // that feed a tensor-core GEMM are emitted as (hi, lo) bf16 pairs.
 #include "decoder.h"
+#include "conv_gemm.h"
 #include "ptx.cuh"
 
 #include <cfloat>
@@ -438,7 +439,10 @@ __global__ void fill_f32_kernel(float* dst, float v, int n) {
 }
 
 inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
-inline int last_err() { return static_cast<int>(cudaGetLastError()); }
+inline int last_err() {
+  note_launch();
+  return static_cast<int>(cudaGetLastError());
+}
 
 }  // namespace
 
@@ -507,6 +511,7 @@ int launch_gather_state(const GatherArgs& a, cudaStream_t stream) {
 int launch_backtrack(const BacktrackArgs& a, cudaStream_t stream) {
   const int rows = a.n_neurons * a.beam;
   backtrack_kernel<<<blocks_for(rows, 128), 128, 0, stream>>>(a);
+  note_launch();
   const int groups = (a.n_neurons + a.group_size - 1) / a.group_size;
   group_T_kernel<<<groups, 256, 0, stream>>>(a);
   return last_err();

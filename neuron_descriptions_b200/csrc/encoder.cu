@@ -6,6 +6,7 @@
 //   bn_relu_maxpool  : bn1 + ReLU + 3x3/2 max-pool after the stem (torchvision resnet forward)
 // All are HBM/L2-bound streaming kernels: coalesced along channels, 128-bit where the layout allows.
 #include "encoder.h"
+#include "conv_gemm.h"
 #include "ptx.cuh"
 
 #include <cstdint>
@@ -240,6 +241,7 @@ int launch_stem_im2col(const void* images, int dtype, int n_images, __nv_bfloat1
     stem_im2col_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         static_cast<const float*>(images), n_images, a_hi, a_lo, m, s, split);
   }
+  note_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -249,6 +251,7 @@ int launch_mask_pyramid(const void* masks, int dtype, int n_images, float* wts, 
   } else {
     mask_pyramid_kernel<float><<<n_images, 256, 0, stream>>>(static_cast<const float*>(masks), wts);
   }
+  note_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -256,6 +259,7 @@ int launch_masked_pool(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const f
                        int n_images, int P, int C, float* out, int out_stride, cudaStream_t stream) {
   dim3 grid(n_images, C / 64);
   masked_pool_kernel<<<grid, 256, 0, stream>>>(hi, lo, wts, wts_stride, P, C, out, out_stride);
+  note_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -267,6 +271,7 @@ int launch_bn_relu_maxpool(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
   const long long blocks = (total + threads - 1) / threads;
   bn_relu_maxpool_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x_hi, x_lo, alpha, beta, n_images,
                                                                                y_hi, y_lo);
+  note_launch();
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -592,7 +592,7 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   RC(launch_stem_im2col(d_images, dtype, n, stemA[0], stemA[1], mean, stdv, sp, st));
   if (d_masks == nullptr) {
     if (ones_masks == nullptr) {
-      uint8_t* p;
+      uint8_t* p = nullptr;
       if (dalloc(&p, static_cast<size_t>(cfg.max_images) * 224 * 224)) return 1;
       CU(cudaMemset(p, 1, static_cast<size_t>(cfg.max_images) * 224 * 224));
       ones_masks = p;
@@ -1101,7 +1101,7 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
   return 0;
 }
 
-int64_t milan_launch_count(void) { return conv_gemm_launch_count(); }
+int64_t milan_launch_count(void) { return total_launch_count(); }
 
 int milan_set_profiling(MilanEngine* engine, int32_t enabled) {
   if (engine == nullptr) return fail("null engine");

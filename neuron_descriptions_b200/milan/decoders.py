@@ -344,6 +344,8 @@ class Decoder:
             except ImportError:
                 pass
         captions = []
+        token_rows = []
+        length = kwargs.get('length') or self.length
         for lo in ranges:
             hi = min(lo + chunk, total)
             group = batch_size if chunk > batch_size else None
@@ -365,6 +367,10 @@ class Decoder:
                     else:
                         output = self(images, masks, group_size=group, **kwargs)
             captions += output.captions
+            rows = torch.full((len(output.tokens), length), self.indexer.stop_index, dtype=torch.long)
+            rows[:, :output.tokens.shape[1]] = output.tokens.cpu()
+            token_rows.append(rows)
+        self.last_predict_tokens = torch.cat(token_rows) if token_rows else torch.empty(0, length, dtype=torch.long)
         return tuple(captions)
 
     def fit(self, *args, **kwargs):

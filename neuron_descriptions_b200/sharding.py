@@ -1,0 +1,92 @@
+"""Neuron sharding across the GPUs of one box.
+
+Neurons are independent: rank r describes the contiguous range [r*ceil(N/G), (r+1)*ceil(N/G)) of the dataset
+order with a full replica of the (~280 MB) weights; there is no exchange during compute. The one collective is an
+all-gather of the final token ids (int64, padded to equal shard length) at the end — NCCL over NVLink on GPUs,
+gloo in the CPU tests — after which every rank (rank 0 matters) detokenises in dataset order.
+The reference has no multi-GPU path; this is new.
+"""
+import os
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of rank `rank`; the last shards may be short or empty."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def init_distributed() -> Tuple[int, int, int]:
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        else:
+            dist.init_process_group('gloo')
+    return world, rank, local_rank
+
+
+def finalize_distributed():
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def gather_token_rows(local: torch.Tensor, n_total: int, world: int, pad_value: int) -> torch.Tensor:
+    """All-gather per-rank (n_local, T) int64 rows into (n_total, T) in dataset order."""
+    if world == 1:
+        return local
+    per = (n_total + world - 1) // world
+    T = local.shape[1]
+    padded = torch.full((per, T), pad_value, dtype=torch.long, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty(world * per, T, dtype=torch.long, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return out[:n_total]
+
+
+class _Slice(torch.utils.data.Dataset):
+    def __init__(self, base, lo, hi):
+        self.base, self.lo, self.hi = base, lo, hi
+
+    def __len__(self):
+        return self.hi - self.lo
+
+    def __getitem__(self, index):
+        return self.base[self.lo + index]
+
+
+
+class _SliceU8(_Slice):
+    def batch_u8(self, lo, hi):
+        return self.base.batch_u8(self.lo + lo, self.lo + hi)
+
+
+def predict_sharded(decoder, dataset, world: int = 1, rank: int = 0, batch_size: int = 16, **kwargs) -> Sequence[str]:
+    """`Decoder.predict` over this rank's shard + all-gather of the token ids; returns all captions."""
+    n = len(dataset)
+    if world == 1:
+        return decoder.predict(dataset, batch_size=batch_size, **kwargs)
+    lo, hi = shard_range(n, rank, world)
+    # shards start on reference-batch boundaries only if ceil(N/G) is a multiple of batch_size; the reference's
+    # batch-level early exit only changes trailing <stop> columns, never a caption, so captions are unaffected.
+    shard = (_SliceU8 if hasattr(dataset, 'batch_u8') else _Slice)(dataset, lo, hi)
+    length = kwargs.get('length') or decoder.length
+    stop = decoder.indexer.stop_index
+    tokens = torch.full((hi - lo, length), stop, dtype=torch.long)
+    kwargs.setdefault('display_progress_as', None)
+    captions_local: List[str] = list(decoder.predict(shard, batch_size=batch_size, **kwargs)) if hi > lo else []
+    # captions -> token ids would need the tokenizer; gather the ids the engine produced instead
+    ids = getattr(decoder, 'last_predict_tokens', None)
+    if ids is not None and len(ids) == hi - lo:
+        tokens[:, :ids.shape[1]] = ids.cpu()
+    device = decoder.engine.device if torch.cuda.is_available() else torch.device('cpu')
+    gathered = gather_token_rows(tokens.to(device), n, world, stop)
+    return tuple(decoder.indexer.reconstruct(gathered.cpu().tolist())) if n else ()
