@@ -1,9 +1,11 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h for the contract).
 //
-// CTA = 6 warps, persistent over output tiles (static round-robin):
+// CTA = 7 warps, persistent over output tiles (static round-robin):
 //   warp 0      : TMA producer  (A boxes per tap / k-block, B weight tiles) -> smem ring, mbarrier full/empty
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer -> fp32 accumulators in TMEM (2 buffers)
-//   warps 2..5  : epilogue: tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo split or fp32 -> global
+//   warps 2..5  : epilogue: tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo split -> swizzled smem ->
+//                 TMA store (EPI_BF16), or fp32 direct stores (EPI_F32)
+//   warp 6      : residual prefetcher: TMA-loads the residual tile of each 64-column chunk into a 2-deep ring
 // The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_gemm.h"
 #include "ptx.cuh"
@@ -17,32 +19,46 @@ namespace milan {
 
 namespace {
 
-constexpr int kNumThreads = 192;
-constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KiB, one A plane per stage
+constexpr int kNumThreads = 224;
+constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KiB: one 128-row x 64-col bf16 plane
+constexpr int kSmemBudget = 224 * 1024;
 
-template <int BLOCK_N, bool SPLIT>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
 struct SmemLayout {
   static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
   static constexpr int kPlanes = SPLIT ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kStages = (192 * 1024) / kStageBytes;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotalBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 alignment slack
+  static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kABytes : 0;            // one 64-col chunk
+  static constexpr int kResBytes = (EPI == EPI_BF16 && HAS_RES) ? 2 * kPlanes * kABytes : 0;  // 2-deep ring
+  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kResBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kTotalBytes = kStages * kStageBytes + kStagingBytes + kResBytes + kBarrierBytes + 1024;
+  static_assert(kStages >= 2, "not enough shared memory for a pipelined main loop");
+  static_assert(kTotalBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <int BLOCK_N, bool SPLIT, int EPI>
+// byte offset of 16-byte chunk j of row r inside a [128][128 B] tile with the TMA/UMMA 128-byte swizzle
+__device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
+
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = SmemLayout<BLOCK_N, SPLIT>;
+  using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; power of two (128 or 256)
+  constexpr int kChunks = BLOCK_N / 64;        // 64-column epilogue chunks per tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+  uint8_t* staging = smem + kStages * L::kStageBytes;
+  uint8_t* res_smem = staging + L::kStagingBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_smem + L::kResBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint64_t* res_empty_bar = res_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -54,6 +70,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     tma_prefetch_desc(&p.tmap_b[0]);
     if (SPLIT) tma_prefetch_desc(&p.tmap_b[1]);
+    if (EPI == EPI_BF16) {
+      tma_prefetch_desc(&p.tmap_out[0]);
+      if (SPLIT) tma_prefetch_desc(&p.tmap_out[1]);
+      if (HAS_RES) {
+        tma_prefetch_desc(&p.tmap_res[0]);
+        if (SPLIT) tma_prefetch_desc(&p.tmap_res[1]);
+      }
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -61,6 +85,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&res_full_bar[s], 1);
+      mbar_init(&res_empty_bar[s], 128);
     }
     fence_barrier_init();
   }
@@ -96,8 +122,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * L::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
-            if (SPLIT) tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+            if (p.stem_mode) {
+              // filter row `tap`: window of padded row 2*(h0 + tap/2) + (tap & 1): coords (k, ow, parity, pair, n)
+              tma_load_5d(st, &p.tmap_a[0][0], &full_bar[stage], 0, w0, p.tap_dw[tap], ch, n0);
+              if (SPLIT) tma_load_5d(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 0, w0, p.tap_dw[tap], ch, n0);
+            } else {
+              tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+              if (SPLIT)
+                tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+            }
             uint8_t* sb = st + L::kPlanes * kABytes;
             const int kcoord = (tap * cin_blocks + cb) * kGemmBlockK;
             tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
@@ -146,17 +179,48 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
     }
     __syncwarp();
+  } else if (warp == 6) {
+    // ------------------------------------------------------------ residual prefetcher
+    if (EPI == EPI_BF16 && HAS_RES && lane == 0) {
+      int rb = 0;
+      uint32_t rphase = 0;
+      const uint32_t tx_bytes = L::kPlanes * p.a_box_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = n_tile * BLOCK_N + c * 64;
+          if (col0 >= p.cout) break;
+          mbar_wait(&res_empty_bar[rb], rphase ^ 1);
+          uint8_t* dst = res_smem + rb * (L::kPlanes * kABytes);
+          mbar_arrive_expect_tx(&res_full_bar[rb], tx_bytes);
+          tma_load_4d(dst, &p.tmap_res[0], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+          if (SPLIT)
+            tma_load_4d(dst + kABytes, &p.tmap_res[1], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h,
+                        tn * p.box_n);
+          if (++rb == 2) { rb = 0; rphase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;
+    const bool leader = (warp == 2 && lane == 0);
+    int iter = 0;
+    int rb = 0;
+    uint32_t rphase = 0;
+    // EPI_F32 only: row -> output pixel
     const int box_hw = p.box_w * p.box_h;
     const int dn = row / box_hw;
     const int rem = row - dn * box_hw;
     const int dh = rem / p.box_w;
     const int dw = rem - dh * p.box_w;
     const bool row_in_box = row < box_hw * p.box_n;
-    int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
@@ -165,48 +229,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int tn = m_tile / (p.tiles_w * p.tiles_h);
-      const int w = tw * p.box_w + dw, h = th * p.box_h + dh, n = tn * p.box_n + dn;
-      const bool valid = row_in_box && w < p.out_w && h < p.out_h && n < p.out_n;
-      const long long pix = (static_cast<long long>(n) * p.out_h + h) * p.out_w + w;
 
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+
+      if (EPI == EPI_BF16) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c0, acc);
-        tmem_ld_wait();
-        const int col0 = n_tile * BLOCK_N + c0;
-        if (valid && col0 < p.cout) {
-          float v[32];
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = n_tile * BLOCK_N + c * 64;
+          const bool active = col0 < p.cout;  // uniform across the CTA
+          if (active && HAS_RES) mbar_wait(&res_full_bar[rb], rphase);
+          // previous TMA store must have finished reading the staging tile before it is overwritten
+          if (leader) tma_store_wait_read<0>();
+          named_bar_sync(1, 128);
+          const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kABytes);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t acc[32];
+            tmem_ld_32x32(taddr + c * 64 + half * 32, acc);
+            tmem_ld_wait();
+            if (c == kChunks - 1 && half == 1) {
+              // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+              tcgen05_fence_before();
+              mbar_arrive(&tmem_empty_bar[as]);
             }
-          }
-          if (EPI == EPI_BF16) {
-            const long long off = pix * p.ldc + col0;
-            if (p.res_hi != nullptr) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.res_hi + off);
+            if (!active) continue;
+            float v[32];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 r = __ldg(r4 + j);
-                v[8 * j + 0] += bf16_lo_to_f32(r.x); v[8 * j + 1] += bf16_hi_to_f32(r.x);
-                v[8 * j + 2] += bf16_lo_to_f32(r.y); v[8 * j + 3] += bf16_hi_to_f32(r.y);
-                v[8 * j + 4] += bf16_lo_to_f32(r.z); v[8 * j + 5] += bf16_hi_to_f32(r.z);
-                v[8 * j + 6] += bf16_lo_to_f32(r.w); v[8 * j + 7] += bf16_hi_to_f32(r.w);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + half * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
-              if (SPLIT && p.res_lo != nullptr) {
-                const uint4* q4 = reinterpret_cast<const uint4*>(p.res_lo + off);
+            }
+            if (HAS_RES) {
+#pragma unroll
+              for (int pl = 0; pl < L::kPlanes; ++pl) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const uint4 r = __ldg(q4 + j);
+                  const uint4 r = *reinterpret_cast<const uint4*>(rsrc + pl * kABytes + swz(row, half * 4 + j));
                   v[8 * j + 0] += bf16_lo_to_f32(r.x); v[8 * j + 1] += bf16_hi_to_f32(r.x);
                   v[8 * j + 2] += bf16_lo_to_f32(r.y); v[8 * j + 3] += bf16_hi_to_f32(r.y);
                   v[8 * j + 4] += bf16_lo_to_f32(r.z); v[8 * j + 5] += bf16_hi_to_f32(r.z);
@@ -227,20 +292,54 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               hi[j] = pack_bf16x2(h0, h1);
               lo[j] = pack_bf16x2(l0, l1);
             }
-            uint4* o4 = reinterpret_cast<uint4*>(p.out_hi + off);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (SPLIT) {
-              uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + off);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(staging + swz(row, half * 4 + j)) =
+                  make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (SPLIT)
+                *reinterpret_cast<uint4*>(staging + kABytes + swz(row, half * 4 + j)) =
+                    make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
-          } else {  // EPI_F32
-            float* o = p.out_f32 + pix * p.ldc + col0;
+          }
+          if (active && HAS_RES) {
+            mbar_arrive(&res_empty_bar[rb]);  // residual chunk consumed
+            if (++rb == 2) { rb = 0; rphase ^= 1; }
+          }
+          fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
+          named_bar_sync(1, 128);
+          if (leader && active) {
+            tma_store_4d(&p.tmap_out[0], staging, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+            if (SPLIT) tma_store_4d(&p.tmap_out[1], staging + kABytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+            tma_store_commit();
+          }
+        }
+      } else {  // EPI_F32: direct fp32 stores, 128 B contiguous per thread per 32-column chunk
+        const int w = tw * p.box_w + dw, h = th * p.box_h + dh, n = tn * p.box_n + dn;
+        const bool valid = row_in_box && w < p.out_w && h < p.out_h && n < p.out_n;
+        const long long pix = (static_cast<long long>(n) * p.out_h + h) * p.out_w + w;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c0, acc);
+          tmem_ld_wait();
+          const int col0 = n_tile * BLOCK_N + c0;
+          if (valid && col0 < p.cout) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
             if (p.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
+            float* o = p.out_f32 + pix * p.ldc + col0;
             if (col0 + 32 <= p.cout) {
               float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
@@ -252,10 +351,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             }
           }
         }
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty_bar[as]);
       }
-      tcgen05_fence_before();
-      mbar_arrive(&tmem_empty_bar[as]);
     }
+    if (EPI == EPI_BF16 && leader) tma_store_wait_all<0>();  // all stores complete before the CTA exits
   }
 
   tcgen05_fence_before();
@@ -269,10 +369,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_all_launches{0};
 
-template <int BLOCK_N, bool SPLIT, int EPI>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
 int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, SPLIT>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI>;
+  using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI, HAS_RES>;
   static bool configured = false;
   static std::mutex mu;
   {
@@ -300,14 +400,18 @@ void note_launch(int n) { g_all_launches.fetch_add(n, std::memory_order_relaxed)
 
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream) {
-#define MILAN_DISPATCH(BN, SP, EP) \
-  if (block_n == BN && (split != 0) == SP && epilogue == EP) return launch_impl<BN, SP, EP>(p, num_sms, stream);
-  MILAN_DISPATCH(128, true, EPI_BF16)
-  MILAN_DISPATCH(128, false, EPI_BF16)
-  MILAN_DISPATCH(64, true, EPI_BF16)
-  MILAN_DISPATCH(64, false, EPI_BF16)
-  MILAN_DISPATCH(128, true, EPI_F32)
-  MILAN_DISPATCH(128, false, EPI_F32)
+  const bool res = p.has_res != 0;
+#define MILAN_DISPATCH(BN, SP, EP, RS)                                           \
+  if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS)        \
+    return launch_impl<BN, SP, EP, RS>(p, num_sms, stream);
+  MILAN_DISPATCH(128, true, EPI_BF16, false)
+  MILAN_DISPATCH(128, true, EPI_BF16, true)
+  MILAN_DISPATCH(128, false, EPI_BF16, false)
+  MILAN_DISPATCH(128, false, EPI_BF16, true)
+  MILAN_DISPATCH(64, true, EPI_BF16, false)
+  MILAN_DISPATCH(64, false, EPI_BF16, false)
+  MILAN_DISPATCH(128, true, EPI_F32, false)
+  MILAN_DISPATCH(128, false, EPI_F32, false)
 #undef MILAN_DISPATCH
   return static_cast<int>(cudaErrorInvalidValue);
 }
@@ -317,7 +421,7 @@ namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-char g_tmap_err[256] = "";
+char g_tmap_err[384] = "";
 
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -334,55 +438,57 @@ EncodeTiledFn get_encode_fn() {
 
 const char* tmap_last_error() { return g_tmap_err; }
 
-int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n,
-                 uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
-                 uint32_t box_h, uint32_t box_n) {
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled entry point unavailable");
     return -1;
   }
-  cuuint64_t dims[4] = {c, w, h, n};
-  cuuint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(kGemmBlockK), box_w, box_h, box_n};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  cuuint64_t d[5];
+  cuuint64_t s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    e[i] = 1;
+    if (i + 1 < rank) s[i] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s,
+                  b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    snprintf(g_tmap_err, sizeof g_tmap_err,
-             "cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
-             "box=(64,%u,%u,%u) base=%p",
-             static_cast<int>(r), (unsigned long long)c, (unsigned long long)w, (unsigned long long)h,
-             (unsigned long long)n, (unsigned long long)stride_w_bytes, (unsigned long long)stride_h_bytes,
-             (unsigned long long)stride_n_bytes, box_w, box_h, box_n, base);
+    int n = snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled(rank %d) failed: %d base=%p dims=(", rank,
+                     static_cast<int>(r), base);
+    for (int i = 0; i < rank && n < static_cast<int>(sizeof g_tmap_err) - 32; ++i)
+      n += snprintf(g_tmap_err + n, sizeof g_tmap_err - n, "%llu,", (unsigned long long)dims[i]);
+    n += snprintf(g_tmap_err + n, sizeof g_tmap_err - n, ") strides=(");
+    for (int i = 0; i + 1 < rank && n < static_cast<int>(sizeof g_tmap_err) - 32; ++i)
+      n += snprintf(g_tmap_err + n, sizeof g_tmap_err - n, "%llu,", (unsigned long long)strides_bytes[i]);
+    n += snprintf(g_tmap_err + n, sizeof g_tmap_err - n, ") box=(");
+    for (int i = 0; i < rank && n < static_cast<int>(sizeof g_tmap_err) - 32; ++i)
+      n += snprintf(g_tmap_err + n, sizeof g_tmap_err - n, "%u,", box[i]);
+    snprintf(g_tmap_err + n, sizeof g_tmap_err - n, ")");
     return static_cast<int>(r);
   }
   return 0;
 }
 
+int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n,
+                 uint64_t stride_w_bytes, uint64_t stride_h_bytes, uint64_t stride_n_bytes, uint32_t box_w,
+                 uint32_t box_h, uint32_t box_n) {
+  const uint64_t dims[4] = {c, w, h, n};
+  const uint64_t strides[3] = {stride_w_bytes, stride_h_bytes, stride_n_bytes};
+  const uint32_t box[4] = {static_cast<uint32_t>(kGemmBlockK), box_w, box_h, box_n};
+  return make_tmap_nd(out, base, 4, dims, strides, box);
+}
+
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes,
                  uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) {
-    snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled entry point unavailable");
-    return -1;
-  }
-  cuuint64_t dims[2] = {k, rows};
-  cuuint64_t strides[1] = {pitch_bytes};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBlockK), box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    snprintf(g_tmap_err, sizeof g_tmap_err,
-             "cuTensorMapEncodeTiled(2d) failed: %d dims=(%llu,%llu) pitch=%llu box=(64,%u) base=%p",
-             static_cast<int>(r), (unsigned long long)k, (unsigned long long)rows,
-             (unsigned long long)pitch_bytes, box_rows, base);
-    return static_cast<int>(r);
-  }
-  return 0;
+  const uint64_t dims[2] = {k, rows};
+  const uint64_t strides[1] = {pitch_bytes};
+  const uint32_t box[2] = {static_cast<uint32_t>(kGemmBlockK), box_rows};
+  return make_tmap_nd(out, base, 2, dims, strides, box);
 }
 
 void choose_box(int W, int H, int N, int* bw, int* bh, int* bn) {

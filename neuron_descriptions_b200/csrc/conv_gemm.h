@@ -34,6 +34,10 @@ enum EpilogueKind : int {
 struct alignas(64) ConvGemmParams {
   CUtensorMap tmap_a[2][4];  // [hi|lo][parity plane]
   CUtensorMap tmap_b[2];     // [hi|lo]
+  CUtensorMap tmap_out[2];   // [hi|lo] EPI_BF16: output tensor, box (64, box_w, box_h, box_n), TMA store
+  CUtensorMap tmap_res[2];   // [hi|lo] EPI_BF16 + residual: same geometry as tmap_out, TMA load
+  int stem_mode;             // 1: A is the 5-D overlapping-window map of the 7x7/2 stem (see build_stem_params)
+  int has_res;               // residual add in the epilogue
   int box_w, box_h, box_n;   // M tile = box_w*box_h*box_n (<=128) output pixels
   int tiles_w, tiles_h, tiles_n;
   int out_w, out_h, out_n;   // output extents (pixels / images)
@@ -54,6 +58,7 @@ struct alignas(64) ConvGemmParams {
 };
 
 // block_n: 64 or 128. split: hi/lo planes (1) or hi only (0). Returns cudaError_t as int.
+// EPI_BF16 kernels store through tmap_out (and read the residual through tmap_res when p.has_res).
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream);
 // Kernel launches performed by this library since process start (for bench.py's gpu_launches).
@@ -69,6 +74,9 @@ int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uin
 // 2-D bf16 map: dims (k, rows), row pitch bytes, box (64, box_rows).
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes,
                  uint32_t box_rows);
+// Generic bf16 map of `rank` dims (dims[0] innermost; strides_bytes[i] is the stride of dim i+1), 128B swizzle.
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box);
 const char* tmap_last_error();
 
 // Pick an M-tile box (bw, bh, bn) with bw*bh*bn <= 128 minimising the number of tiles for a WxHxN output.
@@ -105,6 +113,21 @@ struct ConvIO {
 // Fills `p` (tensor maps, tiling, taps) for the convolution; returns 0 on success. *block_n receives the
 // N-tile width the kernel must be launched with.
 int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n);
+
+// The 7x7 stride-2 stem as an implicit GEMM without im2col: the input is the zero-padded NHWC4 image
+// [N][232][240][4] (pixel (ih, iw) at (ih + 3, iw + 4); channel 3 = 0) and the k-block of filter row r is the
+// 128-byte window {16 pixels x 4 channels} of padded row 2*oh + r starting at pixel 2*ow, addressed by a 5-D tensor
+// map (k, ow, row parity, row pair, n) whose `ow` stride (16 B) is smaller than the window (overlapping boxes).
+// Only window pixels 1..7 carry weights. Weights: [64][7*64] (pack_stem_weights). Output: raw conv1
+// [N][112][112][64] through tmap_out. block_n is 64.
+constexpr int kStemPadH = 232;
+constexpr int kStemPadW = 240;
+constexpr int kStemKTotal = 7 * 64;
+int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, const __nv_bfloat16* img_lo,
+                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, __nv_bfloat16* out_hi,
+                      __nv_bfloat16* out_lo, int split);
+// w: torchvision conv1.weight [64][3][7][7] -> packed [64][448] in the k order build_stem_params expects.
+void pack_stem_weights(const float* w, float* packed);
 
 // Plain GEMM out[M][ldc] (fp32) = A[M][K] * W[N][K]^T + bias, A given as bf16 hi/lo planes with row pitch
 // a_pitch (elements), W contiguous [N][K]. K must be a multiple of 64. Launch with block_n = 128, EPI_F32.

@@ -97,6 +97,32 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
     p->num_taps = t;
   }
   p->a_box_bytes = static_cast<uint32_t>(p->box_w) * p->box_h * p->box_n * kGemmBlockK * 2;
+  if (io.out_hi != nullptr) {
+    // Output (and residual) tensors [N][Ho][Wo][Cout] addressed with the same M-tile boxes, 64 channels wide.
+    const __nv_bfloat16* outs[2] = {io.out_hi, io.out_lo};
+    const __nv_bfloat16* ress[2] = {io.res_hi, io.res_lo};
+    const uint64_t opitch = static_cast<uint64_t>(p->ldc) * esz;
+    p->has_res = io.res_hi != nullptr ? 1 : 0;
+    for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
+      for (int which = 0; which < 2; ++which) {
+        const __nv_bfloat16* base = which == 0 ? outs[hl] : ress[hl];
+        if (base == nullptr) continue;
+        CUtensorMap* tm = which == 0 ? &p->tmap_out[hl] : &p->tmap_res[hl];
+        if (d.ksize == 1 && d.stride == 1) {
+          const uint64_t M = static_cast<uint64_t>(p->out_w);
+          rc = make_tmap_4d(tm, base, d.Cout, M, 1, 1, opitch, opitch * M, opitch * M, kGemmBlockM, 1, 1);
+        } else {
+          rc = make_tmap_4d(tm, base, d.Cout, p->out_w, p->out_h, p->out_n, opitch, opitch * p->out_w,
+                            opitch * p->out_w * p->out_h, p->box_w, p->box_h, p->box_n);
+        }
+        if (rc) return rc;
+      }
+    }
+    if (!split) {
+      p->tmap_out[1] = p->tmap_out[0];
+      p->tmap_res[1] = p->tmap_res[0];
+    }
+  }
   const uint64_t ktot = static_cast<uint64_t>(p->num_taps) * d.Cin;
   for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
     rc = make_tmap_2d(&p->tmap_b[hl], w_planes[hl], ktot, d.Cout, ktot * esz, bn_tile);
@@ -106,6 +132,70 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
     p->tmap_b[1] = p->tmap_b[0];
     for (int pl = 0; pl < 4; ++pl) p->tmap_a[1][pl] = p->tmap_a[0][pl];
   }
+  return 0;
+}
+
+void pack_stem_weights(const float* w, float* packed) {
+  // k = r*64 + sp*4 + c  <-  w[co][c][r][s = sp - 1]; zero for sp = 0, sp > 7, c = 3.
+  for (int co = 0; co < 64; ++co) {
+    for (int k = 0; k < kStemKTotal; ++k) {
+      const int r = k / 64, sp = (k / 4) & 15, c = k & 3;
+      const int s = sp - 1;
+      float v = 0.f;
+      if (s >= 0 && s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+      packed[co * kStemKTotal + k] = v;
+    }
+  }
+}
+
+int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, const __nv_bfloat16* img_lo,
+                      const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, __nv_bfloat16* out_hi,
+                      __nv_bfloat16* out_lo, int split) {
+  memset(p, 0, sizeof(*p));
+  const int O = 112;
+  p->stem_mode = 1;
+  p->cin = 64;   // one 128-byte k-block per filter row
+  p->cout = 64;
+  p->n_tiles = 1;
+  p->ldc = 64;
+  p->num_taps = 7;
+  for (int r = 0; r < 7; ++r) {  // padded row 2*oh + r = 2*(oh + r/2) + (r & 1)
+    p->tap_plane[r] = 0;
+    p->tap_dw[r] = static_cast<int8_t>(r & 1);   // row parity coordinate
+    p->tap_dh[r] = static_cast<int8_t>(r >> 1);  // row-pair offset
+  }
+  int bw, bh, bn;
+  choose_box(O, O, N, &bw, &bh, &bn);
+  p->box_w = bw; p->box_h = bh; p->box_n = bn;
+  p->tiles_w = (O + bw - 1) / bw; p->tiles_h = (O + bh - 1) / bh; p->tiles_n = (N + bn - 1) / bn;
+  p->out_w = O; p->out_h = O; p->out_n = N;
+  p->a_box_bytes = static_cast<uint32_t>(bw) * bh * bn * 128;
+  const uint64_t P = static_cast<uint64_t>(kStemPadW) * 4 * 2;  // padded row pitch in bytes
+  const __nv_bfloat16* imgs[2] = {img_hi, img_lo};
+  const __nv_bfloat16* ws[2] = {w_hi, w_lo};
+  __nv_bfloat16* outs[2] = {out_hi, out_lo};
+  const int np = split ? 2 : 1;
+  for (int hl = 0; hl < np; ++hl) {
+    // dims: (k: 64 elems = 16 px x 4 ch, ow, row parity, row pair, n)
+    const uint64_t dims[5] = {64, static_cast<uint64_t>(O), 2, static_cast<uint64_t>(kStemPadH / 2),
+                              static_cast<uint64_t>(N)};
+    const uint64_t strides[4] = {16, P, 2 * P, static_cast<uint64_t>(kStemPadH) * P};
+    const uint32_t box[5] = {64, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    int rc = make_tmap_nd(&p->tmap_a[hl][0], imgs[hl], 5, dims, strides, box);
+    if (rc) return rc;
+    for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];
+    rc = make_tmap_2d(&p->tmap_b[hl], ws[hl], kStemKTotal, 64, kStemKTotal * 2, 64);
+    if (rc) return rc;
+    const uint64_t opitch = 64 * 2;
+    rc = make_tmap_4d(&p->tmap_out[hl], outs[hl], 64, O, O, N, opitch, opitch * O, opitch * O * O, bw, bh, bn);
+    if (rc) return rc;
+  }
+  if (!split) {
+    p->tmap_b[1] = p->tmap_b[0];
+    p->tmap_out[1] = p->tmap_out[0];
+    for (int pl = 0; pl < 4; ++pl) p->tmap_a[1][pl] = p->tmap_a[0][pl];
+  }
+  p->out_hi = out_hi; p->out_lo = out_lo;
   return 0;
 }
 

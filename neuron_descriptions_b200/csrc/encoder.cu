@@ -1,5 +1,5 @@
 // Non-GEMM kernels of the pyramid encoder (reference: PyramidConvEncoder.forward, src/milan/encoders.py:286-320).
-//   stem_im2col      : normalise (encoders.py:294-295) + im2col of the 7x7/2 stem -> bf16 hi/lo GEMM operand
+//   stem_pack        : normalise (encoders.py:294-295) + repack to padded NHWC4 bf16 hi/lo for the im2col-free stem
 //   mask_pyramid     : bilinear (align_corners=False) mask downsample to the 5 retained resolutions +
 //                      per-image sum-normalisation with the all-zero exception (encoders.py:303-314)
 //   masked_pool      : weighted spatial sum of a retained NHWC map (encoders.py:317)
@@ -17,7 +17,6 @@ namespace {
 
 constexpr int kImg = 224;
 constexpr int kStemOut = 112;
-constexpr int kStemK = 192;  // 7*7*3 = 147 padded to 3 x 64
 
 template <typename T>
 __device__ __forceinline__ float load_pixel(const T* p);
@@ -32,50 +31,36 @@ __device__ __forceinline__ float load_pixel<float>(const float* p) {
   return *p;
 }
 
-// One warp per output pixel; lane l writes k = 6l .. 6l+5 of the 192-wide row.
+// Normalise + repack NCHW images into the zero-padded NHWC4 bf16 layout the stem GEMM reads through its 5-D
+// overlapping-window tensor map: [n][232][240][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
+// One thread per padded pixel; 8-byte stores per plane, coalesced along x.
 template <typename T>
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const T* __restrict__ images, int n_images,
-                                                          __nv_bfloat16* __restrict__ a_hi,
-                                                          __nv_bfloat16* __restrict__ a_lo, float3 mean, float3 stdv,
-                                                          int split) {
-  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = static_cast<long long>(n_images) * kStemOut * kStemOut;
-  if (warp_global >= total) return;
-  const int ow = warp_global % kStemOut;
-  const int oh = (warp_global / kStemOut) % kStemOut;
-  const int n = warp_global / (kStemOut * kStemOut);
-  const T* img = images + static_cast<long long>(n) * 3 * kImg * kImg;
-  const float m[3] = {mean.x, mean.y, mean.z};
-  const float s[3] = {stdv.x, stdv.y, stdv.z};
-  uint32_t hi[3], lo[3];
+__global__ void __launch_bounds__(256) stem_pack_kernel(const T* __restrict__ images, int n_images,
+                                                        __nv_bfloat16* __restrict__ p_hi,
+                                                        __nv_bfloat16* __restrict__ p_lo, float3 mean, float3 stdv,
+                                                        int split) {
+  constexpr int PH = kStemPadH, PW = kStemPadW;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_images) * PH * PW;
+  if (idx >= total) return;
+  const int x = idx % PW;
+  const int y = (idx / PW) % PH;
+  const int n = idx / (PH * PW);
+  const int ih = y - 3, iw = x - 4;
+  float v[3] = {0.f, 0.f, 0.f};
+  if (ih >= 0 && ih < kImg && iw >= 0 && iw < kImg) {
+    const T* img = images + static_cast<long long>(n) * 3 * kImg * kImg + static_cast<long long>(ih) * kImg + iw;
+    const float m[3] = {mean.x, mean.y, mean.z};
+    const float s[3] = {stdv.x, stdv.y, stdv.z};
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    __nv_bfloat16 h2[2], l2[2];
+    for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(load_pixel<T>(img + c * kImg * kImg), m[c]), s[c]);
+  }
+  __nv_bfloat16 h[3], l[3];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int k = lane * 6 + j * 2 + e;
-      float v = 0.0f;
-      if (k < 147) {
-        const int r = k / 21, rem = k - r * 21, ss = rem / 3, c = rem - ss * 3;
-        const int ih = oh * 2 + r - 3, iw = ow * 2 + ss - 3;
-        if (ih >= 0 && ih < kImg && iw >= 0 && iw < kImg) {
-          const float x = load_pixel<T>(img + (static_cast<long long>(c) * kImg + ih) * kImg + iw);
-          v = __fdiv_rn(__fsub_rn(x, m[c]), s[c]);
-        }
-      }
-      split_bf16(v, h2[e], l2[e]);
-    }
-    hi[j] = pack_bf16x2(h2[0], h2[1]);
-    lo[j] = pack_bf16x2(l2[0], l2[1]);
-  }
-  const long long off = warp_global * kStemK + lane * 6;  // 12-byte aligned -> 4-byte stores
-  uint32_t* ph = reinterpret_cast<uint32_t*>(a_hi + off);
-  ph[0] = hi[0]; ph[1] = hi[1]; ph[2] = hi[2];
-  if (split) {
-    uint32_t* pl = reinterpret_cast<uint32_t*>(a_lo + off);
-    pl[0] = lo[0]; pl[1] = lo[1]; pl[2] = lo[2];
-  }
+  for (int c = 0; c < 3; ++c) split_bf16(v[c], h[c], l[c]);
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  *reinterpret_cast<uint2*>(p_hi + idx * 4) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], zero));
+  if (split) *reinterpret_cast<uint2*>(p_lo + idx * 4) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], zero));
 }
 
 template <typename T>
@@ -227,19 +212,19 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
 
 }  // namespace
 
-int launch_stem_im2col(const void* images, int dtype, int n_images, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
-                       const float mean[3], const float stdv[3], int split, cudaStream_t stream) {
-  const long long warps = static_cast<long long>(n_images) * kStemOut * kStemOut;
+int launch_stem_pack(const void* images, int dtype, int n_images, __nv_bfloat16* p_hi, __nv_bfloat16* p_lo,
+                     const float mean[3], const float stdv[3], int split, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_images) * kStemPadH * kStemPadW;
   const int threads = 256;
-  const long long blocks = (warps * 32 + threads - 1) / threads;
+  const long long blocks = (total + threads - 1) / threads;
   const float3 m = make_float3(mean[0], mean[1], mean[2]);
   const float3 s = make_float3(stdv[0], stdv[1], stdv[2]);
   if (dtype == 0) {
-    stem_im2col_kernel<uint8_t><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        static_cast<const uint8_t*>(images), n_images, a_hi, a_lo, m, s, split);
+    stem_pack_kernel<uint8_t><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        static_cast<const uint8_t*>(images), n_images, p_hi, p_lo, m, s, split);
   } else {
-    stem_im2col_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        static_cast<const float*>(images), n_images, a_hi, a_lo, m, s, split);
+    stem_pack_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        static_cast<const float*>(images), n_images, p_hi, p_lo, m, s, split);
   }
   note_launch();
   return static_cast<int>(cudaGetLastError());

@@ -89,7 +89,6 @@ struct Plan {
 constexpr int kRes[4] = {56, 28, 14, 7};
 constexpr int kBlocks[4] = {3, 4, 23, 3};
 constexpr int kPlanes[4] = {64, 128, 256, 512};
-constexpr int kStemK = 192;
 constexpr double kBnEps = 1e-5;
 
 }  // namespace
@@ -231,17 +230,13 @@ int MilanEngine::finalize_encoder() {
   } else {
     return fail("missing tensor encoder.std");
   }
-  // stem: [64][3][7][7] -> [64][(r*7+s)*3 + c], K padded to 192, no BN fold (raw conv1 output is pooled).
+  // stem: [64][3][7][7] -> [64][256] in the window order of build_stem_params; no BN fold (raw conv1 is pooled).
   const HostTensor* w = get(pre + "conv1.weight");
   if (w == nullptr || w->numel() != 64 * 3 * 49) return fail("missing/invalid %sconv1.weight", pre.c_str());
   {
-    std::vector<float> packed(64 * kStemK, 0.f);
-    for (int co = 0; co < 64; ++co)
-      for (int c = 0; c < 3; ++c)
-        for (int r = 0; r < 7; ++r)
-          for (int s = 0; s < 7; ++s)
-            packed[co * kStemK + (r * 7 + s) * 3 + c] = w->data[((co * 3 + c) * 7 + r) * 7 + s];
-    if (upload_split(&stem_w, packed, 64, kStemK)) return 1;
+    std::vector<float> packed(64 * kStemKTotal, 0.f);
+    pack_stem_weights(w->data.data(), packed.data());
+    if (upload_split(&stem_w, packed, 64, kStemKTotal)) return 1;
   }
   auto bn_fold = [&](const std::string& bn, int c, std::vector<double>* scale, std::vector<double>* shift) -> int {
     const HostTensor *g = get(bn + ".weight"), *b = get(bn + ".bias"), *m = get(bn + ".running_mean"),
@@ -421,7 +416,7 @@ int MilanEngine::alloc_workspace() {
   (void)V;
   if (cfg.has_encoder) {
     const size_t n = cfg.max_images;
-    if (dalloc2(stemA, n * 12544 * kStemK)) return 1;
+    if (dalloc2(stemA, n * kStemPadH * kStemPadW * 4)) return 1;
     if (dalloc2(c1raw, n * 12544 * 64)) return 1;
     if (dalloc2(bufX, n * 3136 * 256)) return 1;
     if (dalloc2(bufY, n * 3136 * 256)) return 1;
@@ -525,14 +520,11 @@ int MilanEngine::build_encoder_plans(int n, std::vector<Plan>** out) {
   }
   std::vector<Plan> plans;
   const int sp = split ? 1 : 0;
-  {  // stem GEMM: [n*112*112][192] x [64][192]^T -> raw conv1 (no bias, no ReLU)
+  {  // stem: im2col-free implicit GEMM over the padded NHWC4 image -> raw conv1 (no bias, no ReLU)
     Plan pl;
-    ConvDesc d{n, 112, 112, kStemK, 64, 1, 1};
-    ConvIO io{};
-    io.in_hi = stemA[0]; io.in_lo = stemA[1];
-    io.w_hi = stem_w.hi; io.w_lo = stem_w.lo;
-    io.out_hi = c1raw[0]; io.out_lo = c1raw[1];
-    if (build_conv_params(&pl.p, d, io, sp, &pl.block_n)) return fail("stem plan: %s", tmap_last_error());
+    pl.block_n = 64;
+    if (build_stem_params(&pl.p, n, stemA[0], stemA[1], stem_w.hi, stem_w.lo, c1raw[0], c1raw[1], sp))
+      return fail("stem plan: %s", tmap_last_error());
     plans.push_back(pl);
   }
   __nv_bfloat16** x = bufX;
@@ -589,7 +581,7 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   const int F = cfg.feature_size;
   const int sp = split ? 1 : 0;
   if (profiling) conv_events_used = 0;
-  RC(launch_stem_im2col(d_images, dtype, n, stemA[0], stemA[1], mean, stdv, sp, st));
+  RC(launch_stem_pack(d_images, dtype, n, stemA[0], stemA[1], mean, stdv, sp, st));
   if (d_masks == nullptr) {
     if (ones_masks == nullptr) {
       uint8_t* p = nullptr;

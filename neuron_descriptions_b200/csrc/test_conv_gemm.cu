@@ -1,6 +1,7 @@
 // Standalone check of the tcgen05 conv/GEMM kernel against a double-precision CPU convolution.
 // Build: make -C neuron_descriptions_b200/csrc test_conv_gemm ; run on a B200 (gpurun).
 #include "conv_gemm.h"
+#include "encoder.h"
 
 #include <cmath>
 #include <cstdio>
@@ -32,7 +33,7 @@ static float bf2f(uint16_t h) {
   memcpy(&f, &u, 4);
   return f;
 }
-static void split(const std::vector<float>& x, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+static void split_vec(const std::vector<float>& x, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
   hi.resize(x.size());
   lo.resize(x.size());
   for (size_t i = 0; i < x.size(); ++i) {
@@ -68,9 +69,9 @@ static int run_case(const Case& c, int num_sms) {
   for (int i = 0; i < c.Cout; ++i) bias[i] = nd(rng) * 0.1f;
   for (auto& v : res) v = nd(rng);
   std::vector<uint16_t> xh, xl, wh, wl, rh, rl;
-  split(x, xh, xl);
-  split(w, wh, wl);
-  split(res, rh, rl);
+  split_vec(x, xh, xl);
+  split_vec(w, wh, wl);
+  split_vec(res, rh, rl);
   // The CPU reference uses exactly the values the GPU sees.
   std::vector<float> xe(in_elems), we(w_elems), re(out_elems);
   for (size_t i = 0; i < in_elems; ++i) xe[i] = c.split ? bf2f(xh[i]) + bf2f(xl[i]) : bf2f(xh[i]);
@@ -100,8 +101,10 @@ static int run_case(const Case& c, int num_sms) {
     io.res_hi = reinterpret_cast<__nv_bfloat16*>(drh);
     io.res_lo = reinterpret_cast<__nv_bfloat16*>(drl);
   }
-  io.out_hi = reinterpret_cast<__nv_bfloat16*>(doh);
-  io.out_lo = reinterpret_cast<__nv_bfloat16*>(dol);
+  if (!c.f32out) {
+    io.out_hi = reinterpret_cast<__nv_bfloat16*>(doh);
+    io.out_lo = reinterpret_cast<__nv_bfloat16*>(dol);
+  }
   io.out_f32 = dof;
   io.relu = c.relu;
   ConvGemmParams p;
@@ -182,6 +185,102 @@ static int run_case(const Case& c, int num_sms) {
   return ok ? 0 : 1;
 }
 
+// 7x7 stride-2 stem through the 5-D overlapping-window tensor map vs a direct CPU convolution.
+static int run_stem(int N, int split, int num_sms) {
+  std::mt19937 rng(99);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  std::uniform_int_distribution<int> ud(0, 255);
+  const size_t img_elems = static_cast<size_t>(N) * 3 * 224 * 224;
+  std::vector<uint8_t> img(img_elems);
+  for (auto& v : img) v = static_cast<uint8_t>(ud(rng));
+  std::vector<float> w(64 * 3 * 49), packed(64 * kStemKTotal);
+  for (auto& v : w) v = nd(rng) * 0.08f;
+  pack_stem_weights(w.data(), packed.data());
+  std::vector<uint16_t> wh, wl;
+  split_vec(packed, wh, wl);
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  uint8_t* dimg = upload(img);
+  uint16_t *dwh = upload(wh), *dwl = upload(wl), *dph, *dpl, *doh, *dol;
+  const size_t pad_elems = static_cast<size_t>(N) * kStemPadH * kStemPadW * 4;
+  const size_t out_elems = static_cast<size_t>(N) * 112 * 112 * 64;
+  CK(cudaMalloc(&dph, pad_elems * 2 + 256));
+  CK(cudaMalloc(&dpl, pad_elems * 2 + 256));
+  CK(cudaMalloc(&doh, out_elems * 2 + 256));
+  CK(cudaMalloc(&dol, out_elems * 2 + 256));
+  CK(cudaMemset(doh, 0xFF, out_elems * 2));
+  CK(cudaMemset(dol, 0xFF, out_elems * 2));
+  int rc = launch_stem_pack(dimg, 0, N, reinterpret_cast<__nv_bfloat16*>(dph), reinterpret_cast<__nv_bfloat16*>(dpl), mean,
+                            stdv, split, 0);
+  if (rc) { printf("[stem] pack launch failed %d\n", rc); return 1; }
+  ConvGemmParams p;
+  rc = build_stem_params(&p, N, reinterpret_cast<__nv_bfloat16*>(dph), reinterpret_cast<__nv_bfloat16*>(dpl),
+                         reinterpret_cast<__nv_bfloat16*>(dwh), reinterpret_cast<__nv_bfloat16*>(dwl),
+                         reinterpret_cast<__nv_bfloat16*>(doh), reinterpret_cast<__nv_bfloat16*>(dol), split);
+  if (rc) { printf("[stem] build_stem_params failed rc=%d: %s\n", rc, tmap_last_error()); return 1; }
+  rc = launch_conv_gemm(p, 64, split, EPI_BF16, num_sms, 0);
+  if (rc) { printf("[stem] launch failed rc=%d\n", rc); return 1; }
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) { printf("[stem] kernel failed: %s\n", cudaGetErrorString(se)); return 1; }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < 3; ++i) launch_conv_gemm(p, 64, split, EPI_BF16, num_sms, 0);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= 3;
+  std::vector<uint16_t> oh(out_elems), ol(out_elems);
+  CK(cudaMemcpy(oh.data(), doh, out_elems * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ol.data(), dol, out_elems * 2, cudaMemcpyDeviceToHost));
+  // CPU reference on the values the GPU sees
+  std::vector<float> xn(img_elems);
+  for (size_t i = 0; i < img_elems; ++i) {
+    const int c = (i / (224 * 224)) % 3;
+    const float x = static_cast<float>(img[i]) * 0.00392156862745098f;
+    const float v = (x - mean[c]) / stdv[c];
+    const uint16_t h = f2bf(v);
+    xn[i] = split ? bf2f(h) + bf2f(f2bf(v - bf2f(h))) : bf2f(h);
+  }
+  std::vector<float> we(w.size());
+  for (size_t i = 0; i < w.size(); ++i) {
+    const uint16_t h = f2bf(w[i]);
+    we[i] = split ? bf2f(h) + bf2f(f2bf(w[i] - bf2f(h))) : bf2f(h);
+  }
+  double max_err = 0, max_ref = 0;
+  size_t checked = 0;
+  for (size_t idx = 0; idx < out_elems; idx += 53) {
+    const int co = idx % 64;
+    size_t pix = idx / 64;
+    const int ow = pix % 112, oh_ = (pix / 112) % 112, n = pix / (112 * 112);
+    double acc = 0;
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 7; ++r) {
+        const int ih = oh_ * 2 + r - 3;
+        if (ih < 0 || ih >= 224) continue;
+        for (int s = 0; s < 7; ++s) {
+          const int iw = ow * 2 + s - 3;
+          if (iw < 0 || iw >= 224) continue;
+          acc += static_cast<double>(xn[((static_cast<size_t>(n) * 3 + c) * 224 + ih) * 224 + iw]) *
+                 we[((co * 3 + c) * 7 + r) * 7 + s];
+        }
+      }
+    const double got = split ? static_cast<double>(bf2f(oh[idx])) + bf2f(ol[idx]) : bf2f(oh[idx]);
+    const double err = std::fabs(got - acc);
+    if (!(err <= 1e30)) max_err = 1e30;
+    if (err > max_err) max_err = err;
+    if (std::fabs(acc) > max_ref) max_ref = std::fabs(acc);
+    ++checked;
+  }
+  const bool ok = max_err <= (split ? 2e-4 : 6e-2) * (max_ref > 1 ? max_ref : 1);
+  printf("[stem N=%d split=%d] box=(%d,%d,%d) tiles=%d : max_err=%.3e (max_ref=%.2f, checked=%zu) %.3f ms %.1f TFLOP/s(alg) %s\n",
+         N, split, p.box_w, p.box_h, p.box_n, p.tiles_w * p.tiles_h * p.tiles_n, max_err, max_ref, checked, ms,
+         2.0 * out_elems * 147 / ms * 1e-9, ok ? "OK" : "FAIL");
+  cudaFree(dimg); cudaFree(dwh); cudaFree(dwl); cudaFree(dph); cudaFree(dpl); cudaFree(doh); cudaFree(dol);
+  return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -211,6 +310,10 @@ int main(int argc, char** argv) {
       {"perf_l3_1x1b", 240, 14,  14, 256, 1024, 1, 1, 1, 1, 1, 0},
       {"perf_l3_3x3f", 240, 14,  14, 256,  256, 3, 1, 1, 0, 0, 0},
       {"perf_l1_3x3",  240, 56,  56,  64,   64, 3, 1, 1, 0, 1, 0},
+      {"perf_l1_c3",   240, 56,  56,  64,  256, 1, 1, 1, 1, 1, 0},
+      {"perf_l2_c3",   240, 28,  28, 128,  512, 1, 1, 1, 1, 1, 0},
+      {"perf_l1_c1",   240, 56,  56, 256,   64, 1, 1, 1, 0, 1, 0},
+      {"perf_l3_c3f",  240, 14,  14, 256, 1024, 1, 1, 1, 1, 0, 0},
   };
   int only = argc > 1 ? atoi(argv[1]) : -1;
   int fails = 0;
@@ -218,6 +321,11 @@ int main(int argc, char** argv) {
     if (only >= 0 && static_cast<int>(i) != only) continue;
     fails += run_case(cases[i], sms);
     fflush(stdout);
+  }
+  if (only < 0 || only >= 100) {
+    fails += run_stem(3, 1, sms);
+    fails += run_stem(2, 0, sms);
+    fails += run_stem(240, 1, sms);
   }
   printf("%s (%d failures)\n", fails ? "SOME FAILED" : "ALL OK", fails);
   return fails ? 1 : 0;
