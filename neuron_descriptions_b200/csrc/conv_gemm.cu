@@ -1,11 +1,12 @@
 // tcgen05 implicit-GEMM convolution kernel (see conv_gemm.h for the contract).
 //
-// CTA = 7 warps, persistent over output tiles (static round-robin):
+// CTA = 11 warps, persistent over output tiles (static round-robin):
 //   warp 0      : TMA producer  (A boxes per tap / k-block, B weight tiles) -> smem ring, mbarrier full/empty
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer -> fp32 accumulators in TMEM (2 buffers)
-//   warps 2..5  : epilogue: tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo split -> swizzled smem ->
-//                 TMA store (EPI_BF16), or fp32 direct stores (EPI_F32)
-//   warp 6      : residual prefetcher: TMA-loads the residual tile of each 64-column chunk into a 2-deep ring
+//   warps 2..9  : epilogue, two groups of 4 warps (one warp per TMEM lane quarter and group; group g owns columns
+//                 [32g, 32g+32) of every 64-column chunk): tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo
+//                 split -> swizzled smem -> TMA store (EPI_BF16), or fp32 direct stores (EPI_F32)
+//   warp 10     : residual prefetcher: TMA-loads the residual tile of each 64-column chunk into a 2-deep ring
 // The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "conv_gemm.h"
 #include "ptx.cuh"
@@ -19,7 +20,8 @@ namespace milan {
 
 namespace {
 
-constexpr int kNumThreads = 224;
+constexpr int kNumThreads = 352;
+constexpr int kEpiThreads = 256;
 constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KiB: one 128-row x 64-col bf16 plane
 constexpr int kSmemBudget = 224 * 1024;
 
@@ -84,9 +86,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], kEpiThreads);
       mbar_init(&res_full_bar[s], 1);
-      mbar_init(&res_empty_bar[s], 128);
+      mbar_init(&res_empty_bar[s], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
     }
     __syncwarp();
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ------------------------------------------------------------ residual prefetcher
     if (EPI == EPI_BF16 && HAS_RES && lane == 0) {
       int rb = 0;
@@ -207,8 +209,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int group = (warp - 2) >> 2;     // which 32-column half of each 64-column chunk
     const int row = quarter * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
     int iter = 0;
@@ -239,27 +242,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         for (int c = 0; c < kChunks; ++c) {
           const int col0 = n_tile * BLOCK_N + c * 64;
           const bool active = col0 < p.cout;  // uniform across the CTA
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 64 + group * 32, acc);
           if (active && HAS_RES) mbar_wait(&res_full_bar[rb], rphase);
           // previous TMA store must have finished reading the staging tile before it is overwritten
           if (leader) tma_store_wait_read<0>();
-          named_bar_sync(1, 128);
-          const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kABytes);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t acc[32];
-            tmem_ld_32x32(taddr + c * 64 + half * 32, acc);
-            tmem_ld_wait();
-            if (c == kChunks - 1 && half == 1) {
-              // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
-              tcgen05_fence_before();
-              mbar_arrive(&tmem_empty_bar[as]);
-            }
-            if (!active) continue;
+          named_bar_sync(1, kEpiThreads);
+          tmem_ld_wait();
+          if (c == kChunks - 1) {
+            // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty_bar[as]);
+          }
+          if (active) {
+            const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kABytes);
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
             if (p.bias != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + half * 32);
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + group * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b = __ldg(b4 + j);
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               for (int pl = 0; pl < L::kPlanes; ++pl) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(rsrc + pl * kABytes + swz(row, half * 4 + j));
+                  const uint4 r = *reinterpret_cast<const uint4*>(rsrc + pl * kABytes + swz(row, group * 4 + j));
                   v[8 * j + 0] += bf16_lo_to_f32(r.x); v[8 * j + 1] += bf16_hi_to_f32(r.x);
                   v[8 * j + 2] += bf16_lo_to_f32(r.y); v[8 * j + 3] += bf16_hi_to_f32(r.y);
                   v[8 * j + 4] += bf16_lo_to_f32(r.z); v[8 * j + 5] += bf16_hi_to_f32(r.z);
@@ -285,28 +286,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             }
             uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[2 * j], h0, l0);
-              split_bf16(v[2 * j + 1], h1, l1);
-              hi[j] = pack_bf16x2(h0, h1);
-              lo[j] = pack_bf16x2(l0, l1);
-            }
+            for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(staging + swz(row, half * 4 + j)) =
+              *reinterpret_cast<uint4*>(staging + swz(row, group * 4 + j)) =
                   make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
               if (SPLIT)
-                *reinterpret_cast<uint4*>(staging + kABytes + swz(row, half * 4 + j)) =
+                *reinterpret_cast<uint4*>(staging + kABytes + swz(row, group * 4 + j)) =
                     make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
-          }
-          if (active && HAS_RES) {
-            mbar_arrive(&res_empty_bar[rb]);  // residual chunk consumed
-            if (++rb == 2) { rb = 0; rphase ^= 1; }
+            if (HAS_RES) {
+              mbar_arrive(&res_empty_bar[rb]);  // residual chunk consumed
+              if (++rb == 2) { rb = 0; rphase ^= 1; }
+            }
           }
           fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
           if (leader && active) {
             tma_store_4d(&p.tmap_out[0], staging, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
             if (SPLIT) tma_store_4d(&p.tmap_out[1], staging + kABytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
@@ -318,7 +313,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const bool valid = row_in_box && w < p.out_w && h < p.out_h && n < p.out_n;
         const long long pix = (static_cast<long long>(n) * p.out_h + h) * p.out_w + w;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int c0 = group * 32; c0 < BLOCK_N; c0 += 64) {
           uint32_t acc[32];
           tmem_ld_32x32(taddr + c0, acc);
           tmem_ld_wait();

@@ -65,8 +65,10 @@ __global__ void init_finish_kernel(const float* __restrict__ pre, int B, int H, 
 }
 
 // ------------------------------------------------------------------ attention + gating + LSTM input assembly
-// One CTA (256 threads) per row.
-__global__ void __launch_bounds__(256) attend_kernel(const AttendArgs a) {
+// Kernel 1 (one CTA per row): attention scores + softmax over keys (Attention.forward, decoders.py:57-73) and the
+// token embedding (decoders.py:618). Kernel 2 (one CTA per feature set x column slice): attenuate + gate
+// (decoders.py:613-615); the feature tile is read once per neuron and reused by all of its beam rows.
+__global__ void __launch_bounds__(256) attn_scores_kernel(const AttendArgs a, float* __restrict__ attn_ws) {
   extern __shared__ float sm[];
   float* q_s = sm;                 // [A]
   float* sc_s = sm + a.A;          // [n_keys]
@@ -76,7 +78,6 @@ __global__ void __launch_bounds__(256) attend_kernel(const AttendArgs a) {
   const float* qrow = a.qg + static_cast<long long>(r) * a.qg_pitch;
   for (int i = threadIdx.x; i < a.A; i += blockDim.x) q_s[i] = qrow[i];
   __syncthreads();
-  // scores: warp w handles keys w, w+8, ...  (Attention.forward, decoders.py:69-73)
   for (int k = warp; k < a.n_keys; k += 8) {
     const float* khr = a.kh + (static_cast<long long>(fidx) * a.n_keys + k) * a.A;
     float s = 0.f;
@@ -86,38 +87,78 @@ __global__ void __launch_bounds__(256) attend_kernel(const AttendArgs a) {
     if (lane == 0) sc_s[k] = s + a.b_o;
   }
   __syncthreads();
-  // softmax over keys (every thread redundantly; n_keys is small)
   float mx = -INFINITY;
   for (int k = 0; k < a.n_keys; ++k) mx = fmaxf(mx, sc_s[k]);
   float den = 0.f;
   for (int k = 0; k < a.n_keys; ++k) den += expf(sc_s[k] - mx);
-  __syncthreads();
   for (int k = threadIdx.x; k < a.n_keys; k += blockDim.x) {
     const float w = expf(sc_s[k] - mx) / den;
-    sc_s[k] = w;
+    attn_ws[static_cast<long long>(r) * a.n_keys + k] = w;
     if (a.attn_out != nullptr) a.attn_out[static_cast<long long>(r) * a.attn_pitch + k] = w;
   }
-  __syncthreads();
-  // attenuated = sum_k a_k f_k ; gated = attenuated * sigmoid(W_g h + b_g)   (decoders.py:613-615)
-  const float* fb = a.features + static_cast<long long>(fidx) * a.n_keys * a.F;
-  const float* gate_pre = qrow + a.A;
   const long long xoff = static_cast<long long>(r) * a.x_pitch;
-  for (int j2 = threadIdx.x; j2 < a.F / 2; j2 += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int k = 0; k < a.n_keys; ++k) {
-      const float2 v = __ldg(reinterpret_cast<const float2*>(fb + static_cast<long long>(k) * a.F + 2 * j2));
-      const float w = sc_s[k];
-      s0 += w * v.x;
-      s1 += w * v.y;
-    }
-    const float2 g = *reinterpret_cast<const float2*>(gate_pre + 2 * j2);
-    store_split2(a.x_hi, a.x_lo, xoff + a.E + 2 * j2, s0 * sigmoidf_(g.x), s1 * sigmoidf_(g.y));
-  }
-  // embedding of the input token (decoders.py:618)
   const float* erow = a.embedding + a.tokens[r] * a.E;
   for (int e2 = threadIdx.x; e2 < a.E / 2; e2 += blockDim.x) {
     const float2 v = *reinterpret_cast<const float2*>(erow + 2 * e2);
     store_split2(a.x_hi, a.x_lo, xoff + 2 * e2, v.x, v.y);
+  }
+}
+
+constexpr int kApplyKeys = 16;  // keys held in registers per pass
+__global__ void __launch_bounds__(256) attn_apply_kernel(const AttendArgs a, const float* __restrict__ attn_ws) {
+  extern __shared__ float w_s[];  // [rows_per_feature][n_keys]
+  const int fidx = blockIdx.x;
+  const int j2 = blockIdx.y * blockDim.x + threadIdx.x;
+  const int rpf = a.rows_per_feature;
+  const long long row0 = static_cast<long long>(fidx) * rpf;
+  for (int i = threadIdx.x; i < rpf * a.n_keys; i += blockDim.x) w_s[i] = attn_ws[row0 * a.n_keys + i];
+  __syncthreads();
+  if (j2 >= a.F / 2) return;
+  const float* fb = a.features + static_cast<long long>(fidx) * a.n_keys * a.F + 2 * j2;
+  for (int k0 = 0; k0 < a.n_keys; k0 += kApplyKeys) {
+    float2 f[kApplyKeys];
+#pragma unroll
+    for (int k = 0; k < kApplyKeys; ++k)
+      f[k] = (k0 + k < a.n_keys) ? __ldg(reinterpret_cast<const float2*>(fb + static_cast<long long>(k0 + k) * a.F))
+                                 : make_float2(0.f, 0.f);
+    if (a.n_keys <= kApplyKeys) {
+      // common case (k = 15 exemplars): a single pass, results go straight to the LSTM operand
+      for (int r = 0; r < rpf; ++r) {
+        const float* w = w_s + r * a.n_keys;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kApplyKeys; ++k) {
+          if (k < a.n_keys) {
+            s0 += w[k] * f[k].x;
+            s1 += w[k] * f[k].y;
+          }
+        }
+        const float2 g = *reinterpret_cast<const float2*>(a.qg + (row0 + r) * a.qg_pitch + a.A + 2 * j2);
+        store_split2(a.x_hi, a.x_lo, (row0 + r) * a.x_pitch + a.E + 2 * j2, s0 * sigmoidf_(g.x), s1 * sigmoidf_(g.y));
+      }
+    } else {
+      // many keys (e.g. a spatial encoder's k*49): accumulate per row across passes in the gate buffer
+      for (int r = 0; r < rpf; ++r) {
+        const float* w = w_s + r * a.n_keys + k0;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kApplyKeys; ++k) {
+          if (k0 + k < a.n_keys) {
+            s0 += w[k] * f[k].x;
+            s1 += w[k] * f[k].y;
+          }
+        }
+        float* acc = const_cast<float*>(a.acc_ws) + (row0 + r) * a.F + 2 * j2;
+        if (k0 > 0) { s0 += acc[0]; s1 += acc[1]; }
+        if (k0 + kApplyKeys < a.n_keys) {
+          acc[0] = s0; acc[1] = s1;
+        } else {
+          const float2 g = *reinterpret_cast<const float2*>(a.qg + (row0 + r) * a.qg_pitch + a.A + 2 * j2);
+          store_split2(a.x_hi, a.x_lo, (row0 + r) * a.x_pitch + a.E + 2 * j2, s0 * sigmoidf_(g.x),
+                       s1 * sigmoidf_(g.y));
+        }
+      }
+    }
   }
 }
 
@@ -209,6 +250,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// order-preserving float -> uint key (larger float <-> larger key)
+__device__ __forceinline__ unsigned float_key(float x) {
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 // log_softmax of one row into shared memory; returns nothing, pred_s[v] filled. (decoders.py:621, :624-630)
 __device__ __forceinline__ void row_log_softmax(const float* __restrict__ x, int V, float* pred_s, float* red,
                                                 float scale_sub, bool subtract) {
@@ -272,25 +319,85 @@ __global__ void __launch_bounds__(256) row_kernel(const RowArgs a) {
     }
     return;
   }
-  ValIdx mine{-INFINITY, 0x7fffffff};
-  for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
-    const ValIdx c{pred_s[v], v};
-    if (better(c, mine)) mine = c;
+  // Exact top-`beam` by MSB radix select on order-preserving keys (4 passes of 8 bits), then rank the survivors.
+  __shared__ unsigned hist[256];
+  __shared__ unsigned warp_tot[8];
+  __shared__ unsigned sel_digit, sel_need;
+  __shared__ int n_gt, n_eq;
+  __shared__ float cval[kMaxBeam];
+  __shared__ int cidx[kMaxBeam];
+  __shared__ int eqidx[kMaxBeam];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned prefix = 0, need = static_cast<unsigned>(a.beam);
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
+      const unsigned k = float_key(pred_s[v]);
+      if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    // inclusive suffix sum over digits (thread t <-> digit t)
+    const unsigned own = hist[threadIdx.x];
+    unsigned suf = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    if (lane == 0) warp_tot[warp] = suf;
+    __syncthreads();
+    for (int w = warp + 1; w < 8; ++w) suf += warp_tot[w];
+    const unsigned excl = suf - own;
+    if (excl < need && suf >= need) {
+      sel_digit = threadIdx.x;
+      sel_need = need - excl;
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | sel_digit;
+    need = sel_need;
   }
-  for (int j = 0; j < a.beam; ++j) {
-    const ValIdx best = block_argmax(mine, redvi);
-    if (threadIdx.x == 0) {
-      cv[j] = best.v + lp;
-      cc[j] = best.i;
+  // prefix = key of the beam-th largest value; `need` of the elements equal to it are taken (lowest indices first)
+  if (threadIdx.x == 0) { n_gt = 0; n_eq = 0; }
+  __syncthreads();
+  for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
+    const float x = pred_s[v];
+    const unsigned k = float_key(x);
+    if (k > prefix) {
+      const int pos = atomicAdd(&n_gt, 1);
+      cval[pos] = x;
+      cidx[pos] = v;
+    } else if (k == prefix) {
+      const int pos = atomicAdd(&n_eq, 1);
+      if (pos < kMaxBeam) eqidx[pos] = v;
     }
-    if (best.i != 0x7fffffff && (best.i % blockDim.x) == threadIdx.x) {
-      pred_s[best.i] = -INFINITY;
-      mine = ValIdx{-INFINITY, 0x7fffffff};
-      for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
-        const ValIdx c{pred_s[v], v};
-        if (better(c, mine)) mine = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int base = n_gt;
+    const int take = static_cast<int>(need);
+    if (n_eq <= kMaxBeam) {
+      for (int i = 1; i < n_eq; ++i) {  // insertion sort by index (n_eq is almost always 1)
+        const int x = eqidx[i];
+        int j = i - 1;
+        while (j >= 0 && eqidx[j] > x) { eqidx[j + 1] = eqidx[j]; --j; }
+        eqidx[j + 1] = x;
       }
+      for (int i = 0; i < take; ++i) { cidx[base + i] = eqidx[i]; cval[base + i] = pred_s[eqidx[i]]; }
+    } else {  // many exact ties (e.g. -inf logits): lowest indices by a linear scan
+      int got = 0;
+      for (int v = 0; v < a.V && got < take; ++v)
+        if (float_key(pred_s[v]) == prefix) { cidx[base + got] = v; cval[base + got] = pred_s[v]; ++got; }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.beam; i += blockDim.x) {
+    const ValIdx me{cval[i], cidx[i]};
+    int rank = 0;
+    for (int j = 0; j < a.beam; ++j) rank += better(ValIdx{cval[j], cidx[j]}, me) ? 1 : 0;
+    cv[rank] = me.v + lp;
+    cc[rank] = me.i;
   }
 }
 
@@ -467,8 +574,13 @@ int launch_init_finish(const float* pre, int B, int H, float* h, float* c, __nv_
 }
 int launch_attend(const AttendArgs& a, cudaStream_t stream) {
   if (a.R == 0) return 0;
-  const size_t smem = (a.A + a.n_keys) * sizeof(float);
-  attend_kernel<<<a.R, 256, smem, stream>>>(a);
+  if (a.n_keys > kApplyKeys && a.acc_ws == nullptr) return static_cast<int>(cudaErrorInvalidValue);
+  const size_t smem1 = (a.A + a.n_keys) * sizeof(float);
+  attn_scores_kernel<<<a.R, 256, smem1, stream>>>(a, a.attn_ws);
+  note_launch();
+  const size_t smem2 = static_cast<size_t>(a.rows_per_feature) * a.n_keys * sizeof(float);
+  dim3 grid(a.R / a.rows_per_feature, (a.F / 2 + 255) / 256);
+  attn_apply_kernel<<<grid, 256, smem2, stream>>>(a, a.attn_ws);
   return last_err();
 }
 int launch_lstm_point(const LstmPointArgs& a, cudaStream_t stream) {

@@ -36,6 +36,8 @@ struct AttendArgs {
   long long x_pitch;
   float* attn_out;        // [R][attn_pitch] or nullptr
   long long attn_pitch;
+  float* attn_ws;         // workspace [R][n_keys]
+  const float* acc_ws;    // workspace [R][F], only needed when n_keys > 16
 };
 int launch_attend(const AttendArgs& a, cudaStream_t stream);
 

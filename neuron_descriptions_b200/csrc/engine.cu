@@ -132,7 +132,7 @@ struct MilanEngine {
   float *kh = nullptr, *init_pre = nullptr, *qg = nullptr, *gates = nullptr, *hnew_f32 = nullptr, *c = nullptr,
         *cnew = nullptr, *logits = nullptr, *logits_lm = nullptr, *cand_val = nullptr, *last_lp = nullptr,
         *next_lp = nullptr, *lm_c0 = nullptr, *lm_c1 = nullptr, *lm_c0n = nullptr, *lm_c1n = nullptr,
-        *lm_scores = nullptr, *feat_enc = nullptr, *out_scores = nullptr, *greedy_scores = nullptr, *lm_h_f32 = nullptr;
+        *lm_scores = nullptr, *feat_enc = nullptr, *out_scores = nullptr, *attn_ws = nullptr, *attn_acc = nullptr, *greedy_scores = nullptr, *lm_h_f32 = nullptr;
   int *cand_cls = nullptr, *backptr = nullptr, *hist_tok = nullptr, *hist_bp = nullptr, *group_T = nullptr;
   long long *tok_cur = nullptr, *tok_next = nullptr, *seqs = nullptr, *lm_inputs = nullptr, *out_tokens = nullptr;
   std::map<std::pair<int, long long>, Plan> gemm_plans;  // (which, M)
@@ -438,6 +438,8 @@ int MilanEngine::alloc_workspace() {
   if (dalloc(&init_pre, R * 2 * H)) return 1;
   if (dalloc2(Alstm, R * (E + F + H))) return 1;
   if (dalloc(&qg, R * (A + F))) return 1;
+  if (dalloc(&attn_ws, R * std::max(Kk, 64))) return 1;
+  if (Kk > 16 && dalloc(&attn_acc, R * F)) return 1;
   if (dalloc(&gates, R * 4 * std::max(H, cfg.lm_hidden_size))) return 1;
   if (dalloc2(hnew, R * H)) return 1;
   if (dalloc(&hnew_f32, R * H)) return 1;
@@ -660,6 +662,7 @@ int MilanEngine::step_core(int R, int rpf, int n_keys, const float* d_features, 
   aa.R = R; aa.rows_per_feature = rpf; aa.n_keys = n_keys; aa.A = A; aa.F = F; aa.E = E;
   aa.x_hi = Alstm[0]; aa.x_lo = Alstm[1]; aa.x_pitch = xp;
   aa.attn_out = attn_out; aa.attn_pitch = attn_pitch;
+  aa.attn_ws = attn_ws; aa.acc_ws = n_keys > 16 ? attn_acc : nullptr;
   RC(launch_attend(aa, st));
   if (gemm(G_LSTM, R, W2, b2, Alstm[0], Alstm[1], xp, static_cast<int>(xp), gates, 4 * H, st)) return 1;
   LstmPointArgs la{};
