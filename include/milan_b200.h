@@ -97,11 +97,13 @@ int milan_decode_greedy(MilanEngine* engine, const float* d_features, int32_t B,
 /* Beam search + optional LM rerank of Decoder.forward (src/milan/decoders.py:465-512; allennlp 2.10 BeamSearch
  * semantics). group_size = the reference DataLoader batch size (decoders.py:814): the
  * reference's early exit, and through it the LM mask, depends on which neurons share a batch.
+ * mi != 0: MI beam decoding (the LM is advanced inside the loop and its state follows the beam backpointers,
+ * decoders.py:170-175,192-196,624-630); incompatible with rerank (decoders.py:395-396).
  * Outputs: d_beam_tokens_out (B,beam,length) int64 (columns >= steps are <stop>), d_beam_scores_out (B,beam),
  * d_group_steps_out (ceil(B/group_size)) int32 = T the reference would return for each group,
  * and if rerank != 0: d_tokens_out (B,length), d_scores_out (B), d_lm_scores_out (B,beam) (may be NULL). */
 int milan_decode_beam(MilanEngine* engine, const float* d_features, int32_t B, int32_t n_keys, int32_t length,
-                      int32_t beam, int32_t group_size, int32_t rerank, float temperature,
+                      int32_t beam, int32_t group_size, int32_t rerank, int32_t mi, float temperature,
                       int64_t* d_beam_tokens_out, float* d_beam_scores_out, int32_t* d_group_steps_out,
                       int64_t* d_tokens_out, float* d_scores_out, float* d_lm_scores_out, void* stream);
 

@@ -37,7 +37,8 @@ SIGNATURES = {
                              c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     'milan_decode_greedy': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'milan_decode_beam': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
+    'milan_decode_beam': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'milan_lm_score': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     'milan_describe_host': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
@@ -77,6 +78,7 @@ def check(status: int):
     if status != 0:
         message = load().milan_last_error().decode('utf-8', 'replace')
         # Argument errors mirror the reference's ValueErrors (src/milan/decoders.py:395-409, :605-608).
-        if any(key in message for key in ('cannot use MI', 'state must have', 'state has h_lm', 'too small relative')):
+        if any(key in message for key in ('cannot use MI', 'cannot set `mi=`', 'state must have', 'state has h_lm',
+                                          'too small relative')):
             raise ValueError(message)
         raise MilanError(message)

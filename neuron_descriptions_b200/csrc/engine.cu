@@ -210,7 +210,7 @@ struct MilanEngine {
   int decode_greedy(const float* d_features, int B, int n_keys, int length, int mi, float temperature,
                     const long long* d_forced, long long* d_tokens_out, float* d_scores_out, float* d_pred_out,
                     float* d_attn_out, cudaStream_t st);
-  int decode_beam(const float* d_features, int B, int n_keys, int length, int beam, int group_size, int rerank,
+  int decode_beam(const float* d_features, int B, int n_keys, int length, int beam, int group_size, int rerank, int mi,
                   float temperature, long long* d_beam_tokens, float* d_beam_scores, int* d_group_steps,
                   long long* d_tokens_out, float* d_scores_out, float* d_lm_scores_out, cudaStream_t st);
   int lm_score_seqs(const long long* d_seqs, int M, int length, int beam, int group_size, cudaStream_t st);
@@ -789,7 +789,7 @@ int MilanEngine::lm_score_seqs(const long long* d_seqs, int M, int length, int b
 }
 
 int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int length, int beam, int group_size,
-                             int rerank, float temperature, long long* d_beam_tokens, float* d_beam_scores,
+                             int rerank, int mi, float temperature, long long* d_beam_tokens, float* d_beam_scores,
                              int* d_group_steps, long long* d_tokens_out, float* d_scores_out, float* d_lm_scores_out,
                              cudaStream_t st) {
   const int V = cfg.vocab_size, H = cfg.hidden_size, E = cfg.embedding_size, F = cfg.feature_size;
@@ -798,18 +798,23 @@ int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int len
   if (B > Bmax) return fail("decode_beam: B=%d exceeds max_neurons %d", B, Bmax);
   if (static_cast<size_t>(B) * n_keys > FRcap) return fail("decode_beam: too many feature rows");
   if (length > cfg.max_length) return fail("length %d exceeds max_length %d", length, cfg.max_length);
-  if (rerank && !cfg.has_lm) return fail("cannot use MI/rerank decoding without an LM");
+  if ((rerank || mi) && !cfg.has_lm) return fail("cannot use MI/rerank decoding without an LM");
+  if (rerank && mi) return fail("cannot set `mi=` decoding when reranking");
   if (group_size <= 0) group_size = B;
   const int R = B * beam;
   if (prepare_features(d_features, B, n_keys, st)) return 1;
   if (init_state_impl(this, d_features, B, n_keys, nullptr, nullptr, st)) return 1;
   RC(launch_fill_i64(tok_cur, cfg.start_index, B, st));
+  if (mi && lm_reset(R, st)) return 1;
+  const int Hl = cfg.lm_hidden_size, El = cfg.lm_embedding_size;
   for (int t = 0; t < length; ++t) {
     const int rows = t == 0 ? B : R;
     const int rpf = t == 0 ? 1 : beam;
     if (step_core(rows, rpf, n_keys, d_features, tok_cur, nullptr, 0, st)) return 1;
+    if (mi && lm_step_core(rows, tok_cur, true, st)) return 1;
     RowArgs ra{};
-    ra.logits = logits; ra.ld = ldv; ra.R = rows; ra.V = V; ra.temperature = temperature;
+    ra.logits = logits; ra.logits_lm = mi ? logits_lm : nullptr; ra.ld = ldv; ra.R = rows; ra.V = V;
+    ra.temperature = temperature;
     ra.beam = beam; ra.last_tokens = tok_cur; ra.last_lp = t == 0 ? nullptr : last_lp;
     ra.stop_index = cfg.stop_index; ra.cand_val = cand_val; ra.cand_cls = cand_cls;
     RC(launch_row_logsoftmax(ra, st));
@@ -824,6 +829,20 @@ int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int len
     ga.dst_hi = Alstm[0] + E + F; ga.dst_lo = split ? Alstm[1] + E + F : nullptr; ga.dst_pitch = E + F + H;
     ga.c_src = cnew; ga.c_dst = c;
     RC(launch_gather_state(ga, st));
+    if (mi) {  // the LM state follows the same backpointers (AllenNLPDecoderState h_lm / c_lm)
+      GatherArgs g0{};
+      g0.backptr = backptr; g0.R = R; g0.H = Hl;
+      g0.src_hi = lmnew0[0]; g0.src_lo = lmnew0[1]; g0.src_pitch = Hl;
+      g0.dst_hi = Alm0[0] + El; g0.dst_lo = split ? Alm0[1] + El : nullptr; g0.dst_pitch = El + Hl;
+      g0.c_src = lm_c0n; g0.c_dst = lm_c0;
+      RC(launch_gather_state(g0, st));
+      GatherArgs g1{};
+      g1.backptr = backptr; g1.R = R; g1.H = Hl;
+      g1.src_hi = lmnew1[0]; g1.src_lo = lmnew1[1]; g1.src_pitch = Hl;
+      g1.dst_hi = Alm1[0] + Hl; g1.dst_lo = split ? Alm1[1] + Hl : nullptr; g1.dst_pitch = 2 * Hl;
+      g1.c_src = lm_c1n; g1.c_dst = lm_c1;
+      RC(launch_gather_state(g1, st));
+    }
     std::swap(tok_cur, tok_next);
     std::swap(last_lp, next_lp);
   }
@@ -1007,11 +1026,11 @@ int milan_decode_greedy(MilanEngine* engine, const float* d_features, int32_t B,
 }
 
 int milan_decode_beam(MilanEngine* engine, const float* d_features, int32_t B, int32_t n_keys, int32_t length,
-                      int32_t beam, int32_t group_size, int32_t rerank, float temperature,
+                      int32_t beam, int32_t group_size, int32_t rerank, int32_t mi, float temperature,
                       int64_t* d_beam_tokens_out, float* d_beam_scores_out, int32_t* d_group_steps_out,
                       int64_t* d_tokens_out, float* d_scores_out, float* d_lm_scores_out, void* stream) {
   CHECK_READY(engine);
-  return engine->decode_beam(d_features, B, n_keys, length, beam, group_size, rerank, temperature,
+  return engine->decode_beam(d_features, B, n_keys, length, beam, group_size, rerank, mi, temperature,
                              reinterpret_cast<long long*>(d_beam_tokens_out), d_beam_scores_out, d_group_steps_out,
                              reinterpret_cast<long long*>(d_tokens_out), d_scores_out, d_lm_scores_out,
                              static_cast<cudaStream_t>(stream));
@@ -1070,7 +1089,8 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
       if (e->decode_greedy(e->feat_enc, nb, k, length, mi, temperature, nullptr, d_tok, e->out_scores, nullptr, nullptr, st))
         return 1;
     } else {
-      if (e->decode_beam(e->feat_enc, nb, k, length, beam, group_size, strategy == 2, temperature, nullptr, nullptr,
+      if (e->decode_beam(e->feat_enc, nb, k, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0, temperature,
+                         nullptr, nullptr,
                          nullptr, d_tok, e->out_scores, nullptr, st))
         return 1;
     }

@@ -144,7 +144,7 @@ class Engine:
                                                 _ptr(predictions), _ptr(attentions), _stream(self.device)))
         return tokens, scores, predictions, attentions
 
-    def decode_beam(self, features, length, beam, rerank, temperature, group_size=None):
+    def decode_beam(self, features, length, beam, rerank, temperature, group_size=None, mi=False):
         features = self._f32(features)
         B, n_keys, _ = features.shape
         group_size = group_size or B
@@ -156,7 +156,7 @@ class Engine:
         scores = self._new(B)
         lm_scores = self._new(B, beam) if rerank else None
         _lib.check(self.lib.milan_decode_beam(self.handle, _ptr(features), B, n_keys, length, beam, group_size,
-                                              int(bool(rerank)), float(temperature), _ptr(beam_tokens),
+                                              int(bool(rerank)), int(bool(mi)), float(temperature), _ptr(beam_tokens),
                                               _ptr(beam_scores), _ptr(steps), _ptr(tokens), _ptr(scores),
                                               _ptr(lm_scores), _stream(self.device)))
         return beam_tokens, beam_scores, steps, tokens, scores, lm_scores

@@ -239,12 +239,9 @@ class Decoder:
         elif strategy == STRATEGY_SAMPLE:
             tokens, scores, predictions, attentions = self._sample(features, length, mi, temperature)
         else:
-            if mi:
-                raise NotImplementedError("MI beam decoding (strategy='beam' with an LM and mi=True) is a SURVEY 8(f) "
-                                          "'next' row; pass mi=False or use strategy='rerank'")
             rerank = strategy == STRATEGY_RERANK
             beam_tokens, beam_scores, steps, tokens, scores, _ = engine.decode_beam(
-                features, length, beam_size, rerank, temperature, group_size=group_size or batch_size)
+                features, length, beam_size, rerank, temperature, group_size=group_size or batch_size, mi=mi)
             if group_size is None or group_size >= batch_size:
                 # the reference returns only the T <= length columns produced before its early exit
                 T = int(steps[0].item())

@@ -90,6 +90,7 @@ def main():
             beam = decoder(feats, strategy='beam', mi=False, beam_size=50)
             rerank = decoder(feats, strategy='rerank', beam_size=50)
             small_beam = decoder(feats, strategy='rerank', beam_size=7, length=9)
+            beam_mi = decoder(feats, strategy='beam', beam_size=10)  # mi defaults to True (decoders.py:385-387)
             inputs_lm = torch.cat([torch.full((DEC_NEURONS * 50, 1), decoder.indexer.start_index, dtype=torch.long),
                                    beam.beam_tokens.view(DEC_NEURONS * 50, -1)], dim=-1)
             lm_scores = decoder.lm(inputs_lm, reduce=True)
@@ -109,6 +110,7 @@ def main():
             small_beam_tokens=small_beam.beam_tokens.numpy(), small_beam_scores=small_beam.beam_scores.numpy(),
             small_rerank_tokens=small_beam.tokens.numpy(), small_rerank_scores=small_beam.scores.numpy(),
             lm_scores=lm_scores.numpy(),
+            beam_mi_tokens=beam_mi.beam_tokens.numpy(), beam_mi_scores=beam_mi.beam_scores.numpy(),
             captions=np.array(rerank.captions), greedy_captions=np.array(greedy.captions),
             meta=np.array([DEC_NEURONS, K, stop_index], dtype=np.int64))
         print(f'decoder golden [{name}]: beam T={beam.beam_tokens.shape[-1]} rerank[0]={rerank.captions[0]!r} '

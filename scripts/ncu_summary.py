@@ -61,4 +61,36 @@ def full(path, out):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+
+
+def traffic(path, out_json):
+    """ncu csv with dram__bytes_{read,write}.sum + gpu__time_duration.sum + tensor pipe % for every conv launch of a
+    step -> profiles/conv_traffic.json (mean DRAM bytes per launch, consumed by bench.py's roofline.traffic)."""
+    import json
+    with open(path) as handle:
+        lines = [line for line in handle if not line.startswith('==')]
+    rows = list(csv.DictReader(lines))
+    per = collections.defaultdict(dict)
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for row in rows:
+        value = float(row['Metric Value'].replace(',', ''))
+        name = row['Metric Name']
+        if name.startswith('dram__bytes'):
+            value *= scale.get(row['Metric Unit'], 1.0)
+        elif name == 'gpu__time_duration.sum':
+            value = to_us(row['Metric Value'], row['Metric Unit'])
+        per[row['ID']][name] = value
+    n = len(per)
+    read = sum(v.get('dram__bytes_read.sum', 0.0) for v in per.values())
+    write = sum(v.get('dram__bytes_write.sum', 0.0) for v in per.values())
+    time_us = sum(v.get('gpu__time_duration.sum', 0.0) for v in per.values())
+    tensor = [v.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active') for v in per.values()]
+    tensor_w = sum(t * v.get('gpu__time_duration.sum', 0.0) for t, v in zip(tensor, per.values()) if t is not None)
+    result = {'source': path, 'launches': n, 'dram_bytes_per_launch': (read + write) / max(n, 1),
+              'dram_read_bytes_total': read, 'dram_write_bytes_total': write, 'time_us_total': time_us,
+              'tensor_pipe_active_pct_time_weighted': tensor_w / max(time_us, 1e-9),
+              'dram_gbs_while_running': (read + write) / max(time_us, 1e-9) / 1e3}
+    with open(out_json, 'w') as handle:
+        json.dump(result, handle, indent=1)
+    print(json.dumps(result, indent=1))

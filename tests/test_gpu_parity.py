@@ -175,6 +175,22 @@ def test_decoder_beam_and_rerank(variant):
         np.testing.assert_array_equal(tok[..., :T].cpu().numpy(), g['small_rerank_tokens'])
 
 
+def test_decoder_mi_beam(variant):
+    """strategy='beam' with an LM defaults to MI decoding: the LM state follows the beam (decoders.py:385-387)."""
+    name, sd, engine, g = variant
+    n, k, _ = g['meta'].tolist()
+    feats = synthetic_features(n, k, seed=0)
+    bt, bs, steps, tok, sc, _ = engine.decode_beam(feats, 15, 10, False, 0.2, mi=True)
+    T = int(steps[0].item())
+    assert T == g['beam_mi_tokens'].shape[-1]
+    np.testing.assert_allclose(bs.cpu().numpy(), g['beam_mi_scores'], atol=LOGP_TOL)
+    if name != 'flat':
+        _tokens_match(bt[..., :T].cpu().numpy(), g['beam_mi_tokens'], bs.cpu().numpy(), g['beam_mi_scores'], 'mi-beam')
+        np.testing.assert_array_equal(tok[..., :T].cpu().numpy(), g['beam_mi_tokens'][:, 0])
+    with pytest.raises(ValueError, match='cannot set `mi=` decoding when reranking'):
+        engine.decode_beam(feats, 15, 10, True, 0.2, mi=True)
+
+
 def test_lm_score_matches_oracle(variant):
     name, sd, engine, g = variant
     gen = torch.Generator().manual_seed(3)

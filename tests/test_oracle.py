@@ -77,6 +77,10 @@ def test_decoder_matches_reference_golden(golden_dir, name):
                            rerank.beam_tokens.view(n * 50, -1)], dim=-1)
     np.testing.assert_allclose(O.lm_forward(inputs_lm, sd, stop_index).numpy(), g['lm_scores'], atol=1e-4)
 
+    beam_mi = O.decode(feats, sd, VOCAB, strategy='beam', beam_size=10)
+    np.testing.assert_array_equal(beam_mi.beam_tokens.numpy(), g['beam_mi_tokens'])
+    np.testing.assert_allclose(beam_mi.beam_scores.numpy(), g['beam_mi_scores'], atol=1e-4)
+
     small = O.decode(feats, sd, VOCAB, strategy='rerank', beam_size=7, length=9)
     np.testing.assert_array_equal(small.beam_tokens.numpy(), g['small_beam_tokens'])
     np.testing.assert_array_equal(small.tokens.numpy(), g['small_rerank_tokens'])
