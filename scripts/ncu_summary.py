@@ -60,8 +60,6 @@ def full(path, out):
     print(open(out).read())
 
 
-if __name__ == '__main__':
-    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
 
 
 def traffic(path, out_json):
@@ -94,3 +92,7 @@ def traffic(path, out_json):
     with open(out_json, 'w') as handle:
         json.dump(result, handle, indent=1)
     print(json.dumps(result, indent=1))
+
+
+if __name__ == '__main__':
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
