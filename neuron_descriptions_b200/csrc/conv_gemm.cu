@@ -7,7 +7,10 @@
 //                 [32g, 32g+32) of every 64-column chunk): tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo
 //                 split -> swizzled smem -> TMA store (EPI_BF16), or fp32 direct stores (EPI_F32)
 //   warp 10     : residual prefetcher: TMA-loads the residual tile of each 64-column chunk into a 2-deep ring
-// The two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of tile i+1.
+// Two-level accumulation: the tensor core's fp32 accumulation truncates (measured: error grows linearly with the
+// number of chained MMAs, 2.5e-5 abs at K=4544), so the MMA warp starts a fresh TMEM accumulator every
+// `kb_per_chunk` k-blocks and the epilogue warps add the partials in fp32 registers (round-to-nearest). 4 TMEM
+// buffers (512 columns at BLOCK_N=128) let partial drains and the final epilogue overlap the next chunks' MMAs.
 #include "conv_gemm.h"
 #include "ptx.cuh"
 
@@ -47,7 +50,8 @@ template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
   constexpr int kStages = L::kStages;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; power of two (128 or 256)
+  constexpr int kTmemBufs = 4;                 // accumulator ring
+  constexpr uint32_t kTmemCols = kTmemBufs * BLOCK_N;  // 512 or 256 columns (power of two)
   constexpr int kChunks = BLOCK_N / 64;        // 64-column epilogue chunks per tile
 
   extern __shared__ uint8_t smem_raw[];
@@ -57,8 +61,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_smem + L::kResBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kTmemBufs;
+  uint64_t* res_full_bar = tmem_empty_bar + kTmemBufs;
   uint64_t* res_empty_bar = res_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
 
@@ -84,9 +88,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kTmemBufs; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], kEpiThreads);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&res_full_bar[s], 1);
       mbar_init(&res_empty_bar[s], kEpiThreads);
     }
@@ -102,6 +108,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int num_kb = p.num_taps * cin_blocks;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
+  const int kb_per_chunk = (p.kb_per_chunk > 0 && p.kb_per_chunk < num_kb) ? p.kb_per_chunk : num_kb;
+  const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -146,37 +154,42 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N);
+      const uint32_t idesc = make_idesc_16bit(kGemmBlockM, BLOCK_N, p.fp16_operands ? 0u : 1u);
       int stage = 0;
       uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-        const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+      uint32_t cc = 0;  // running accumulator-chunk counter: buffer = cc % kTmemBufs, phase = (cc / kTmemBufs) & 1
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int kb = 0;
+        for (int chunk = 0; chunk < num_chunks; ++chunk, ++cc) {
+          const int as = cc % kTmemBufs;
+          const uint32_t aphase = (cc / kTmemBufs) & 1;
+          mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t b_hi = a_hi + L::kPlanes * kABytes;
-          const uint64_t da_hi = make_smem_desc_sw128(a_hi);
-          const uint64_t db_hi = make_smem_desc_sw128(b_hi);
-          const uint64_t da_lo = make_smem_desc_sw128(a_hi + kABytes);
-          const uint64_t db_lo = make_smem_desc_sw128(b_hi + L::kBBytes);
+          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+          const int kb_end = (kb + kb_per_chunk < num_kb) ? kb + kb_per_chunk : num_kb;
+          const int kb_first = kb;
+          for (; kb < kb_end; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t b_hi = a_hi + L::kPlanes * kABytes;
+            const uint64_t da_hi = make_smem_desc_sw128(a_hi);
+            const uint64_t db_hi = make_smem_desc_sw128(b_hi);
+            const uint64_t da_lo = make_smem_desc_sw128(a_hi + kABytes);
+            const uint64_t db_lo = make_smem_desc_sw128(b_hi + L::kBBytes);
 #pragma unroll
-          for (int k = 0; k < kGemmBlockK / 16; ++k) {
-            const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
-            umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (SPLIT) {
-              umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
-              umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+            for (int k = 0; k < kGemmBlockK / 16; ++k) {
+              const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
+              umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
+              if (SPLIT) {
+                umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+              }
             }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kb == kb_end - 1) umma_commit(&tmem_full_bar[as]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[as]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     const int group = (warp - 2) >> 2;     // which 32-column half of each 64-column chunk
     const int row = quarter * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
-    int iter = 0;
+    uint32_t cc = 0;
     int rb = 0;
     uint32_t rphase = 0;
     // EPI_F32 only: row -> output pixel
@@ -224,47 +237,55 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     const int dh = rem / p.box_w;
     const int dw = rem - dh * p.box_w;
     const bool row_in_box = row < box_hw * p.box_n;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int tw = m_tile % p.tiles_w;
       const int th = (m_tile / p.tiles_w) % p.tiles_h;
       const int tn = m_tile / (p.tiles_w * p.tiles_h);
 
-      mbar_wait(&tmem_full_bar[as], aphase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+      // ---- gather the accumulator: this thread owns columns c*64 + group*32 + [0,32) of row `row`
+      float v[kChunks][32];
+      for (int chunk = 0; chunk < num_chunks; ++chunk, ++cc) {
+        const int as = cc % kTmemBufs;
+        const uint32_t aphase = (cc / kTmemBufs) & 1;
+        mbar_wait(&tmem_full_bar[as], aphase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + group * 32;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 64, acc);
+          tmem_ld_wait();
+          if (chunk == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c][j] = __uint_as_float(acc[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c][j] += __uint_as_float(acc[j]);
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty_bar[as]);  // partial drained: the MMA warp may reuse this buffer
+      }
 
       if (EPI == EPI_BF16) {
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           const int col0 = n_tile * BLOCK_N + c * 64;
           const bool active = col0 < p.cout;  // uniform across the CTA
-          uint32_t acc[32];
-          tmem_ld_32x32(taddr + c * 64 + group * 32, acc);
           if (active && HAS_RES) mbar_wait(&res_full_bar[rb], rphase);
           // previous TMA store must have finished reading the staging tile before it is overwritten
           if (leader) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiThreads);
-          tmem_ld_wait();
-          if (c == kChunks - 1) {
-            // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
-            tcgen05_fence_before();
-            mbar_arrive(&tmem_empty_bar[as]);
-          }
           if (active) {
             const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kABytes);
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
             if (p.bias != nullptr) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + group * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b = __ldg(b4 + j);
-                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                v[c][4 * j + 0] += b.x; v[c][4 * j + 1] += b.y; v[c][4 * j + 2] += b.z; v[c][4 * j + 3] += b.w;
               }
             }
             if (HAS_RES) {
@@ -273,20 +294,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const uint4 r = *reinterpret_cast<const uint4*>(rsrc + pl * kABytes + swz(row, group * 4 + j));
-                  v[8 * j + 0] += bf16_lo_to_f32(r.x); v[8 * j + 1] += bf16_hi_to_f32(r.x);
-                  v[8 * j + 2] += bf16_lo_to_f32(r.y); v[8 * j + 3] += bf16_hi_to_f32(r.y);
-                  v[8 * j + 4] += bf16_lo_to_f32(r.z); v[8 * j + 5] += bf16_hi_to_f32(r.z);
-                  v[8 * j + 6] += bf16_lo_to_f32(r.w); v[8 * j + 7] += bf16_hi_to_f32(r.w);
+                  v[c][8 * j + 0] += bf16_lo_to_f32(r.x); v[c][8 * j + 1] += bf16_hi_to_f32(r.x);
+                  v[c][8 * j + 2] += bf16_lo_to_f32(r.y); v[c][8 * j + 3] += bf16_hi_to_f32(r.y);
+                  v[c][8 * j + 4] += bf16_lo_to_f32(r.z); v[c][8 * j + 5] += bf16_hi_to_f32(r.z);
+                  v[c][8 * j + 6] += bf16_lo_to_f32(r.w); v[c][8 * j + 7] += bf16_hi_to_f32(r.w);
                 }
               }
             }
             if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+              for (int j = 0; j < 32; ++j) v[c][j] = fmaxf(v[c][j], 0.0f);
             }
             uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            for (int j = 0; j < 16; ++j) split_bf16x2(v[c][2 * j], v[c][2 * j + 1], hi[j], lo[j]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               *reinterpret_cast<uint4*>(staging + swz(row, group * 4 + j)) =
@@ -312,42 +333,35 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int w = tw * p.box_w + dw, h = th * p.box_h + dh, n = tn * p.box_n + dn;
         const bool valid = row_in_box && w < p.out_w && h < p.out_h && n < p.out_n;
         const long long pix = (static_cast<long long>(n) * p.out_h + h) * p.out_w + w;
-#pragma unroll 1
-        for (int c0 = group * 32; c0 < BLOCK_N; c0 += 64) {
-          uint32_t acc[32];
-          tmem_ld_32x32(taddr + c0, acc);
-          tmem_ld_wait();
-          const int col0 = n_tile * BLOCK_N + c0;
-          if (valid && col0 < p.cout) {
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        for (int c = 0; c < kChunks; ++c) {
+          const int col0 = n_tile * BLOCK_N + c * 64 + group * 32;
+          if (valid && col0 < p.cout) {
             if (p.bias != nullptr) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b = __ldg(b4 + j);
-                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                v[c][4 * j + 0] += b.x; v[c][4 * j + 1] += b.y; v[c][4 * j + 2] += b.z; v[c][4 * j + 3] += b.w;
               }
             }
             if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+              for (int j = 0; j < 32; ++j) v[c][j] = fmaxf(v[c][j], 0.0f);
             }
             float* o = p.out_f32 + pix * p.ldc + col0;
             if (col0 + 32 <= p.cout) {
               float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 8; ++j)
+                o4[j] = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.cout) o[j] = v[j];
+                if (col0 + j < p.cout) o[j] = v[c][j];
             }
           }
         }
-        tcgen05_fence_before();
-        mbar_arrive(&tmem_empty_bar[as]);
       }
     }
     if (EPI == EPI_BF16 && leader) tma_store_wait_all<0>();  // all stores complete before the CTA exits

@@ -38,6 +38,8 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap tmap_res[2];   // [hi|lo] EPI_BF16 + residual: same geometry as tmap_out, TMA load
   int stem_mode;             // 1: A is the 5-D overlapping-window map of the 7x7/2 stem (see build_stem_params)
   int has_res;               // residual add in the epilogue
+  int kb_per_chunk;          // k-blocks accumulated in TMEM before promotion to fp32 registers (0 = all)
+  int fp16_operands;         // 1: A/B planes hold IEEE fp16 bit patterns (decoder GEMMs); 0: bf16 (encoder)
   int box_w, box_h, box_n;   // M tile = box_w*box_h*box_n (<=128) output pixels
   int tiles_w, tiles_h, tiles_n;
   int out_w, out_h, out_n;   // output extents (pixels / images)
@@ -133,6 +135,7 @@ void pack_stem_weights(const float* w, float* packed);
 // a_pitch (elements), W contiguous [N][K]. K must be a multiple of 64. Launch with block_n = 128, EPI_F32.
 int build_gemm_params(ConvGemmParams* p, long long M, int K, int N, const __nv_bfloat16* a_hi,
                       const __nv_bfloat16* a_lo, long long a_pitch, const __nv_bfloat16* w_hi,
-                      const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split);
+                      const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split,
+                      int fp16_operands = 0);
 
 }  // namespace milan

@@ -6,6 +6,11 @@
 
 namespace milan {
 
+// Chained tcgen05 accumulations per TMEM partial (see conv_gemm.cu): 4 k-blocks x 12 MMAs for the encoder convs,
+// 2 k-blocks for the decoder / LM GEMMs whose log-probabilities are compared at 1e-3.
+constexpr int kEncoderKbPerChunk = 4;
+constexpr int kDecoderKbPerChunk = 2;
+
 int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n) {
   memset(p, 0, sizeof(*p));
   if (d.Cin % kGemmBlockK != 0) return -2;
@@ -97,6 +102,7 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
     p->num_taps = t;
   }
   p->a_box_bytes = static_cast<uint32_t>(p->box_w) * p->box_h * p->box_n * kGemmBlockK * 2;
+  p->kb_per_chunk = split ? kEncoderKbPerChunk : 0;
   if (io.out_hi != nullptr) {
     // Output (and residual) tensors [N][Ho][Wo][Cout] addressed with the same M-tile boxes, 64 channels wide.
     const __nv_bfloat16* outs[2] = {io.out_hi, io.out_lo};
@@ -154,6 +160,7 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
   memset(p, 0, sizeof(*p));
   const int O = 112;
   p->stem_mode = 1;
+  p->kb_per_chunk = split ? kEncoderKbPerChunk : 0;
   p->cin = 64;   // one 128-byte k-block per filter row
   p->cout = 64;
   p->n_tiles = 1;
@@ -201,9 +208,12 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
 
 int build_gemm_params(ConvGemmParams* p, long long M, int K, int N, const __nv_bfloat16* a_hi,
                       const __nv_bfloat16* a_lo, long long a_pitch, const __nv_bfloat16* w_hi,
-                      const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split) {
+                      const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split,
+                      int fp16_operands) {
   memset(p, 0, sizeof(*p));
   if (K % kGemmBlockK != 0 || M <= 0) return -2;
+  p->fp16_operands = fp16_operands;
+  p->kb_per_chunk = split ? kDecoderKbPerChunk : 0;
   const int bn_tile = 128;
   p->cin = K;
   p->cout = N;

@@ -13,13 +13,15 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Decoder / LM GEMM operands are stored as IEEE fp16 (hi, lo) pairs: 22 mantissa bits, ~30x tighter than the
+// bf16 pair the encoder uses; safe because every decoder operand is bounded (|x| << 65504). The planes keep the
+// 16-bit `__nv_bfloat16*` pointer type of the shared GEMM plumbing; only the bit patterns differ.
 __device__ __forceinline__ void store_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, float v0,
                                              float v1) {
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(v0, h0, l0);
-  split_bf16(v1, h1, l1);
-  *reinterpret_cast<uint32_t*>(hi + off) = pack_bf16x2(h0, h1);
-  if (lo != nullptr) *reinterpret_cast<uint32_t*>(lo + off) = pack_bf16x2(l0, l1);
+  uint32_t h, l;
+  split_fp16x2(v0, v1, h, l);
+  *reinterpret_cast<uint32_t*>(hi + off) = h;
+  if (lo != nullptr) *reinterpret_cast<uint32_t*>(lo + off) = l;
 }
 
 // ------------------------------------------------------------------ split / mean / init

@@ -6,6 +6,8 @@
 #include "decoder.h"
 #include "encoder.h"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -175,11 +177,19 @@ struct MilanEngine {
     CU(cudaMemcpy(*out, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
   }
-  int upload_split(SplitMat* m, const std::vector<float>& w, int rows, int cols) {
+  // fp16 = true: IEEE half (hi, lo) pairs for the decoder / LM matrices; false: bf16 pairs for the encoder.
+  int upload_split(SplitMat* m, const std::vector<float>& w, int rows, int cols, bool fp16 = false) {
     std::vector<uint16_t> hi(w.size()), lo(w.size());
     for (size_t i = 0; i < w.size(); ++i) {
-      hi[i] = f2bf(w[i]);
-      lo[i] = f2bf(w[i] - bf2f(hi[i]));
+      if (fp16) {
+        const __half h = __float2half_rn(w[i]);
+        const __half l = __float2half_rn(w[i] - __half2float(h));
+        memcpy(&hi[i], &h, 2);
+        memcpy(&lo[i], &l, 2);
+      } else {
+        hi[i] = f2bf(w[i]);
+        lo[i] = f2bf(w[i] - bf2f(hi[i]));
+      }
     }
     m->rows = rows;
     m->cols = cols;
@@ -338,14 +348,14 @@ int MilanEngine::finalize_decoder() {
   if (!wq || !bq || !wk || !bkk || !wo || !bo || !wg || !bg || !wih || !whh || !bih || !bhh || !wout || !bout ||
       !wh || !bh || !wc || !bc || !em)
     return 1;
-  if (upload_split(&Wk, wk->data, A, F)) return 1;
+  if (upload_split(&Wk, wk->data, A, F, true)) return 1;
   if (upload_f32(&bk, bkk->data, (A + 127) / 128 * 128)) return 1;
   {  // Winit = [W_h; W_c]
     std::vector<float> w(wh->data);
     w.insert(w.end(), wc->data.begin(), wc->data.end());
     std::vector<float> b(bh->data);
     b.insert(b.end(), bc->data.begin(), bc->data.end());
-    if (upload_split(&Winit, w, 2 * H, F)) return 1;
+    if (upload_split(&Winit, w, 2 * H, F, true)) return 1;
     if (upload_f32(&binit, b, (2 * H + 127) / 128 * 128)) return 1;
   }
   {  // W1 = [W_q; W_g]
@@ -353,7 +363,7 @@ int MilanEngine::finalize_decoder() {
     w.insert(w.end(), wg->data.begin(), wg->data.end());
     std::vector<float> b(bq->data);
     b.insert(b.end(), bg->data.begin(), bg->data.end());
-    if (upload_split(&W1, w, A + F, H)) return 1;
+    if (upload_split(&W1, w, A + F, H, true)) return 1;
     if (upload_f32(&b1, b, (A + F + 127) / 128 * 128)) return 1;
   }
   {  // W2 = [W_ih | W_hh], bias = b_ih + b_hh
@@ -365,10 +375,10 @@ int MilanEngine::finalize_decoder() {
     }
     std::vector<float> b(4 * H);
     for (int i = 0; i < 4 * H; ++i) b[i] = bih->data[i] + bhh->data[i];
-    if (upload_split(&W2, w, 4 * H, K)) return 1;
+    if (upload_split(&W2, w, 4 * H, K, true)) return 1;
     if (upload_f32(&b2, b)) return 1;
   }
-  if (upload_split(&W3, wout->data, V, H)) return 1;
+  if (upload_split(&W3, wout->data, V, H, true)) return 1;
   if (upload_f32(&b3, bout->data, (V + 127) / 128 * 128)) return 1;
   if (upload_f32(&w_o, wo->data)) return 1;
   b_o = bo->data[0];
@@ -392,7 +402,7 @@ int MilanEngine::finalize_decoder() {
         memcpy(&w[static_cast<size_t>(r) * (ka + kb)], &a->data[static_cast<size_t>(r) * ka], sizeof(float) * ka);
         memcpy(&w[static_cast<size_t>(r) * (ka + kb) + ka], &b->data[static_cast<size_t>(r) * kb], sizeof(float) * kb);
       }
-      return upload_split(out, w, 4 * Hl, ka + kb);
+      return upload_split(out, w, 4 * Hl, ka + kb, true);
     };
     if (cat(i0, El, h0, Hl, &L0)) return 1;
     if (cat(i1, Hl, h1, Hl, &L1)) return 1;
@@ -403,7 +413,7 @@ int MilanEngine::finalize_decoder() {
     }
     if (upload_f32(&bl0, b0)) return 1;
     if (upload_f32(&bl1, b1v)) return 1;
-    if (upload_split(&Lout, lo->data, V, Hl)) return 1;
+    if (upload_split(&Lout, lo->data, V, Hl, true)) return 1;
     if (upload_f32(&blout, lb->data, (V + 127) / 128 * 128)) return 1;
     if (upload_f32(&lm_emb, le->data)) return 1;
   }
@@ -629,7 +639,7 @@ int MilanEngine::gemm(int which, long long M, const SplitMat& W, const float* bi
     Plan pl;
     pl.block_n = 128;
     pl.epilogue = EPI_F32;
-    if (build_gemm_params(&pl.p, M, K, W.rows, a_hi, a_lo, a_pitch, W.hi, W.lo, bias, out, ldc, split ? 1 : 0))
+    if (build_gemm_params(&pl.p, M, K, W.rows, a_hi, a_lo, a_pitch, W.hi, W.lo, bias, out, ldc, split ? 1 : 0, 1))
       return fail("gemm plan %d (M=%lld K=%d N=%d): %s", which, M, K, W.rows, tmap_last_error());
     it = gemm_plans.emplace(key, pl).first;
   }

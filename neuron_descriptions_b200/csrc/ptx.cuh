@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace milan {
 
@@ -157,9 +158,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                    // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: A,B = bf16 (K-major), D = fp32, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// Instruction descriptor: A,B = bf16 (format 1) or fp16 (format 0), K-major, D = fp32, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_16bit(uint32_t M, uint32_t N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- small helpers
@@ -180,6 +181,15 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, u
   const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
   hi = *reinterpret_cast<const uint32_t*>(&h2);
   const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xFFFF0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
+// fp16 flavour (22 mantissa bits across the pair) for the decoder / LM GEMM operands, whose values are bounded.
+__device__ __forceinline__ void split_fp16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h2 = __floats2half2_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  const float2 hf = __half22float2(h2);
+  const __half2 l2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 

@@ -294,6 +294,10 @@ int main(int argc, char** argv) {
       {"gemm_small_sp",  1,  1, 128,  64,  128, 1, 1, 0, 0, 1, 0},
       {"gemm_k256",      1,  1, 300, 256,  128, 1, 1, 0, 0, 1, 0},
       {"gemm_f32_tail",  1,  1, 200, 512,  300, 1, 1, 0, 0, 1, 1},
+      {"acc_exact_k64",  1,  1, 256,   64,  256, 1, 1, 0, 0, 0, 1},
+      {"acc_exact_k512", 1,  1, 256,  512,  256, 1, 1, 0, 0, 0, 1},
+      {"acc_exact_k4544",1,  1, 256, 4544,  256, 1, 1, 0, 0, 0, 1},
+      {"acc_split_k4544",1,  1, 256, 4544,  256, 1, 1, 0, 0, 1, 1},
       {"c1x1_56",        2, 56,  56,  64,  256, 1, 1, 1, 1, 1, 0},
       {"c1x1_cout64",    2, 56,  56, 256,   64, 1, 1, 1, 0, 1, 0},
       {"c3x3_56",        3, 56,  56,  64,   64, 3, 1, 1, 0, 1, 0},
