@@ -164,24 +164,30 @@ __global__ void __launch_bounds__(256) masked_pool_kernel(const __nv_bfloat16* _
   }
 }
 
-// y[n][oh][ow][c] = max_{3x3, stride 2, pad 1} relu(alpha[c] * x + beta[c]);  C = 64, thread = 2 channels.
+// y[n][oh][ow][c] = max_{3x3, stride 2, pad 1} relu(alpha[c] * x + beta[c]);  C = 64, thread = 8 channels
+// (one 16-byte load per plane and window tap; 8 threads cover a pixel's 128-byte channel row).
 __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ x_hi,
                                                               const __nv_bfloat16* __restrict__ x_lo,
                                                               const float* __restrict__ alpha,
                                                               const float* __restrict__ beta, int n_images,
                                                               __nv_bfloat16* __restrict__ y_hi,
                                                               __nv_bfloat16* __restrict__ y_lo) {
-  constexpr int C = 64, IN = 112, OUT = 56;
+  constexpr int C = 64, IN = 112, OUT = 56, G = C / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n_images) * OUT * OUT * (C / 2);
+  const long long total = static_cast<long long>(n_images) * OUT * OUT * G;
   if (idx >= total) return;
-  const int c2 = idx % (C / 2);
-  const long long pix = idx / (C / 2);
+  const int cg = idx % G;
+  const long long pix = idx / G;
   const int ow = pix % OUT;
   const int oh = (pix / OUT) % OUT;
   const int n = pix / (OUT * OUT);
-  const float a0 = alpha[2 * c2], a1 = alpha[2 * c2 + 1], b0 = beta[2 * c2], b1 = beta[2 * c2 + 1];
-  float m0 = 0.0f, m1 = 0.0f;  // relu output >= 0 and every window holds >= 1 valid pixel
+  float a[8], b[8], m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = __ldg(alpha + cg * 8 + j);
+    b[j] = __ldg(beta + cg * 8 + j);
+    m[j] = 0.0f;  // relu output >= 0 and every window holds >= 1 valid pixel
+  }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int ih = oh * 2 + r - 1;
@@ -190,24 +196,25 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
     for (int s = 0; s < 3; ++s) {
       const int iw = ow * 2 + s - 1;
       if (iw < 0 || iw >= IN) continue;
-      const long long off = ((static_cast<long long>(n) * IN + ih) * IN + iw) * C + 2 * c2;
-      const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(x_hi + off));
-      float v0 = bf16_lo_to_f32(h), v1 = bf16_hi_to_f32(h);
+      const long long off = ((static_cast<long long>(n) * IN + ih) * IN + iw) * C + cg * 8;
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
+      float v[8] = {bf16_lo_to_f32(h.x), bf16_hi_to_f32(h.x), bf16_lo_to_f32(h.y), bf16_hi_to_f32(h.y),
+                    bf16_lo_to_f32(h.z), bf16_hi_to_f32(h.z), bf16_lo_to_f32(h.w), bf16_hi_to_f32(h.w)};
       if (x_lo != nullptr) {
-        const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(x_lo + off));
-        v0 += bf16_lo_to_f32(l);
-        v1 += bf16_hi_to_f32(l);
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+        v[0] += bf16_lo_to_f32(l.x); v[1] += bf16_hi_to_f32(l.x); v[2] += bf16_lo_to_f32(l.y); v[3] += bf16_hi_to_f32(l.y);
+        v[4] += bf16_lo_to_f32(l.z); v[5] += bf16_hi_to_f32(l.z); v[6] += bf16_lo_to_f32(l.w); v[7] += bf16_hi_to_f32(l.w);
       }
-      m0 = fmaxf(m0, fmaf(v0, a0, b0));
-      m1 = fmaxf(m1, fmaf(v1, a1, b1));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], a[j], b[j]));
     }
   }
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(m0, h0, l0);
-  split_bf16(m1, h1, l1);
-  const long long o = pix * C + 2 * c2;
-  *reinterpret_cast<uint32_t*>(y_hi + o) = pack_bf16x2(h0, h1);
-  if (y_lo != nullptr) *reinterpret_cast<uint32_t*>(y_lo + o) = pack_bf16x2(l0, l1);
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16x2(m[2 * j], m[2 * j + 1], hi[j], lo[j]);
+  const long long o = pix * C + cg * 8;
+  *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (y_lo != nullptr) *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 }  // namespace
@@ -251,7 +258,7 @@ int launch_masked_pool(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const f
 int launch_bn_relu_maxpool(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const float* alpha,
                            const float* beta, int n_images, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
                            cudaStream_t stream) {
-  const long long total = static_cast<long long>(n_images) * 56 * 56 * 32;
+  const long long total = static_cast<long long>(n_images) * 56 * 56 * 8;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   bn_relu_maxpool_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x_hi, x_lo, alpha, beta, n_images,

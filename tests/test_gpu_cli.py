@@ -1,0 +1,52 @@
+"""GPU: the `scripts/compute_milan_descriptions.py` entry point end to end on a tiny on-disk exemplar set and a
+synthetic checkpoint in the reference payload format; captions are checked against the oracle's predict."""
+import csv
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from neuron_descriptions_b200 import milan, synthetic
+from neuron_descriptions_b200.milan import lang
+from oracle import milan_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_compute_milan_descriptions_cli(tmp_path):
+    vocab = synthetic.synthetic_vocab(5000)
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=1.0)
+    indexer = lang.Indexer(lang.Vocab(vocab), start=True, stop=True, pad=True, unk=True)
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer))
+    decoder.load_state_dict(sd)
+    models = tmp_path / 'models'
+    models.mkdir()
+    decoder.save(models / 'base.pth')
+
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(5, 15, seed=21)
+    data = tmp_path / 'data' / 'alexnet' / 'imagenet'
+    for name, sl, units in (('conv1', slice(0, 2), [3, 9]), ('conv2', slice(2, 5), None)):
+        (data / name).mkdir(parents=True)
+        np.save(data / name / 'images.npy', images_u8[sl].numpy())
+        np.save(data / name / 'masks.npy', masks_u8[sl].numpy())
+        if units is not None:
+            np.save(data / name / 'units.npy', np.asarray(units))
+    results = tmp_path / 'results'
+    env = dict(os.environ, MILAN_MODELS_DIR=str(models), PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'compute_milan_descriptions.py'), 'alexnet',
+                          'imagenet', '--data-dir', str(tmp_path / 'data'), '--results-dir', str(results),
+                          '--beam-size', '10'], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    with open(results / 'alexnet_imagenet.csv') as handle:
+        rows = list(csv.reader(handle))
+    assert rows[0] == ['layer', 'unit', 'description']
+    assert [r[:2] for r in rows[1:]] == [['conv1', '3'], ['conv1', '9'], ['conv2', '0'], ['conv2', '1'], ['conv2', '2']]
+    images_f, masks_f = O.to_float_inputs(images_u8, masks_u8)
+    with torch.no_grad():
+        ref = O.describe(images_f, masks_f, sd, vocab, strategy='rerank', beam_size=10, temperature=.2)
+    assert [r[2] for r in rows[1:]] == list(ref)
