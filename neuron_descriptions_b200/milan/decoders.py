@@ -84,7 +84,7 @@ class Decoder:
                  temperature: float = .2,
                  beam_size: int = 50,
                  precision: str = 'split',
-                 max_neurons: int = 32):
+                 max_neurons: int = 64):
         if lm is not None:
             my_vocab, lm_vocab = indexer.vocab.unique, lm.indexer.vocab.unique
             if my_vocab != lm_vocab:
@@ -333,32 +333,55 @@ class Decoder:
         total = len(source)
         chunk = max(batch_size, (engine.cfg.max_neurons // batch_size) * batch_size)
         chunk = min(chunk, engine.cfg.max_neurons) if engine.cfg.max_neurons < batch_size else chunk
-        ranges = range(0, total, chunk)
-        if display_progress_as is not None:
-            try:
-                from tqdm.auto import tqdm
-                ranges = tqdm(ranges, desc=display_progress_as)
-            except ImportError:
-                pass
         captions = []
         token_rows = []
         length = kwargs.get('length') or self.length
-        for lo in ranges:
-            hi = min(lo + chunk, total)
+        bounds = [(lo, min(lo + chunk, total)) for lo in range(0, total, chunk)]
+
+        # Host feed: uint8 batches are assembled from the mmapped exemplar files into two alternating pinned staging
+        # buffers by a worker thread while the GPU works on the previous chunk (numpy copies release the GIL).
+        use_u8 = features is None and hasattr(dataset, 'batch_u8')
+        pool = staging = None
+        if use_u8:
+            import concurrent.futures
+            pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+            staging = [dataset.alloc_batch_u8(chunk) if hasattr(dataset, 'alloc_batch_u8') else None for _ in range(2)]
+
+            def load(i):
+                lo_, hi_ = bounds[i]
+                if staging[i % 2] is not None:
+                    return dataset.batch_u8(lo_, hi_, out=staging[i % 2])
+                return dataset.batch_u8(lo_, hi_)
+
+            pending = pool.submit(load, 0) if bounds else None
+        iterator = range(len(bounds))
+        if display_progress_as is not None:
+            try:
+                from tqdm.auto import tqdm
+                iterator = tqdm(iterator, desc=display_progress_as)
+            except ImportError:
+                pass
+        for i in iterator:
+            lo, hi = bounds[i]
             group = batch_size if chunk > batch_size else None
             with torch.no_grad():
                 if features is not None:
-                    feats = torch.stack([torch.as_tensor(features[i][0]) for i in range(lo, hi)])
+                    feats = torch.stack([torch.as_tensor(features[j][0]) for j in range(lo, hi)])
                     output = self(feats, group_size=group, **kwargs)
                 else:
-                    if hasattr(dataset, 'batch_u8'):
-                        images, masks = dataset.batch_u8(lo, hi)
+                    if use_u8:
+                        images, masks = pending.result()
+                        images = images.to(engine.device, non_blocking=True)
+                        masks = masks.to(engine.device, non_blocking=True) if mask else None
+                        torch.cuda.current_stream(engine.device).synchronize()  # staging buffer is free again
+                        if i + 1 < len(bounds):
+                            pending = pool.submit(load, i + 1)
                     else:
-                        samples = [dataset[i] for i in range(lo, hi)]
+                        samples = [dataset[j] for j in range(lo, hi)]
                         images = torch.stack([torch.as_tensor(s[image_index]) for s in samples])
                         masks = torch.stack([torch.as_tensor(s[mask_index]) for s in samples])
-                    images = images.to(engine.device, non_blocking=True)
-                    masks = masks.to(engine.device, non_blocking=True) if mask else None
+                        images = images.to(engine.device, non_blocking=True)
+                        masks = masks.to(engine.device, non_blocking=True) if mask else None
                     if masks is None:
                         output = self(images, encode=True, group_size=group, **kwargs)
                     else:
@@ -367,6 +390,8 @@ class Decoder:
             rows = torch.full((len(output.tokens), length), self.indexer.stop_index, dtype=torch.long)
             rows[:, :output.tokens.shape[1]] = output.tokens.cpu()
             token_rows.append(rows)
+        if pool is not None:
+            pool.shutdown(wait=True)
         self.last_predict_tokens = torch.cat(token_rows) if token_rows else torch.empty(0, length, dtype=torch.long)
         return tuple(captions)
 

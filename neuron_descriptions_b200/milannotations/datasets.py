@@ -86,18 +86,40 @@ class TopImagesDataset(torch.utils.data.Dataset):
     def __len__(self) -> int:
         return len(self._index)
 
-    def batch_u8(self, lo: int, hi: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """uint8 (hi-lo, k, 3, H, W) images and (hi-lo, k, 1, H, W) masks in pinned memory (engine fast path)."""
+    def batch_u8(self, lo: int, hi: int, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """uint8 (hi-lo, k, 3, H, W) images and (hi-lo, k, 1, H, W) masks for samples [lo, hi) (engine fast path).
+
+        Copies straight from the memory-mapped .npy files into `out` (reusable pinned tensors, see
+        `alloc_batch_u8`) — one memcpy per contiguous run of units, no intermediate stack.
+        """
         if self.transform_images is not None or self.transform_masks is not None:
             raise RuntimeError('batch_u8 bypasses transforms; use __getitem__')
-        images = numpy.stack([self.images_by_layer[layer][i] for layer, i in self._index[lo:hi]])
-        masks = numpy.stack([self.masks_by_layer[layer][i] for layer, i in self._index[lo:hi]])
-        images, masks = torch.from_numpy(images), torch.from_numpy(masks)
-        if masks.dtype != torch.uint8:
-            masks = masks.to(torch.uint8)
-        if torch.cuda.is_available():
-            images, masks = images.pin_memory(), masks.pin_memory()
+        n = hi - lo
+        if out is None:
+            out = self.alloc_batch_u8(n)
+        images, masks = out[0][:n], out[1][:n]
+        images_np, masks_np = images.numpy(), masks.numpy()
+        pos = lo
+        while pos < hi:  # contiguous runs inside one layer
+            layer, start = self._index[pos]
+            run = 1
+            while pos + run < hi and self._index[pos + run] == (layer, start + run):
+                run += 1
+            numpy.copyto(images_np[pos - lo:pos - lo + run], self.images_by_layer[layer][start:start + run])
+            numpy.copyto(masks_np[pos - lo:pos - lo + run], self.masks_by_layer[layer][start:start + run],
+                         casting='unsafe')
+            pos += run
         return images, masks
+
+    def alloc_batch_u8(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Reusable (pinned when CUDA is present) staging tensors for `batch_u8`."""
+        layer, _ = self._index[0]
+        im_shape = self.images_by_layer[layer].shape[1:]
+        mk_shape = self.masks_by_layer[layer].shape[1:]
+        pin = torch.cuda.is_available()
+        return (torch.empty((n, *im_shape), dtype=torch.uint8, pin_memory=pin),
+                torch.empty((n, *mk_shape), dtype=torch.uint8, pin_memory=pin))
 
     def lookup(self, layer, unit: int) -> TopImages:
         layer = str(layer)

@@ -65,8 +65,11 @@ class _Slice(torch.utils.data.Dataset):
 
 
 class _SliceU8(_Slice):
-    def batch_u8(self, lo, hi):
-        return self.base.batch_u8(self.lo + lo, self.lo + hi)
+    def batch_u8(self, lo, hi, out=None):
+        return self.base.batch_u8(self.lo + lo, self.lo + hi, out=out)
+
+    def alloc_batch_u8(self, n):
+        return self.base.alloc_batch_u8(n)
 
 
 def predict_sharded(decoder, dataset, world: int = 1, rank: int = 0, batch_size: int = 16, **kwargs) -> Sequence[str]:

@@ -50,3 +50,34 @@ def test_compute_milan_descriptions_cli(tmp_path):
     with torch.no_grad():
         ref = O.describe(images_f, masks_f, sd, vocab, strategy='rerank', beam_size=10, temperature=.2)
     assert [r[2] for r in rows[1:]] == list(ref)
+
+
+def test_predict_streams_chunks_from_disk(tmp_path):
+    """Decoder.predict over an on-disk TopImagesDataset with more neurons than one engine chunk: exercises the
+    prefetching uint8 host feed (two pinned staging buffers) and per-chunk grouping."""
+    from neuron_descriptions_b200 import milannotations
+    vocab = synthetic.synthetic_vocab(5000)
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=1.0)
+    indexer = lang.Indexer(lang.Vocab(vocab), start=True, stop=True, pad=True, unk=True)
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer), max_neurons=2)
+    decoder.load_state_dict(sd)
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(5, 15, seed=33)
+    root = tmp_path / 'resnet152' / 'places365'
+    for name, sl in (('layer1', slice(0, 3)), ('layer2', slice(3, 5))):
+        (root / name).mkdir(parents=True)
+        np.save(root / name / 'images.npy', images_u8[sl].numpy())
+        np.save(root / name / 'masks.npy', masks_u8[sl].numpy())
+    dataset = milannotations.load('resnet152/places365', path=root)
+    captions = decoder.predict(dataset, strategy='rerank', beam_size=8, batch_size=2, device='cuda:0',
+                               display_progress_as=None)
+    images_f, masks_f = O.to_float_inputs(images_u8, masks_u8)
+    with torch.no_grad():
+        ref = O.describe(images_f, masks_f, sd, vocab, batch_size=2, strategy='rerank', beam_size=8)
+    assert list(captions) == list(ref)
+    assert decoder.last_predict_tokens.shape == (5, 15)
+    # the same through precomputed features (Encoder.map + predict(features=...), src/milan/encoders.py:61-148)
+    feats = decoder.encoder.map(dataset, batch_size=2, device='cuda:0', display_progress_as=None)
+    again = decoder.predict(dataset, features=feats, strategy='rerank', beam_size=8, batch_size=2,
+                            display_progress_as=None)
+    assert list(again) == list(ref)
