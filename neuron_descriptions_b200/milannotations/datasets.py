@@ -68,8 +68,8 @@ class TopImagesDataset(torch.utils.data.Dataset):
         self._index = [(layer, i) for layer in layers for i in range(len(self.images_by_layer[layer]))]
 
     def _convert(self, layer: str, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        images = torch.from_numpy(numpy.ascontiguousarray(self.images_by_layer[layer][i])).float().mul(_BYTE_TO_PT)
-        masks = torch.from_numpy(numpy.ascontiguousarray(self.masks_by_layer[layer][i])).float()
+        images = torch.from_numpy(numpy.array(self.images_by_layer[layer][i])).float().mul(_BYTE_TO_PT)
+        masks = torch.from_numpy(numpy.array(self.masks_by_layer[layer][i])).float()
         if self.device is not None:
             images, masks = images.to(self.device), masks.to(self.device)
         if self.transform_images is not None:

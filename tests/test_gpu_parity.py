@@ -282,3 +282,41 @@ def test_facade_matches_reference_surface(full_sd):
         decoder(images_f, masks_f, strategy='rerank', mi=True)
     with pytest.raises(ValueError, match='strategy must have length'):
         decoder(images_f, masks_f, strategy=torch.zeros(3, 4, dtype=torch.long))
+
+
+def test_edge_cases_vs_oracle():
+    """Ragged / extreme sizes: one neuron, beam 1 and the maximum beam, length 1, more keys than the register tile
+    of the attention kernel, empty inputs."""
+    sd = synthetic.synthetic_state_dict(seed=2, sharpen=12.0, stop_bias=1.0, with_encoder=False)
+    from neuron_descriptions_b200.engine import Engine
+    engine = Engine(sd, vocab_size=V, device='cuda:0', max_neurons=4, max_beam=64, max_keys=20)
+    gen = torch.Generator().manual_seed(5)
+    feats = torch.randn(3, 20, synthetic.FEATURE_SIZE, generator=gen).abs() * 0.4  # 20 keys > 16
+    ref = O.decode(feats, sd, VOCAB, strategy='greedy', mi=False)
+    tok, sc, _, attn = engine.decode_greedy(feats, 15, mi=False, temperature=0.2)
+    np.testing.assert_array_equal(tok.cpu().numpy(), ref.tokens.numpy())
+    torch.testing.assert_close(sc.cpu(), ref.scores, atol=LOGP_TOL, rtol=0)
+    torch.testing.assert_close(attn.cpu(), ref.attentions, atol=1e-4, rtol=0)
+    # one neuron, beam 1, length 1 and the largest beam
+    one = feats[:1, :15].contiguous()
+    for beam, length in ((1, 1), (1, 15), (64, 6)):
+        ref = O.decode(one, sd, VOCAB, strategy='rerank', beam_size=beam, length=length)
+        bt, bs, steps, tok, sc, _ = engine.decode_beam(one, length, beam, True, 0.2)
+        T = int(steps[0])
+        assert T == ref.beam_tokens.shape[-1]
+        torch.testing.assert_close(bs.cpu(), ref.beam_scores, atol=LOGP_TOL, rtol=0)
+        torch.testing.assert_close(sc.cpu(), ref.scores, atol=LOGP_TOL, rtol=0)
+        _tokens_match(bt[..., :T].cpu().numpy(), ref.beam_tokens.numpy(), bs.cpu().numpy(), ref.beam_scores.numpy(),
+                      f'beam{beam}')
+    with pytest.raises(Exception, match='beam size'):
+        engine.decode_beam(one, 5, 65, False, 0.2)
+    with pytest.raises(Exception, match='exceeds'):
+        engine.decode_beam(torch.zeros(5, 15, synthetic.FEATURE_SIZE), 5, 4, False, 0.2)
+    engine.close()
+
+
+def test_empty_inputs(full_engine):
+    out = full_engine.encode(torch.zeros(0, 3, 224, 224, dtype=torch.uint8), torch.zeros(0, 1, 224, 224, dtype=torch.uint8))
+    assert out.shape == (0, synthetic.FEATURE_SIZE)
+    with pytest.raises(ValueError, match='expects'):
+        full_engine.encode(torch.zeros(1, 3, 64, 64, dtype=torch.uint8), None)
