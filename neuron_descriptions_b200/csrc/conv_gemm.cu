@@ -47,7 +47,9 @@ struct SmemLayout {
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
 
 template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p,
+                                                                   const int* __restrict__ skip_flag) {
+  if (skip_flag != nullptr && *skip_flag != 0) return;  // uniform: whole grid exits before touching any barrier
   using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
   constexpr int kStages = L::kStages;
   constexpr int kTmemBufs = 4;                 // accumulator ring
@@ -379,7 +381,7 @@ std::atomic<long long> g_launches{0};
 std::atomic<long long> g_all_launches{0};
 
 template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
-int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
   using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
   auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI, HAS_RES>;
   static bool configured = false;
@@ -395,7 +397,7 @@ int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   if (total_tiles <= 0) return 0;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  kernel<<<grid, kNumThreads, L::kTotalBytes, stream>>>(p);
+  kernel<<<grid, kNumThreads, L::kTotalBytes, stream>>>(p, skip_flag);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   g_all_launches.fetch_add(1, std::memory_order_relaxed);
   return static_cast<int>(cudaGetLastError());
@@ -408,11 +410,11 @@ long long total_launch_count() { return g_all_launches.load(); }
 void note_launch(int n) { g_all_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const int* skip_flag) {
   const bool res = p.has_res != 0;
 #define MILAN_DISPATCH(BN, SP, EP, RS)                                           \
   if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS)        \
-    return launch_impl<BN, SP, EP, RS>(p, num_sms, stream);
+    return launch_impl<BN, SP, EP, RS>(p, num_sms, stream, skip_flag);
   MILAN_DISPATCH(128, true, EPI_BF16, false)
   MILAN_DISPATCH(128, true, EPI_BF16, true)
   MILAN_DISPATCH(128, false, EPI_BF16, false)

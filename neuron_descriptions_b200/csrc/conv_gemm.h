@@ -61,8 +61,10 @@ struct alignas(64) ConvGemmParams {
 
 // block_n: 64 or 128. split: hi/lo planes (1) or hi only (0). Returns cudaError_t as int.
 // EPI_BF16 kernels store through tmap_out (and read the residual through tmap_res when p.has_res).
+// skip_flag (device, may be nullptr): when *skip_flag != 0 at kernel start the launch is a no-op — used by the
+// beam-search loop to drop the GEMMs of steps after every beam has ended, without a host round trip.
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const int* skip_flag = nullptr);
 // Kernel launches performed by this library since process start (for bench.py's gpu_launches).
 long long conv_gemm_launch_count();   // tcgen05 conv/GEMM kernel only
 long long total_launch_count();       // every kernel of the library

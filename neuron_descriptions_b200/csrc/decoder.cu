@@ -71,6 +71,7 @@ __global__ void init_finish_kernel(const float* __restrict__ pre, int B, int H, 
 // token embedding (decoders.py:618). Kernel 2 (one CTA per feature set x column slice): attenuate + gate
 // (decoders.py:613-615); the feature tile is read once per neuron and reused by all of its beam rows.
 __global__ void __launch_bounds__(256) attn_scores_kernel(const AttendArgs a, float* __restrict__ attn_ws) {
+  if (a.skip != nullptr && *a.skip) return;
   extern __shared__ float sm[];
   float* q_s = sm;                 // [A]
   float* sc_s = sm + a.A;          // [n_keys]
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(256) attn_scores_kernel(const AttendArgs a, fl
 
 constexpr int kApplyKeys = 16;  // keys held in registers per pass
 __global__ void __launch_bounds__(256) attn_apply_kernel(const AttendArgs a, const float* __restrict__ attn_ws) {
+  if (a.skip != nullptr && *a.skip) return;
   extern __shared__ float w_s[];  // [rows_per_feature][n_keys]
   const int fidx = blockIdx.x;
   const int j2 = blockIdx.y * blockDim.x + threadIdx.x;
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const AttendArgs a, con
 
 // ------------------------------------------------------------------ LSTM pointwise
 __global__ void lstm_point_kernel(const LstmPointArgs a) {
+  if (a.skip != nullptr && *a.skip) return;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int H2 = a.H / 2;
   if (idx >= static_cast<long long>(a.R) * H2) return;
@@ -189,7 +192,9 @@ __global__ void lstm_point_kernel(const LstmPointArgs a) {
 }
 
 __global__ void embed_rows_kernel(const float* __restrict__ table, const long long* __restrict__ tokens, int M,
-                                  int E2, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, long long dst_pitch) {
+                                  int E2, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, long long dst_pitch,
+                                  const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(M) * E2) return;
   const int e2 = idx % E2;
@@ -277,6 +282,7 @@ __device__ __forceinline__ void row_log_softmax(const float* __restrict__ x, int
 }
 
 __global__ void __launch_bounds__(256) row_kernel(const RowArgs a) {
+  if (a.skip != nullptr && *a.skip) return;
   extern __shared__ float pred_s[];  // [V]
   __shared__ float red[8];
   __shared__ ValIdx redvi[8];
@@ -407,6 +413,18 @@ __global__ void __launch_bounds__(256) row_kernel(const RowArgs a) {
 __global__ void __launch_bounds__(32) beam_merge_kernel(const MergeArgs a) {
   const int nrn = blockIdx.x;
   const int lane = threadIdx.x;
+  if (a.skip != nullptr && *a.skip) {
+    // every beam of every neuron has ended: the reference would have left its loop; keep the beams as they are
+    for (int j = lane; j < a.beam; j += 32) {
+      const int out = nrn * a.beam + j;
+      a.next_tokens[out] = a.stop_index;
+      a.next_lp[out] = a.cur_lp[out];
+      a.backptr[out] = out;
+      a.hist_tok[out] = static_cast<int>(a.stop_index);
+      a.hist_bp[out] = j;
+    }
+    return;
+  }
   const int row_base = nrn * a.in_rows;
   int ptr0 = 0, ptr1 = 0;  // heads of source rows lane and lane+32
   const int r0 = lane, r1 = lane + 32;
@@ -436,6 +454,7 @@ __global__ void __launch_bounds__(32) beam_merge_kernel(const MergeArgs a) {
 }
 
 __global__ void gather_state_kernel(const GatherArgs a) {
+  if (a.skip != nullptr && *a.skip) return;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int H8 = a.H / 8;
   if (idx >= static_cast<long long>(a.R) * H8) return;
@@ -491,13 +510,15 @@ __global__ void group_T_kernel(const BacktrackArgs a) {
 
 // ------------------------------------------------------------------ LM scoring
 __global__ void lm_inputs_kernel(const long long* __restrict__ seqs, int M, int length, int t, long long start,
-                                 long long* inputs) {
+                                 long long* inputs, const int* __restrict__ skip) {
+  if (skip != nullptr && *skip) return;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   inputs[m] = t == 0 ? start : seqs[static_cast<long long>(m) * length + t - 1];
 }
 
 __global__ void __launch_bounds__(256) lm_accumulate_kernel(const LmAccumArgs a) {
+  if (a.skip != nullptr && *a.skip) return;
   __shared__ float red[8];
   const int m = blockIdx.x;
   const int T = a.group_T[(m / a.beam) / a.group_size];
@@ -538,6 +559,18 @@ __global__ void rerank_select_kernel(const RerankArgs a) {
   if (a.out_index != nullptr) a.out_index[n] = bi;
 }
 
+__global__ void check_done_kernel(const long long* __restrict__ tokens, int n, long long stop, int* flag) {
+  int ok = 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (tokens[i] != stop) ok = 0;
+  ok = __syncthreads_and(ok);
+  if (threadIdx.x == 0) *flag = ok;
+}
+__global__ void lm_skip_kernel(const int* __restrict__ group_T, int groups, int length, int* lm_skip) {
+  int max_T = 0;
+  for (int g = 0; g < groups; ++g) max_T = max(max_T, group_T[g]);
+  for (int t = threadIdx.x; t < length; t += blockDim.x) lm_skip[t] = t >= max_T ? 1 : 0;
+}
 __global__ void fill_i64_kernel(long long* dst, long long v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;
@@ -592,10 +625,10 @@ int launch_lstm_point(const LstmPointArgs& a, cudaStream_t stream) {
   return last_err();
 }
 int launch_embed_rows(const float* table, const long long* tokens, int M, int E, __nv_bfloat16* dst_hi,
-                      __nv_bfloat16* dst_lo, long long dst_pitch, cudaStream_t stream) {
+                      __nv_bfloat16* dst_lo, long long dst_pitch, cudaStream_t stream, const int* skip) {
   const long long n = static_cast<long long>(M) * (E / 2);
   if (n == 0) return 0;
-  embed_rows_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(table, tokens, M, E / 2, dst_hi, dst_lo, dst_pitch);
+  embed_rows_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(table, tokens, M, E / 2, dst_hi, dst_lo, dst_pitch, skip);
   return last_err();
 }
 int launch_row_logsoftmax(const RowArgs& a, cudaStream_t stream) {
@@ -631,8 +664,8 @@ int launch_backtrack(const BacktrackArgs& a, cudaStream_t stream) {
   return last_err();
 }
 int launch_lm_inputs(const long long* seqs, int M, int length, int t, long long start_index, long long* inputs,
-                     cudaStream_t stream) {
-  lm_inputs_kernel<<<blocks_for(M, 256), 256, 0, stream>>>(seqs, M, length, t, start_index, inputs);
+                     cudaStream_t stream, const int* skip) {
+  lm_inputs_kernel<<<blocks_for(M, 256), 256, 0, stream>>>(seqs, M, length, t, start_index, inputs, skip);
   return last_err();
 }
 int launch_lm_accumulate(const LmAccumArgs& a, cudaStream_t stream) {
@@ -641,6 +674,14 @@ int launch_lm_accumulate(const LmAccumArgs& a, cudaStream_t stream) {
 }
 int launch_rerank_select(const RerankArgs& a, cudaStream_t stream) {
   rerank_select_kernel<<<blocks_for(a.n_neurons, 128), 128, 0, stream>>>(a);
+  return last_err();
+}
+int launch_check_done(const long long* tokens, int n, long long stop_index, int* flag, cudaStream_t stream) {
+  check_done_kernel<<<1, 256, 0, stream>>>(tokens, n, stop_index, flag);
+  return last_err();
+}
+int launch_lm_skip(const int* group_T, int groups, int length, int* lm_skip, cudaStream_t stream) {
+  lm_skip_kernel<<<1, 32, 0, stream>>>(group_T, groups, length, lm_skip);
   return last_err();
 }
 int launch_fill_i64(long long* dst, long long value, int n, cudaStream_t stream) {

@@ -36,6 +36,7 @@ struct AttendArgs {
   long long x_pitch;
   float* attn_out;        // [R][attn_pitch] or nullptr
   long long attn_pitch;
+  const int* skip;        // device flag: non-zero -> no-op (all beams ended); may be nullptr
   float* attn_ws;         // workspace [R][n_keys]
   const float* acc_ws;    // workspace [R][F], only needed when n_keys > 16
 };
@@ -53,12 +54,13 @@ struct LstmPointArgs {
   __nv_bfloat16* h_lo[2];
   long long h_pitch[2];
   int R, H;
+  const int* skip;
 };
 int launch_lstm_point(const LstmPointArgs& a, cudaStream_t stream);
 
 // Embedding lookup -> hi/lo rows: dst[m][0:E] = split(table[tokens[m]]).
 int launch_embed_rows(const float* table, const long long* tokens, int M, int E, __nv_bfloat16* dst_hi,
-                      __nv_bfloat16* dst_lo, long long dst_pitch, cudaStream_t stream);
+                      __nv_bfloat16* dst_lo, long long dst_pitch, cudaStream_t stream, const int* skip = nullptr);
 
 constexpr int kMaxBeam = 64;
 
@@ -85,6 +87,7 @@ struct RowArgs {
   long long stop_index;
   float* cand_val;         // [R][beam]
   int* cand_cls;           // [R][beam]
+  const int* skip;
 };
 int launch_row_logsoftmax(const RowArgs& a, cudaStream_t stream);
 
@@ -98,6 +101,9 @@ struct MergeArgs {
   int* backptr;            // [n_neurons*beam] global source row
   int* hist_tok;           // this step's [n_neurons*beam]
   int* hist_bp;            // this step's [n_neurons*beam] (beam-local parent index)
+  const int* skip;         // non-zero: every beam has ended -> emit <stop> / identity / unchanged scores
+  const float* cur_lp;     // [n_neurons*beam] current scores (used when skipping)
+  long long stop_index;
 };
 int launch_beam_merge(const MergeArgs& a, cudaStream_t stream);
 
@@ -108,6 +114,7 @@ struct GatherArgs {
   const __nv_bfloat16* src_hi; const __nv_bfloat16* src_lo; long long src_pitch;
   __nv_bfloat16* dst_hi; __nv_bfloat16* dst_lo; long long dst_pitch;
   const float* c_src; float* c_dst;  // [R][H] or nullptr
+  const int* skip;
 };
 int launch_gather_state(const GatherArgs& a, cudaStream_t stream);
 
@@ -126,7 +133,7 @@ int launch_backtrack(const BacktrackArgs& a, cudaStream_t stream);
 // LM scoring bookkeeping for position t: input token for the LM step and masked accumulation of the target
 // log-prob with the reference's stop-mask off-by-one (lms.py:93-96).
 int launch_lm_inputs(const long long* seqs, int M, int length, int t, long long start_index, long long* inputs,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const int* skip = nullptr);
 struct LmAccumArgs {
   const float* logits;  // [M][ld]
   long long ld;
@@ -135,6 +142,7 @@ struct LmAccumArgs {
   const int* group_T;     // per group of group_size neurons (M = n_neurons*beam rows)
   long long stop_index;
   float* lm_scores;       // [M] accumulated
+  const int* skip;
 };
 int launch_lm_accumulate(const LmAccumArgs& a, cudaStream_t stream);
 
@@ -149,6 +157,10 @@ struct RerankArgs {
 };
 int launch_rerank_select(const RerankArgs& a, cudaStream_t stream);
 
+// *flag = 1 iff every token equals stop (allennlp: `if (last_predictions == end).all(): break`).
+int launch_check_done(const long long* tokens, int n, long long stop_index, int* flag, cudaStream_t stream);
+// lm_skip[t] = (t >= max_g group_T[g]) for t < length: LM positions no group needs.
+int launch_lm_skip(const int* group_T, int groups, int length, int* lm_skip, cudaStream_t stream);
 int launch_fill_i64(long long* dst, long long value, int n, cudaStream_t stream);
 int launch_fill_f32(float* dst, float value, int n, cudaStream_t stream);
 

@@ -136,6 +136,7 @@ struct MilanEngine {
         *next_lp = nullptr, *lm_c0 = nullptr, *lm_c1 = nullptr, *lm_c0n = nullptr, *lm_c1n = nullptr,
         *lm_scores = nullptr, *feat_enc = nullptr, *out_scores = nullptr, *attn_ws = nullptr, *attn_acc = nullptr, *greedy_scores = nullptr, *lm_h_f32 = nullptr;
   int *cand_cls = nullptr, *backptr = nullptr, *hist_tok = nullptr, *hist_bp = nullptr, *group_T = nullptr;
+  int *d_done = nullptr, *lm_skip = nullptr;  // device early-exit flags (beam loop / LM positions)
   long long *tok_cur = nullptr, *tok_next = nullptr, *seqs = nullptr, *lm_inputs = nullptr, *out_tokens = nullptr;
   std::map<std::pair<int, long long>, Plan> gemm_plans;  // (which, M)
   int host_T = 0;
@@ -211,12 +212,13 @@ struct MilanEngine {
   int collect_conv_events(cudaStream_t st);
 
   int gemm(int which, long long M, const SplitMat& W, const float* bias, const __nv_bfloat16* a_hi,
-           const __nv_bfloat16* a_lo, long long a_pitch, int K, float* out, long long ldc, cudaStream_t st);
+           const __nv_bfloat16* a_lo, long long a_pitch, int K, float* out, long long ldc, cudaStream_t st,
+           const int* skip = nullptr);
   int prepare_features(const float* d_features, int Bf, int n_keys, cudaStream_t st);
   int step_core(int R, int rpf, int n_keys, const float* d_features, const long long* d_tokens, float* attn_out,
-                long long attn_pitch, cudaStream_t st);
+                long long attn_pitch, cudaStream_t st, const int* skip = nullptr);
   int lm_reset(int M, cudaStream_t st);
-  int lm_step_core(int M, const long long* d_tokens, bool to_new, cudaStream_t st);
+  int lm_step_core(int M, const long long* d_tokens, bool to_new, cudaStream_t st, const int* skip = nullptr);
   int decode_greedy(const float* d_features, int B, int n_keys, int length, int mi, float temperature,
                     const long long* d_forced, long long* d_tokens_out, float* d_scores_out, float* d_pred_out,
                     float* d_attn_out, cudaStream_t st);
@@ -464,6 +466,10 @@ int MilanEngine::alloc_workspace() {
   if (dalloc(&hist_tok, R * L)) return 1;
   if (dalloc(&hist_bp, R * L)) return 1;
   if (dalloc(&group_T, B + 1)) return 1;
+  if (dalloc(&d_done, 4)) return 1;
+  if (dalloc(&lm_skip, L + 1)) return 1;
+  CU(cudaMemset(d_done, 0, 4 * sizeof(int)));
+  CU(cudaMemset(lm_skip, 0, (L + 1) * sizeof(int)));
   if (dalloc(&tok_cur, R)) return 1;
   if (dalloc(&tok_next, R)) return 1;
   if (dalloc(&seqs, R * (L + 1))) return 1;
@@ -631,7 +637,7 @@ enum GemmId { G_KH = 0, G_INIT, G_QG, G_LSTM, G_OUT, G_LM0, G_LM1, G_LMOUT };
 
 int MilanEngine::gemm(int which, long long M, const SplitMat& W, const float* bias, const __nv_bfloat16* a_hi,
                       const __nv_bfloat16* a_lo, long long a_pitch, int K, float* out, long long ldc,
-                      cudaStream_t st) {
+                      cudaStream_t st, const int* skip) {
   if (M <= 0) return 0;
   auto key = std::make_pair(which, M);
   auto it = gemm_plans.find(key);
@@ -643,7 +649,7 @@ int MilanEngine::gemm(int which, long long M, const SplitMat& W, const float* bi
       return fail("gemm plan %d (M=%lld K=%d N=%d): %s", which, M, K, W.rows, tmap_last_error());
     it = gemm_plans.emplace(key, pl).first;
   }
-  RC(launch_conv_gemm(it->second.p, 128, split ? 1 : 0, EPI_F32, num_sms, st));
+  RC(launch_conv_gemm(it->second.p, 128, split ? 1 : 0, EPI_F32, num_sms, st, skip));
   return 0;
 }
 
@@ -659,12 +665,12 @@ int MilanEngine::prepare_features(const float* d_features, int Bf, int n_keys, c
 // One Decoder.step on R rows whose recurrent state lives in the workspace (h as hi/lo in Alstm[:, E+F:], c in
 // `c`). Leaves logits in `logits`, the new state in hnew / hnew_f32 / cnew.
 int MilanEngine::step_core(int R, int rpf, int n_keys, const float* d_features, const long long* d_tokens,
-                           float* attn_out, long long attn_pitch, cudaStream_t st) {
+                           float* attn_out, long long attn_pitch, cudaStream_t st, const int* skip) {
   const int V = cfg.vocab_size, E = cfg.embedding_size, H = cfg.hidden_size, A = cfg.attention_size,
             F = cfg.feature_size;
   const long long xp = E + F + H;
   // q and gate pre-activations: [R][A+F] = h W1^T + b1
-  if (gemm(G_QG, R, W1, b1, Alstm[0] + E + F, split ? Alstm[1] + E + F : nullptr, xp, H, qg, A + F, st)) return 1;
+  if (gemm(G_QG, R, W1, b1, Alstm[0] + E + F, split ? Alstm[1] + E + F : nullptr, xp, H, qg, A + F, st, skip)) return 1;
   AttendArgs aa{};
   aa.qg = qg; aa.qg_pitch = A + F;
   aa.kh = kh; aa.features = d_features; aa.w_o = w_o; aa.b_o = b_o;
@@ -672,15 +678,16 @@ int MilanEngine::step_core(int R, int rpf, int n_keys, const float* d_features, 
   aa.R = R; aa.rows_per_feature = rpf; aa.n_keys = n_keys; aa.A = A; aa.F = F; aa.E = E;
   aa.x_hi = Alstm[0]; aa.x_lo = Alstm[1]; aa.x_pitch = xp;
   aa.attn_out = attn_out; aa.attn_pitch = attn_pitch;
+  aa.skip = skip;
   aa.attn_ws = attn_ws; aa.acc_ws = n_keys > 16 ? attn_acc : nullptr;
   RC(launch_attend(aa, st));
-  if (gemm(G_LSTM, R, W2, b2, Alstm[0], Alstm[1], xp, static_cast<int>(xp), gates, 4 * H, st)) return 1;
+  if (gemm(G_LSTM, R, W2, b2, Alstm[0], Alstm[1], xp, static_cast<int>(xp), gates, 4 * H, st, skip)) return 1;
   LstmPointArgs la{};
   la.gates = gates; la.c_in = c; la.c_out = cnew; la.h_out = hnew_f32;
   la.h_hi[0] = hnew[0]; la.h_lo[0] = hnew[1]; la.h_pitch[0] = H;
-  la.R = R; la.H = H;
+  la.R = R; la.H = H; la.skip = skip;
   RC(launch_lstm_point(la, st));
-  if (gemm(G_OUT, R, W3, b3, hnew[0], hnew[1], H, H, logits, ldv, st)) return 1;
+  if (gemm(G_OUT, R, W3, b3, hnew[0], hnew[1], H, H, logits, ldv, st, skip)) return 1;
   (void)V;
   return 0;
 }
@@ -698,29 +705,29 @@ int MilanEngine::lm_reset(int M, cudaStream_t st) {
 
 // One LM step (embedding -> 2 LSTM layers -> vocab logits in logits_lm) on M rows; state in Alm0[:, El:],
 // Alm1[:, Hl:], lm_c0, lm_c1. to_new: write the new state to lmnew0/1 + lm_c0n/1n instead (beam reorder follows).
-int MilanEngine::lm_step_core(int M, const long long* d_tokens, bool to_new, cudaStream_t st) {
+int MilanEngine::lm_step_core(int M, const long long* d_tokens, bool to_new, cudaStream_t st, const int* skip) {
   const int El = cfg.lm_embedding_size, Hl = cfg.lm_hidden_size;
   const long long p0 = El + Hl, p1 = 2 * Hl;
-  RC(launch_embed_rows(lm_emb, d_tokens, M, El, Alm0[0], Alm0[1], p0, st));
-  if (gemm(G_LM0, M, L0, bl0, Alm0[0], Alm0[1], p0, static_cast<int>(p0), gates, 4 * Hl, st)) return 1;
+  RC(launch_embed_rows(lm_emb, d_tokens, M, El, Alm0[0], Alm0[1], p0, st, skip));
+  if (gemm(G_LM0, M, L0, bl0, Alm0[0], Alm0[1], p0, static_cast<int>(p0), gates, 4 * Hl, st, skip)) return 1;
   LstmPointArgs a0{};
   a0.gates = gates; a0.c_in = lm_c0; a0.c_out = to_new ? lm_c0n : lm_c0;
   a0.h_out = lm_h_f32;
   a0.h_hi[0] = Alm1[0]; a0.h_lo[0] = Alm1[1]; a0.h_pitch[0] = p1;  // input of layer 1, this step
   if (to_new) { a0.h_hi[1] = lmnew0[0]; a0.h_lo[1] = lmnew0[1]; a0.h_pitch[1] = Hl; }
   else        { a0.h_hi[1] = Alm0[0] + El; a0.h_lo[1] = split ? Alm0[1] + El : nullptr; a0.h_pitch[1] = p0; }
-  a0.R = M; a0.H = Hl;
+  a0.R = M; a0.H = Hl; a0.skip = skip;
   RC(launch_lstm_point(a0, st));
-  if (gemm(G_LM1, M, L1, bl1, Alm1[0], Alm1[1], p1, static_cast<int>(p1), gates, 4 * Hl, st)) return 1;
+  if (gemm(G_LM1, M, L1, bl1, Alm1[0], Alm1[1], p1, static_cast<int>(p1), gates, 4 * Hl, st, skip)) return 1;
   LstmPointArgs a1{};
   a1.gates = gates; a1.c_in = lm_c1; a1.c_out = to_new ? lm_c1n : lm_c1;
   a1.h_out = lm_h_f32 + static_cast<size_t>(M) * Hl;
   a1.h_hi[0] = lmh[0]; a1.h_lo[0] = lmh[1]; a1.h_pitch[0] = Hl;  // input of the output projection
   if (to_new) { a1.h_hi[1] = lmnew1[0]; a1.h_lo[1] = lmnew1[1]; a1.h_pitch[1] = Hl; }
   else        { a1.h_hi[1] = Alm1[0] + Hl; a1.h_lo[1] = split ? Alm1[1] + Hl : nullptr; a1.h_pitch[1] = p1; }
-  a1.R = M; a1.H = Hl;
+  a1.R = M; a1.H = Hl; a1.skip = skip;
   RC(launch_lstm_point(a1, st));
-  if (gemm(G_LMOUT, M, Lout, blout, lmh[0], lmh[1], Hl, Hl, logits_lm, ldv, st)) return 1;
+  if (gemm(G_LMOUT, M, Lout, blout, lmh[0], lmh[1], Hl, Hl, logits_lm, ldv, st, skip)) return 1;
   return 0;
 }
 
@@ -786,13 +793,16 @@ int MilanEngine::lm_score_seqs(const long long* d_seqs, int M, int length, int b
   const int V = cfg.vocab_size;
   if (lm_reset(M, st)) return 1;
   RC(launch_fill_f32(lm_scores, 0.f, M, st));
+  const int groups = beam > 0 && group_size < (1 << 29) ? ((M / beam) + group_size - 1) / group_size : 1;
+  RC(launch_lm_skip(group_T, groups, length, lm_skip, st));  // positions beyond every group's T are no-ops
   for (int t = 0; t < length; ++t) {
-    RC(launch_lm_inputs(d_seqs, M, length, t, cfg.start_index, lm_inputs, st));
-    if (lm_step_core(M, lm_inputs, false, st)) return 1;
+    const int* skip = lm_skip + t;
+    RC(launch_lm_inputs(d_seqs, M, length, t, cfg.start_index, lm_inputs, st, skip));
+    if (lm_step_core(M, lm_inputs, false, st, skip)) return 1;
     LmAccumArgs la{};
     la.logits = logits_lm; la.ld = ldv; la.M = M; la.V = V; la.length = length; la.t = t; la.beam = beam;
     la.group_size = group_size; la.seqs = d_seqs; la.group_T = group_T; la.stop_index = cfg.stop_index;
-    la.lm_scores = lm_scores;
+    la.lm_scores = lm_scores; la.skip = skip;
     RC(launch_lm_accumulate(la, st));
   }
   return 0;
@@ -815,44 +825,48 @@ int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int len
   if (prepare_features(d_features, B, n_keys, st)) return 1;
   if (init_state_impl(this, d_features, B, n_keys, nullptr, nullptr, st)) return 1;
   RC(launch_fill_i64(tok_cur, cfg.start_index, B, st));
+  CU(cudaMemsetAsync(d_done, 0, sizeof(int), st));
   if (mi && lm_reset(R, st)) return 1;
   const int Hl = cfg.lm_hidden_size, El = cfg.lm_embedding_size;
   for (int t = 0; t < length; ++t) {
     const int rows = t == 0 ? B : R;
     const int rpf = t == 0 ? 1 : beam;
-    if (step_core(rows, rpf, n_keys, d_features, tok_cur, nullptr, 0, st)) return 1;
-    if (mi && lm_step_core(rows, tok_cur, true, st)) return 1;
+    if (step_core(rows, rpf, n_keys, d_features, tok_cur, nullptr, 0, st, d_done)) return 1;
+    if (mi && lm_step_core(rows, tok_cur, true, st, d_done)) return 1;
     RowArgs ra{};
     ra.logits = logits; ra.logits_lm = mi ? logits_lm : nullptr; ra.ld = ldv; ra.R = rows; ra.V = V;
     ra.temperature = temperature;
     ra.beam = beam; ra.last_tokens = tok_cur; ra.last_lp = t == 0 ? nullptr : last_lp;
-    ra.stop_index = cfg.stop_index; ra.cand_val = cand_val; ra.cand_cls = cand_cls;
+    ra.stop_index = cfg.stop_index; ra.cand_val = cand_val; ra.cand_cls = cand_cls; ra.skip = d_done;
     RC(launch_row_logsoftmax(ra, st));
     MergeArgs ma{};
     ma.cand_val = cand_val; ma.cand_cls = cand_cls; ma.n_neurons = B; ma.in_rows = rpf; ma.beam = beam;
     ma.next_tokens = tok_next; ma.next_lp = next_lp; ma.backptr = backptr;
     ma.hist_tok = hist_tok + static_cast<size_t>(t) * R; ma.hist_bp = hist_bp + static_cast<size_t>(t) * R;
+    ma.skip = d_done; ma.cur_lp = last_lp; ma.stop_index = cfg.stop_index;
     RC(launch_beam_merge(ma, st));
     GatherArgs ga{};
     ga.backptr = backptr; ga.R = R; ga.H = H;
     ga.src_hi = hnew[0]; ga.src_lo = hnew[1]; ga.src_pitch = H;
     ga.dst_hi = Alstm[0] + E + F; ga.dst_lo = split ? Alstm[1] + E + F : nullptr; ga.dst_pitch = E + F + H;
-    ga.c_src = cnew; ga.c_dst = c;
+    ga.c_src = cnew; ga.c_dst = c; ga.skip = d_done;
     RC(launch_gather_state(ga, st));
     if (mi) {  // the LM state follows the same backpointers (AllenNLPDecoderState h_lm / c_lm)
       GatherArgs g0{};
       g0.backptr = backptr; g0.R = R; g0.H = Hl;
       g0.src_hi = lmnew0[0]; g0.src_lo = lmnew0[1]; g0.src_pitch = Hl;
       g0.dst_hi = Alm0[0] + El; g0.dst_lo = split ? Alm0[1] + El : nullptr; g0.dst_pitch = El + Hl;
-      g0.c_src = lm_c0n; g0.c_dst = lm_c0;
+      g0.c_src = lm_c0n; g0.c_dst = lm_c0; g0.skip = d_done;
       RC(launch_gather_state(g0, st));
       GatherArgs g1{};
       g1.backptr = backptr; g1.R = R; g1.H = Hl;
       g1.src_hi = lmnew1[0]; g1.src_lo = lmnew1[1]; g1.src_pitch = Hl;
       g1.dst_hi = Alm1[0] + Hl; g1.dst_lo = split ? Alm1[1] + Hl : nullptr; g1.dst_pitch = 2 * Hl;
-      g1.c_src = lm_c1n; g1.c_dst = lm_c1;
+      g1.c_src = lm_c1n; g1.c_dst = lm_c1; g1.skip = d_done;
       RC(launch_gather_state(g1, st));
     }
+    // allennlp: `if (last_predictions == end).all(): break` — evaluated on the device, later steps become no-ops
+    RC(launch_check_done(tok_next, R, cfg.stop_index, d_done, st));
     std::swap(tok_cur, tok_next);
     std::swap(last_lp, next_lp);
   }
