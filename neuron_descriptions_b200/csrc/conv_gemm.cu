@@ -25,16 +25,17 @@ namespace {
 
 constexpr int kNumThreads = 352;
 constexpr int kEpiThreads = 256;
-constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KiB: one 128-row x 64-col bf16 plane
+constexpr int kTileBytes = kGemmBlockM * 64 * 2;  // 16 KiB: one 128-row x 64-col bf16 plane (epilogue tiles)
 constexpr int kSmemBudget = 224 * 1024;
 
-template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK>
 struct SmemLayout {
-  static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
+  static constexpr int kABytes = kGemmBlockM * BK * 2;  // one A plane per stage (BK = 64: 16 KiB, SW128; 32: SW64)
+  static constexpr int kBBytes = BLOCK_N * BK * 2;
   static constexpr int kPlanes = SPLIT ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kABytes : 0;            // one 64-col chunk
-  static constexpr int kResBytes = (EPI == EPI_BF16 && HAS_RES) ? 2 * kPlanes * kABytes : 0;  // 2-deep ring
+  static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kTileBytes : 0;            // one 64-col chunk
+  static constexpr int kResBytes = (EPI == EPI_BF16 && HAS_RES) ? 2 * kPlanes * kTileBytes : 0;  // 2-deep ring
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kResBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarrierBytes = 512;
@@ -46,11 +47,12 @@ struct SmemLayout {
 // byte offset of 16-byte chunk j of row r inside a [128][128 B] tile with the TMA/UMMA 128-byte swizzle
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
 
-template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p,
                                                                    const int* __restrict__ skip_flag) {
   if (skip_flag != nullptr && *skip_flag != 0) return;  // uniform: whole grid exits before touching any barrier
-  using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
+  using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES, BK>;
+  constexpr int kABytes = L::kABytes;
   constexpr int kStages = L::kStages;
   constexpr int kTmemBufs = 4;                 // accumulator ring
   constexpr uint32_t kTmemCols = kTmemBufs * BLOCK_N;  // 512 or 256 columns (power of two)
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int cin_blocks = p.cin / kGemmBlockK;
+  const int cin_blocks = p.cin / BK;
   const int num_kb = p.num_taps * cin_blocks;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
@@ -139,12 +141,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               tma_load_5d(st, &p.tmap_a[0][0], &full_bar[stage], 0, w0, p.tap_dw[tap], ch, n0);
               if (SPLIT) tma_load_5d(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 0, w0, p.tap_dw[tap], ch, n0);
             } else {
-              tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+              tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * BK, cw, ch, n0);
               if (SPLIT)
-                tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * kGemmBlockK, cw, ch, n0);
+                tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
             }
             uint8_t* sb = st + L::kPlanes * kABytes;
-            const int kcoord = (tap * cin_blocks + cb) * kGemmBlockK;
+            const int kcoord = (tap * cin_blocks + cb) * BK;
             tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
             if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -175,12 +177,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
             const uint32_t b_hi = a_hi + L::kPlanes * kABytes;
-            const uint64_t da_hi = make_smem_desc_sw128(a_hi);
-            const uint64_t db_hi = make_smem_desc_sw128(b_hi);
-            const uint64_t da_lo = make_smem_desc_sw128(a_hi + kABytes);
-            const uint64_t db_lo = make_smem_desc_sw128(b_hi + L::kBBytes);
+            const uint64_t da_hi = make_smem_desc_k<BK>(a_hi);
+            const uint64_t db_hi = make_smem_desc_k<BK>(b_hi);
+            const uint64_t da_lo = make_smem_desc_k<BK>(a_hi + kABytes);
+            const uint64_t db_lo = make_smem_desc_k<BK>(b_hi + L::kBBytes);
 #pragma unroll
-            for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            for (int k = 0; k < BK / 16; ++k) {
               const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
               umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
               if (SPLIT) {
@@ -212,11 +214,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const int col0 = n_tile * BLOCK_N + c * 64;
           if (col0 >= p.cout) break;
           mbar_wait(&res_empty_bar[rb], rphase ^ 1);
-          uint8_t* dst = res_smem + rb * (L::kPlanes * kABytes);
+          uint8_t* dst = res_smem + rb * (L::kPlanes * kTileBytes);
           mbar_arrive_expect_tx(&res_full_bar[rb], tx_bytes);
           tma_load_4d(dst, &p.tmap_res[0], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
           if (SPLIT)
-            tma_load_4d(dst + kABytes, &p.tmap_res[1], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h,
+            tma_load_4d(dst + kTileBytes, &p.tmap_res[1], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h,
                         tn * p.box_n);
           if (++rb == 2) { rb = 0; rphase ^= 1; }
         }
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           if (leader) tma_store_wait_read<0>();
           named_bar_sync(1, kEpiThreads);
           if (active) {
-            const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kABytes);
+            const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kTileBytes);
             if (p.bias != nullptr) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + group * 32);
 #pragma unroll
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               for (int pl = 0; pl < L::kPlanes; ++pl) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(rsrc + pl * kABytes + swz(row, group * 4 + j));
+                  const uint4 r = *reinterpret_cast<const uint4*>(rsrc + pl * kTileBytes + swz(row, group * 4 + j));
                   v[c][8 * j + 0] += bf16_lo_to_f32(r.x); v[c][8 * j + 1] += bf16_hi_to_f32(r.x);
                   v[c][8 * j + 2] += bf16_lo_to_f32(r.y); v[c][8 * j + 3] += bf16_hi_to_f32(r.y);
                   v[c][8 * j + 4] += bf16_lo_to_f32(r.z); v[c][8 * j + 5] += bf16_hi_to_f32(r.z);
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               *reinterpret_cast<uint4*>(staging + swz(row, group * 4 + j)) =
                   make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
               if (SPLIT)
-                *reinterpret_cast<uint4*>(staging + kABytes + swz(row, group * 4 + j)) =
+                *reinterpret_cast<uint4*>(staging + kTileBytes + swz(row, group * 4 + j)) =
                     make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
             if (HAS_RES) {
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           named_bar_sync(1, kEpiThreads);
           if (leader && active) {
             tma_store_4d(&p.tmap_out[0], staging, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
-            if (SPLIT) tma_store_4d(&p.tmap_out[1], staging + kABytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+            if (SPLIT) tma_store_4d(&p.tmap_out[1], staging + kTileBytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
             tma_store_commit();
           }
         }
@@ -380,10 +382,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_all_launches{0};
 
-template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK>
 int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
-  using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI, HAS_RES>;
+  using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES, BK>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI, HAS_RES, BK>;
   static bool configured = false;
   static std::mutex mu;
   {
@@ -412,17 +414,20 @@ void note_launch(int n) { g_all_launches.fetch_add(n, std::memory_order_relaxed)
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream, const int* skip_flag) {
   const bool res = p.has_res != 0;
-#define MILAN_DISPATCH(BN, SP, EP, RS)                                           \
-  if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS)        \
-    return launch_impl<BN, SP, EP, RS>(p, num_sms, stream, skip_flag);
-  MILAN_DISPATCH(128, true, EPI_BF16, false)
-  MILAN_DISPATCH(128, true, EPI_BF16, true)
-  MILAN_DISPATCH(128, false, EPI_BF16, false)
-  MILAN_DISPATCH(128, false, EPI_BF16, true)
-  MILAN_DISPATCH(64, true, EPI_BF16, false)
-  MILAN_DISPATCH(64, false, EPI_BF16, false)
-  MILAN_DISPATCH(128, true, EPI_F32, false)
-  MILAN_DISPATCH(128, false, EPI_F32, false)
+  const int bk = p.block_k == 32 ? 32 : 64;
+#define MILAN_DISPATCH(BN, SP, EP, RS, BKV)                                                  \
+  if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV)       \
+    return launch_impl<BN, SP, EP, RS, BKV>(p, num_sms, stream, skip_flag);
+  MILAN_DISPATCH(128, true, EPI_BF16, false, 64)
+  MILAN_DISPATCH(128, true, EPI_BF16, true, 64)
+  MILAN_DISPATCH(128, false, EPI_BF16, false, 64)
+  MILAN_DISPATCH(128, false, EPI_BF16, true, 64)
+  MILAN_DISPATCH(64, true, EPI_BF16, false, 64)
+  MILAN_DISPATCH(64, false, EPI_BF16, false, 64)
+  MILAN_DISPATCH(64, true, EPI_BF16, false, 32)   // stem: 64-byte k-blocks (SWIZZLE_64B)
+  MILAN_DISPATCH(64, false, EPI_BF16, false, 32)
+  MILAN_DISPATCH(128, true, EPI_F32, false, 64)
+  MILAN_DISPATCH(128, false, EPI_F32, false, 64)
 #undef MILAN_DISPATCH
   return static_cast<int>(cudaErrorInvalidValue);
 }
@@ -450,7 +455,7 @@ EncodeTiledFn get_encode_fn() {
 const char* tmap_last_error() { return g_tmap_err; }
 
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box) {
+                 const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled entry point unavailable");
@@ -466,7 +471,9 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
     if (i + 1 < rank) s[i] = strides_bytes[i];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s,
-                  b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     int n = snprintf(g_tmap_err, sizeof g_tmap_err, "cuTensorMapEncodeTiled(rank %d) failed: %d base=%p dims=(", rank,
@@ -495,11 +502,11 @@ int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uin
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes,
-                 uint32_t box_rows) {
+                 uint32_t box_rows, int block_k) {
   const uint64_t dims[2] = {k, rows};
   const uint64_t strides[1] = {pitch_bytes};
-  const uint32_t box[2] = {static_cast<uint32_t>(kGemmBlockK), box_rows};
-  return make_tmap_nd(out, base, 2, dims, strides, box);
+  const uint32_t box[2] = {static_cast<uint32_t>(block_k), box_rows};
+  return make_tmap_nd(out, base, 2, dims, strides, box, block_k * 2);
 }
 
 void choose_box(int W, int H, int N, int* bw, int* bh, int* bn) {

@@ -38,6 +38,7 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap tmap_res[2];   // [hi|lo] EPI_BF16 + residual: same geometry as tmap_out, TMA load
   int stem_mode;             // 1: A is the 5-D overlapping-window map of the 7x7/2 stem (see build_stem_params)
   int has_res;               // residual add in the epilogue
+  int block_k;               // k-block width in elements: 64 (default, 128B swizzle) or 32 (stem, 64B swizzle)
   int kb_per_chunk;          // k-blocks accumulated in TMEM before promotion to fp32 registers (0 = all)
   int fp16_operands;         // 1: A/B planes hold IEEE fp16 bit patterns (decoder GEMMs); 0: bf16 (encoder)
   int box_w, box_h, box_n;   // M tile = box_w*box_h*box_n (<=128) output pixels
@@ -77,10 +78,10 @@ int make_tmap_4d(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uin
                  uint32_t box_h, uint32_t box_n);
 // 2-D bf16 map: dims (k, rows), row pitch bytes, box (64, box_rows).
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t pitch_bytes,
-                 uint32_t box_rows);
+                 uint32_t box_rows, int block_k = kGemmBlockK);
 // Generic bf16 map of `rank` dims (dims[0] innermost; strides_bytes[i] is the stride of dim i+1), 128B swizzle.
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box);
+                 const uint32_t* box, int swizzle_bytes = 128);
 const char* tmap_last_error();
 
 // Pick an M-tile box (bw, bh, bn) with bw*bh*bn <= 128 minimising the number of tiles for a WxHxN output.
@@ -119,18 +120,19 @@ struct ConvIO {
 int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n);
 
 // The 7x7 stride-2 stem as an implicit GEMM without im2col: the input is the zero-padded NHWC4 image
-// [N][232][240][4] (pixel (ih, iw) at (ih + 3, iw + 4); channel 3 = 0) and the k-block of filter row r is the
-// 128-byte window {16 pixels x 4 channels} of padded row 2*oh + r starting at pixel 2*ow, addressed by a 5-D tensor
-// map (k, ow, row parity, row pair, n) whose `ow` stride (16 B) is smaller than the window (overlapping boxes).
-// Only window pixels 1..7 carry weights. Weights: [64][7*64] (pack_stem_weights). Output: raw conv1
-// [N][112][112][64] through tmap_out. block_n is 64.
+// [N][232][232][4] (pixel (ih, iw) at (ih + 3, iw + 4); channel 3 = 0) and the k-block of filter row r is the
+// 64-byte window {8 pixels x 4 channels} of padded row 2*oh + r starting at pixel 2*ow, addressed by a 5-D tensor
+// map (k, ow, row parity, row pair, n) whose `ow` stride (16 B) is smaller than the window (overlapping boxes),
+// 64-byte swizzle, block_k = 32. Window pixel 0 carries zero weights. Weights: [64][7*32] (pack_stem_weights).
+// Output: raw conv1 [N][112][112][64] through tmap_out. block_n is 64.
 constexpr int kStemPadH = 232;
-constexpr int kStemPadW = 240;
-constexpr int kStemKTotal = 7 * 64;
+constexpr int kStemPadW = 232;
+constexpr int kStemBlockK = 32;
+constexpr int kStemKTotal = 7 * kStemBlockK;
 int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, const __nv_bfloat16* img_lo,
                       const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, __nv_bfloat16* out_hi,
                       __nv_bfloat16* out_lo, int split);
-// w: torchvision conv1.weight [64][3][7][7] -> packed [64][448] in the k order build_stem_params expects.
+// w: torchvision conv1.weight [64][3][7][7] -> packed [64][224] in the k order build_stem_params expects.
 void pack_stem_weights(const float* w, float* packed);
 
 // Plain GEMM out[M][ldc] (fp32) = A[M][K] * W[N][K]^T + bias, A given as bf16 hi/lo planes with row pitch

@@ -142,10 +142,10 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
 }
 
 void pack_stem_weights(const float* w, float* packed) {
-  // k = r*64 + sp*4 + c  <-  w[co][c][r][s = sp - 1]; zero for sp = 0, sp > 7, c = 3.
+  // k = r*32 + sp*4 + c  <-  w[co][c][r][s = sp - 1]; zero for sp = 0 and c = 3.
   for (int co = 0; co < 64; ++co) {
     for (int k = 0; k < kStemKTotal; ++k) {
-      const int r = k / 64, sp = (k / 4) & 15, c = k & 3;
+      const int r = k / kStemBlockK, sp = (k / 4) & 7, c = k & 3;
       const int s = sp - 1;
       float v = 0.f;
       if (s >= 0 && s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
@@ -160,8 +160,9 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
   memset(p, 0, sizeof(*p));
   const int O = 112;
   p->stem_mode = 1;
+  p->block_k = kStemBlockK;
   p->kb_per_chunk = split ? kEncoderKbPerChunk : 0;
-  p->cin = 64;   // one 128-byte k-block per filter row
+  p->cin = kStemBlockK;   // one 64-byte k-block per filter row
   p->cout = 64;
   p->n_tiles = 1;
   p->ldc = 64;
@@ -176,22 +177,23 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
   p->box_w = bw; p->box_h = bh; p->box_n = bn;
   p->tiles_w = (O + bw - 1) / bw; p->tiles_h = (O + bh - 1) / bh; p->tiles_n = (N + bn - 1) / bn;
   p->out_w = O; p->out_h = O; p->out_n = N;
-  p->a_box_bytes = static_cast<uint32_t>(bw) * bh * bn * 128;
+  p->a_box_bytes = static_cast<uint32_t>(bw) * bh * bn * kStemBlockK * 2;
   const uint64_t P = static_cast<uint64_t>(kStemPadW) * 4 * 2;  // padded row pitch in bytes
   const __nv_bfloat16* imgs[2] = {img_hi, img_lo};
   const __nv_bfloat16* ws[2] = {w_hi, w_lo};
   __nv_bfloat16* outs[2] = {out_hi, out_lo};
   const int np = split ? 2 : 1;
   for (int hl = 0; hl < np; ++hl) {
-    // dims: (k: 64 elems = 16 px x 4 ch, ow, row parity, row pair, n)
-    const uint64_t dims[5] = {64, static_cast<uint64_t>(O), 2, static_cast<uint64_t>(kStemPadH / 2),
+    // dims: (k: 32 elems = 8 px x 4 ch, ow, row parity, row pair, n)
+    const uint64_t dims[5] = {kStemBlockK, static_cast<uint64_t>(O), 2, static_cast<uint64_t>(kStemPadH / 2),
                               static_cast<uint64_t>(N)};
     const uint64_t strides[4] = {16, P, 2 * P, static_cast<uint64_t>(kStemPadH) * P};
-    const uint32_t box[5] = {64, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
-    int rc = make_tmap_nd(&p->tmap_a[hl][0], imgs[hl], 5, dims, strides, box);
+    const uint32_t box[5] = {kStemBlockK, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh),
+                             static_cast<uint32_t>(bn)};
+    int rc = make_tmap_nd(&p->tmap_a[hl][0], imgs[hl], 5, dims, strides, box, kStemBlockK * 2);
     if (rc) return rc;
     for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];
-    rc = make_tmap_2d(&p->tmap_b[hl], ws[hl], kStemKTotal, 64, kStemKTotal * 2, 64);
+    rc = make_tmap_2d(&p->tmap_b[hl], ws[hl], kStemKTotal, 64, kStemKTotal * 2, 64, kStemBlockK);
     if (rc) return rc;
     const uint64_t opitch = 64 * 2;
     rc = make_tmap_4d(&p->tmap_out[hl], outs[hl], 64, O, O, N, opitch, opitch * O, opitch * O * O, bw, bh, bn);

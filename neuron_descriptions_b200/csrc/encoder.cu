@@ -32,7 +32,7 @@ __device__ __forceinline__ float load_pixel<float>(const float* p) {
 }
 
 // Normalise + repack NCHW images into the zero-padded NHWC4 bf16 layout the stem GEMM reads through its 5-D
-// overlapping-window tensor map: [n][232][240][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
+// overlapping-window tensor map: [n][232][232][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
 // One thread per padded pixel; 8-byte stores per plane, coalesced along x.
 template <typename T>
 __global__ void __launch_bounds__(256) stem_pack_kernel(const T* __restrict__ images, int n_images,

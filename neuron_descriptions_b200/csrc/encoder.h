@@ -10,7 +10,7 @@ constexpr int kMaskPyramidSize = 12544 + 3136 + 784 + 196 + 49;
 constexpr int kMaskLevelOffset[5] = {0, 12544, 15680, 16464, 16660};
 
 // dtype: 0 = uint8, 1 = float32. images NCHW (n,3,224,224); masks (n,1,224,224).
-// -> padded NHWC4 [n][232][240][4] (see conv_gemm.h build_stem_params)
+// -> padded NHWC4 [n][232][232][4] (see conv_gemm.h build_stem_params)
 int launch_stem_pack(const void* images, int dtype, int n_images, __nv_bfloat16* p_hi, __nv_bfloat16* p_lo,
                      const float mean[3], const float stdv[3], int split, cudaStream_t stream);
 int launch_mask_pyramid(const void* masks, int dtype, int n_images, float* wts, cudaStream_t stream);

@@ -158,6 +158,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                    // SWIZZLE_128B
   return d;
 }
+// Same for [rows][32] tiles (64-byte rows, TMA SWIZZLE_64B): 8-row atoms of 512 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
+  return d;
+}
+template <int BK>
+__device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t smem_addr) {
+  return BK == 64 ? make_smem_desc_sw128(smem_addr) : make_smem_desc_sw64(smem_addr);
+}
 // Instruction descriptor: A,B = bf16 (format 1) or fp16 (format 0), K-major, D = fp32, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_16bit(uint32_t M, uint32_t N, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
