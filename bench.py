@@ -29,6 +29,8 @@ METRIC = 'neurons described/sec (k=15, beam=50)'
 UNIT = 'neurons/s'
 K_EXEMPLARS, BEAM, LENGTH, GROUP = 15, 50, 15, 16
 CONV_FLOP_PER_NEURON = 2.0 * 7.79935744e9 * K_EXEMPLARS  # 104 convs through layer4
+# every conv input / residual / output tensor touched once as (hi, lo) bf16 planes
+CONV_BYTES_PER_NEURON = 157.5e9 / 64
 WORKLOAD = ('alexnet/imagenet 1k neurons, k=15, beam=50 + PMI rerank (synthetic exemplars of that shape, '
             'random-init MILAN resnet101 encoder + attention-LSTM decoder + LSTM LM, V=5004)')
 
@@ -288,6 +290,10 @@ def main():
             'algorithmic_flop_per_launch': CONV_FLOP_PER_NEURON * nb * steps / conv_launches,
             'avg_launch_ms': conv_ms / conv_launches, 'conv_share_of_step': conv_ms / ms_res,
             'mma_flop_multiplier': 3 if args.precision == 'split' else 1,
+            'tensor_pipe_frac_incl_split': achieved * (3 if args.precision == 'split' else 1) / peak,
+            'algorithmic_bytes_per_launch': CONV_BYTES_PER_NEURON * nb * steps / conv_launches,
+            'hbm_gbs_while_convs_run': CONV_BYTES_PER_NEURON * nb * steps / (conv_ms / 1e3) / 1e9,
+            'hbm_peak_gbs': peaks['hbm_gbs'],
         },
         'phases_ms_per_step': {'encoder_convs': conv_ms / steps, 'step_total': ms_res / steps},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nb * K_EXEMPLARS * 4 * 224 * 224,
