@@ -108,6 +108,7 @@ class Decoder:
         self.max_neurons = max_neurons
         self._state_dict: Dict[str, torch.Tensor] = {}
         self._engine: Optional[Engine] = None
+        self._capacity = {'max_beam': max(50, beam_size), 'max_length': max(15, length), 'max_keys': 15}
 
     # ------------------------------------------------------------------ module-ish plumbing
     @property
@@ -169,13 +170,27 @@ class Decoder:
                               attention_size=self.attention_hidden_size, feature_size=self.feature_size,
                               lm_embedding_size=self.lm.embedding_size if self.lm else 128,
                               lm_hidden_size=self.lm.hidden_size if self.lm else 512, precision=self.precision,
-                              max_neurons=self.max_neurons, max_beam=max(50, self.beam_size),
-                              max_length=max(15, self.length))
+                              max_neurons=self.max_neurons, **self._capacity)
         if hasattr(self.encoder, 'bind'):
             self.encoder.bind(self._engine)
         if self.lm is not None:
             self.lm.bind(self._engine)
         return self
+
+    def _ensure_capacity(self, length: int, beam_size: int, n_keys: int):
+        """Grow the engine workspace when a call asks for a longer decode, a wider beam or more exemplars per
+        neuron than it was sized for (the reference has no such limits)."""
+        wanted = {'max_beam': beam_size, 'max_length': length, 'max_keys': n_keys}
+        if all(wanted[key] <= self._capacity[key] for key in wanted):
+            return
+        if wanted['max_beam'] > 64:
+            raise ValueError(f'beam_size {beam_size} exceeds the engine limit of 64')
+        self._capacity = {key: max(self._capacity[key], wanted[key]) for key in wanted}
+        if self._engine is not None:
+            device = self._engine.device
+            self._engine.close()
+            self._engine = None
+            self.to(device)
 
     def cuda(self, device=None):
         return self.to(torch.device('cuda', device) if device is not None else 'cuda')
@@ -228,8 +243,11 @@ class Decoder:
             if strategy.shape[-1] != length:
                 raise ValueError(f'strategy must have length {length}, got {strategy.shape[-1]}')
 
-        engine = self.engine
+        self.engine  # raises if not on a CUDA device
         features = self.encode(images_or_features, masks=masks) if encode else images_or_features
+        self._ensure_capacity(length, beam_size if strategy in (STRATEGY_BEAM, STRATEGY_RERANK) else 1,
+                              features.shape[1])
+        engine = self.engine
         features = features.to(engine.device, torch.float32)
 
         predictions = attentions = beam_captions = beam_scores = beam_tokens = None

@@ -278,6 +278,12 @@ def test_facade_matches_reference_surface(full_sd):
     assert out.tokens.shape == (3, 15) and out.predictions.shape == (3, 15, V) and out.attentions.shape == (3, 15, 15)
     with pytest.raises(ValueError, match='unknown strategy'):
         decoder(images_f, masks_f, strategy='nope')
+    # a longer decode / wider beam than the engine was sized for grows the workspace transparently
+    feats = decoder.encode(images_f.cuda(), masks_f.cuda())
+    longer = decoder(feats, strategy='beam', mi=False, length=18, beam_size=60)
+    ref_long = O.decode(feats.cpu(), full_sd, VOCAB, strategy='beam', mi=False, length=18, beam_size=60)
+    assert longer.beam_tokens.shape[-1] == ref_long.beam_tokens.shape[-1]
+    torch.testing.assert_close(longer.beam_scores.cpu(), ref_long.beam_scores, atol=LOGP_TOL, rtol=0)
     with pytest.raises(ValueError, match='cannot set `mi=` decoding when reranking'):
         decoder(images_f, masks_f, strategy='rerank', mi=True)
     with pytest.raises(ValueError, match='strategy must have length'):
