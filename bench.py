@@ -122,7 +122,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 4
+    sample = GROUP  # one reference batch (16 neurons, ~6 s of CPU work) per step
     for _ in range(args.warmup if args.warmup < 1 else 1):
         cpu_oracle_neurons_per_s(1, threads)
     times = []
@@ -306,10 +306,10 @@ def main():
         line['fast_mode'] = fast
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = 4
+        sample = 2 * GROUP  # two reference batches: ~10-15 s of CPU work
         nps, elapsed = cpu_oracle_neurons_per_s(sample, threads)
         line['cpu_baseline'] = {'value': nps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                'sample': f'{sample} neurons (60 exemplars) through the oracle port of the reference '
+                                'sample': f'{sample} neurons ({sample * K_EXEMPLARS} exemplars) through the oracle port of the reference '
                                           f'PyTorch CPU path, rerank beam 50, {elapsed:.1f} s'}
     if rank == 0:
         print(json.dumps(line), flush=True)
