@@ -28,7 +28,7 @@ def to_us(value, unit):
 def launches(path, out):
     with open(path) as handle:
         lines = [line for line in handle if not line.startswith('==')]
-    rows = list(csv.DictReader(lines))
+    rows = [row for row in csv.DictReader(lines) if row['Metric Name'] == 'gpu__time_duration.sum']
     total, count = collections.OrderedDict(), collections.Counter()
     for row in rows:
         name = re.sub(r'\(.*', '', row['Kernel Name']).replace('void ', '').replace('unnamed>::', '')
