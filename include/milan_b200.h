@@ -71,7 +71,7 @@ int milan_engine_finalize(MilanEngine* engine);
 
 /* PyramidConvEncoder.forward (src/milan/encoders.py:286-320) for n_images images.
  * d_images: (n,3,224,224) uint8 [0,255] or float32 [0,1]; d_masks: (n,1,224,224) uint8/float32, or NULL for
- * all-ones masks; d_features_out: (n, feature_size). */
+ * all-ones masks; d_features_out: (n, feature_size). d_images must be 16-byte aligned (vector loads). */
 int milan_encode(MilanEngine* engine, const void* d_images, const void* d_masks, int32_t n_images, int32_t dtype,
                  float* d_features_out, void* stream);
 

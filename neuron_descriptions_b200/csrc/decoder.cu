@@ -263,33 +263,65 @@ __device__ __forceinline__ unsigned float_key(float x) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// log_softmax of one row into shared memory; returns nothing, pred_s[v] filled. (decoders.py:621, :624-630)
-__device__ __forceinline__ void row_log_softmax(const float* __restrict__ x, int V, float* pred_s, float* red,
-                                                float scale_sub, bool subtract) {
-  float mx = -INFINITY;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, x[v]);
-  mx = block_max(mx, red);
-  float s = 0.f;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(x[v] - mx);
-  s = block_sum(s, red);
-  const float lse = logf(s);
+// log_softmax of one row into shared memory (decoders.py:621, :624-630). The row is read from global memory once
+// (128-bit loads; rows are 16-byte aligned because ld % 4 == 0) and normalised in place; with `subtract` the
+// row's log-softmax is scaled and subtracted from pred_s instead (MI decoding), streaming from global.
+// Returns this thread's maximum of the values it wrote (used by the beam top-k prefilter).
+__device__ __forceinline__ float row_log_softmax(const float* __restrict__ x, int V, float* pred_s, float* red,
+                                                 float scale_sub, bool subtract) {
+  float tmax = -INFINITY;
   if (!subtract) {
-    for (int v = threadIdx.x; v < V; v += blockDim.x) pred_s[v] = (x[v] - mx) - lse;
+    float mx = -INFINITY;
+    const int V4 = V >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int v = threadIdx.x; v < V4; v += blockDim.x) {
+      const float4 q = __ldg(x4 + v);
+      *reinterpret_cast<float4*>(pred_s + 4 * v) = q;
+      mx = fmaxf(fmaxf(mx, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+    }
+    for (int v = 4 * V4 + threadIdx.x; v < V; v += blockDim.x) {
+      const float q = x[v];
+      pred_s[v] = q;
+      mx = fmaxf(mx, q);
+    }
+    mx = block_max(mx, red);  // barriers inside also publish pred_s
+    float s = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(pred_s[v] - mx);
+    s = block_sum(s, red);
+    const float lse = logf(s);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float y = (pred_s[v] - mx) - lse;
+      pred_s[v] = y;
+      tmax = fmaxf(tmax, y);
+    }
   } else {
-    for (int v = threadIdx.x; v < V; v += blockDim.x) pred_s[v] -= scale_sub * ((x[v] - mx) - lse);
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, x[v]);
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(x[v] - mx);
+    s = block_sum(s, red);
+    const float lse = logf(s);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float y = pred_s[v] - scale_sub * ((x[v] - mx) - lse);
+      pred_s[v] = y;
+      tmax = fmaxf(tmax, y);
+    }
   }
   __syncthreads();
+  return tmax;
 }
 
+constexpr int kPrefilterCap = 1024;
 __global__ void __launch_bounds__(256) row_kernel(const RowArgs a) {
   if (a.skip != nullptr && *a.skip) return;
   extern __shared__ float pred_s[];  // [V]
   __shared__ float red[8];
   __shared__ ValIdx redvi[8];
   const int r = blockIdx.x;
-  row_log_softmax(a.logits + static_cast<long long>(r) * a.ld, a.V, pred_s, red, 0.f, false);
+  float tmax = row_log_softmax(a.logits + static_cast<long long>(r) * a.ld, a.V, pred_s, red, 0.f, false);
   if (a.logits_lm != nullptr)
-    row_log_softmax(a.logits_lm + static_cast<long long>(r) * a.ld, a.V, pred_s, red, a.temperature, true);
+    tmax = row_log_softmax(a.logits_lm + static_cast<long long>(r) * a.ld, a.V, pred_s, red, a.temperature, true);
   if (a.pred_out != nullptr) {
     float* po = a.pred_out + static_cast<long long>(r) * a.pred_pitch;
     for (int v = threadIdx.x; v < a.V; v += blockDim.x) po[v] = pred_s[v];
@@ -327,7 +359,54 @@ __global__ void __launch_bounds__(256) row_kernel(const RowArgs a) {
     }
     return;
   }
-  // Exact top-`beam` by MSB radix select on order-preserving keys (4 passes of 8 bits), then rank the survivors.
+  // Exact top-`beam`, fast path: the beam-th largest of 64 thread-group maxima is a lower bound of the
+  // beam-th largest value of the row (beam <= kMaxBeam = 64), so only the (typically ~beam) elements >= that bound can be selected;
+  // they are compacted and ranked exactly (ties: lower class index first, like the radix path below).
+  {
+    __shared__ float gmax_s[64];
+    __shared__ float tau_s;
+    __shared__ int n_cand;
+    __shared__ float pval[kPrefilterCap];
+    __shared__ int pidx[kPrefilterCap];
+    // maxima of 64 groups of 4 threads; the beam-th largest of them bounds the beam-th largest value from below
+    float gmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
+    if ((threadIdx.x & 3) == 0) gmax_s[threadIdx.x >> 2] = gmax;
+    if (threadIdx.x == 0) n_cand = 0;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const ValIdx me{gmax_s[threadIdx.x], static_cast<int>(threadIdx.x)};
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < 64; ++j) rank += better(ValIdx{gmax_s[j], j}, me) ? 1 : 0;
+      if (rank == a.beam - 1) tau_s = me.v;
+    }
+    __syncthreads();
+    const float tau = tau_s;
+    for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
+      const float x = pred_s[v];
+      if (x >= tau) {
+        const int pos = atomicAdd(&n_cand, 1);
+        if (pos < kPrefilterCap) { pval[pos] = x; pidx[pos] = v; }
+      }
+    }
+    __syncthreads();
+    const int nc = n_cand;
+    if (nc <= kPrefilterCap) {  // uniform
+      for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+        const ValIdx me{pval[i], pidx[i]};
+        int rank = 0;
+        for (int j = 0; j < nc; ++j) rank += better(ValIdx{pval[j], pidx[j]}, me) ? 1 : 0;
+        if (rank < a.beam) {
+          cv[rank] = me.v + lp;
+          cc[rank] = me.i;
+        }
+      }
+      return;
+    }
+  }
+  // Fallback (more than kPrefilterCap values tie with / exceed the bound, e.g. masses of equal or -inf logits):
+  // exact top-`beam` by MSB radix select on order-preserving keys (4 passes of 8 bits), then rank the survivors.
   __shared__ unsigned hist[256];
   __shared__ unsigned warp_tot[8];
   __shared__ unsigned sel_digit, sel_need;
@@ -410,12 +489,17 @@ __global__ void __launch_bounds__(256) row_kernel(const RowArgs a) {
 }
 
 // ------------------------------------------------------------------ beam merge: one warp per neuron
-__global__ void __launch_bounds__(32) beam_merge_kernel(const MergeArgs a) {
+// The candidate lists of the neuron's source rows (each sorted descending) are staged in shared memory with
+// coalesced loads; the beam-step merge then runs on shared memory and the results are written in parallel.
+__global__ void __launch_bounds__(128) beam_merge_kernel(const MergeArgs a) {
+  __shared__ float val_s[kMaxBeam * kMaxBeam];
+  __shared__ int flat_s[kMaxBeam];
+  __shared__ float best_s[kMaxBeam];
   const int nrn = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   if (a.skip != nullptr && *a.skip) {
     // every beam of every neuron has ended: the reference would have left its loop; keep the beams as they are
-    for (int j = lane; j < a.beam; j += 32) {
+    for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
       const int out = nrn * a.beam + j;
       a.next_tokens[out] = a.stop_index;
       a.next_lp[out] = a.cur_lp[out];
@@ -426,14 +510,17 @@ __global__ void __launch_bounds__(32) beam_merge_kernel(const MergeArgs a) {
     return;
   }
   const int row_base = nrn * a.in_rows;
+  const int n_cand = a.in_rows * a.beam;
+  const float* cand = a.cand_val + static_cast<long long>(row_base) * a.beam;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n_cand; i += blockDim.x) val_s[i] = cand[i];
+  __syncthreads();
   int ptr0 = 0, ptr1 = 0;  // heads of source rows lane and lane+32
   const int r0 = lane, r1 = lane + 32;
-  for (int j = 0; j < a.beam; ++j) {
+  for (int j = 0; threadIdx.x < 32 && j < a.beam; ++j) {
     ValIdx c0{-INFINITY, 0x7fffffff}, c1{-INFINITY, 0x7fffffff};
-    if (r0 < a.in_rows && ptr0 < a.beam)
-      c0 = ValIdx{a.cand_val[static_cast<long long>(row_base + r0) * a.beam + ptr0], r0 * a.beam + ptr0};
-    if (r1 < a.in_rows && ptr1 < a.beam)
-      c1 = ValIdx{a.cand_val[static_cast<long long>(row_base + r1) * a.beam + ptr1], r1 * a.beam + ptr1};
+    if (r0 < a.in_rows && ptr0 < a.beam) c0 = ValIdx{val_s[r0 * a.beam + ptr0], r0 * a.beam + ptr0};
+    if (r1 < a.in_rows && ptr1 < a.beam) c1 = ValIdx{val_s[r1 * a.beam + ptr1], r1 * a.beam + ptr1};
     ValIdx best = better(c1, c0) ? c1 : c0;
     best = warp_argmax(best);
     int flat = best.i;
@@ -442,14 +529,21 @@ __global__ void __launch_bounds__(32) beam_merge_kernel(const MergeArgs a) {
     if (src == r0) ++ptr0;
     if (src == r1) ++ptr1;
     if (lane == 0) {
-      const int out = nrn * a.beam + j;
-      const int cls = a.cand_cls[static_cast<long long>(row_base) * a.beam + flat];
-      a.next_tokens[out] = cls;
-      a.next_lp[out] = best.v;
-      a.backptr[out] = row_base + src;
-      a.hist_tok[out] = cls;
-      a.hist_bp[out] = src;
+      flat_s[j] = flat;
+      best_s[j] = best.v;
     }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
+    const int out = nrn * a.beam + j;
+    const int flat = flat_s[j];
+    const int src = flat / a.beam;
+    const int cls = a.cand_cls[static_cast<long long>(row_base) * a.beam + flat];
+    a.next_tokens[out] = cls;
+    a.next_lp[out] = best_s[j];
+    a.backptr[out] = row_base + src;
+    a.hist_tok[out] = cls;
+    a.hist_bp[out] = src;
   }
 }
 
@@ -531,11 +625,34 @@ __global__ void __launch_bounds__(256) lm_accumulate_kernel(const LmAccumArgs a)
   const bool keep = a.t < T && a.t <= first_stop + 1;
   if (!keep) return;  // uniform across the block
   const float* x = a.logits + static_cast<long long>(m) * a.ld;
+  // one pass over the row: this thread's elements stay in registers between the max and the sum (V <= 8192),
+  // longer rows fall back to re-reading.
+  constexpr int kKeep = 8;
+  float4 q[kKeep];
+  const int V4 = a.V >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
   float mx = -INFINITY;
-  for (int v = threadIdx.x; v < a.V; v += blockDim.x) mx = fmaxf(mx, x[v]);
+#pragma unroll
+  for (int i = 0; i < kKeep; ++i) {
+    const int v = threadIdx.x + i * 256;
+    q[i] = v < V4 ? __ldg(x4 + v) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    mx = fmaxf(fmaxf(mx, fmaxf(q[i].x, q[i].y)), fmaxf(q[i].z, q[i].w));
+  }
+  for (int v = threadIdx.x + kKeep * 256; v < V4; v += 256) {
+    const float4 t = __ldg(x4 + v);
+    mx = fmaxf(fmaxf(mx, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+  }
+  for (int v = 4 * V4 + threadIdx.x; v < a.V; v += 256) mx = fmaxf(mx, x[v]);
   mx = block_max(mx, red);
   float s = 0.f;
-  for (int v = threadIdx.x; v < a.V; v += blockDim.x) s += expf(x[v] - mx);
+#pragma unroll
+  for (int i = 0; i < kKeep; ++i)
+    if (threadIdx.x + i * 256 < V4) s += (expf(q[i].x - mx) + expf(q[i].y - mx)) + (expf(q[i].z - mx) + expf(q[i].w - mx));
+  for (int v = threadIdx.x + kKeep * 256; v < V4; v += 256) {
+    const float4 t = __ldg(x4 + v);
+    s += (expf(t.x - mx) + expf(t.y - mx)) + (expf(t.z - mx) + expf(t.w - mx));
+  }
+  for (int v = 4 * V4 + threadIdx.x; v < a.V; v += 256) s += expf(x[v] - mx);
   s = block_sum(s, red);
   if (threadIdx.x == 0) a.lm_scores[m] += (x[seq[a.t]] - mx) - logf(s);
 }
@@ -646,7 +763,7 @@ int launch_row_logsoftmax(const RowArgs& a, cudaStream_t stream) {
 }
 int launch_beam_merge(const MergeArgs& a, cudaStream_t stream) {
   if (a.in_rows > 64 || a.beam > kMaxBeam) return static_cast<int>(cudaErrorInvalidValue);
-  beam_merge_kernel<<<a.n_neurons, 32, 0, stream>>>(a);
+  beam_merge_kernel<<<a.n_neurons, 128, 0, stream>>>(a);
   return last_err();
 }
 int launch_gather_state(const GatherArgs& a, cudaStream_t stream) {

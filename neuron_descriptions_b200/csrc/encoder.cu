@@ -26,41 +26,69 @@ __device__ __forceinline__ float load_pixel<uint8_t>(const uint8_t* p) {
   // src/deps/netdissect/renormalize.py:118-139)
   return __fmul_rn(static_cast<float>(*p), 0.00392156862745098f);  // no FMA contraction with the mean subtract
 }
+
+template <typename T>
+__device__ __forceinline__ void load_pixels4(const T* p, float (&v)[4]);
 template <>
-__device__ __forceinline__ float load_pixel<float>(const float* p) {
-  return *p;
+__device__ __forceinline__ void load_pixels4<uint8_t>(const uint8_t* p, float (&v)[4]) {
+  const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+  const uint8_t b[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = load_pixel<uint8_t>(&b[j]);
+}
+template <>
+__device__ __forceinline__ void load_pixels4<float>(const float* p, float (&v)[4]) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
 
 // Normalise + repack NCHW images into the zero-padded NHWC4 bf16 layout the stem GEMM reads through its 5-D
 // overlapping-window tensor map: [n][232][232][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
-// One thread per padded pixel; 8-byte stores per plane, coalesced along x.
+// One thread per 4 consecutive padded pixels (the x padding of 4 keeps every group fully inside or fully outside
+// the image): one 4-pixel load per channel, two 16-byte stores per plane.
 template <typename T>
 __global__ void __launch_bounds__(256) stem_pack_kernel(const T* __restrict__ images, int n_images,
                                                         __nv_bfloat16* __restrict__ p_hi,
                                                         __nv_bfloat16* __restrict__ p_lo, float3 mean, float3 stdv,
                                                         int split) {
-  constexpr int PH = kStemPadH, PW = kStemPadW;
+  constexpr int PH = kStemPadH, PW4 = kStemPadW / 4;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n_images) * PH * PW;
+  const long long total = static_cast<long long>(n_images) * PH * PW4;
   if (idx >= total) return;
-  const int x = idx % PW;
-  const int y = (idx / PW) % PH;
-  const int n = idx / (PH * PW);
-  const int ih = y - 3, iw = x - 4;
-  float v[3] = {0.f, 0.f, 0.f};
-  if (ih >= 0 && ih < kImg && iw >= 0 && iw < kImg) {
-    const T* img = images + static_cast<long long>(n) * 3 * kImg * kImg + static_cast<long long>(ih) * kImg + iw;
+  const int x4 = idx % PW4;
+  const int y = (idx / PW4) % PH;
+  const int n = idx / (PH * PW4);
+  const int ih = y - 3, iw0 = 4 * x4 - 4;
+  float v[3][4] = {};
+  if (ih >= 0 && ih < kImg && iw0 >= 0 && iw0 < kImg) {
+    const T* img = images + static_cast<long long>(n) * 3 * kImg * kImg + static_cast<long long>(ih) * kImg + iw0;
     const float m[3] = {mean.x, mean.y, mean.z};
     const float s[3] = {stdv.x, stdv.y, stdv.z};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(load_pixel<T>(img + c * kImg * kImg), m[c]), s[c]);
-  }
-  __nv_bfloat16 h[3], l[3];
+    for (int c = 0; c < 3; ++c) {
+      load_pixels4<T>(img + c * kImg * kImg, v[c]);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) split_bf16(v[c], h[c], l[c]);
+      for (int j = 0; j < 4; ++j) v[c][j] = __fdiv_rn(__fsub_rn(v[c][j], m[c]), s[c]);
+    }
+  }
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-  *reinterpret_cast<uint2*>(p_hi + idx * 4) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], zero));
-  if (split) *reinterpret_cast<uint2*>(p_lo + idx * 4) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], zero));
+  uint32_t hw[8], lw[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat16 h[3], l[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) split_bf16(v[c][j], h[c], l[c]);
+    hw[2 * j] = pack_bf16x2(h[0], h[1]); hw[2 * j + 1] = pack_bf16x2(h[2], zero);
+    lw[2 * j] = pack_bf16x2(l[0], l[1]); lw[2 * j + 1] = pack_bf16x2(l[2], zero);
+  }
+  uint4* dh = reinterpret_cast<uint4*>(p_hi + idx * 16);
+  dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  dh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+  if (split) {
+    uint4* dl = reinterpret_cast<uint4*>(p_lo + idx * 16);
+    dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  }
 }
 
 template <typename T>
@@ -126,8 +154,9 @@ __global__ void __launch_bounds__(256) mask_pyramid_kernel(const T* __restrict__
   }
 }
 
-// pooled[n][c] = sum_p w[n][p] * (hi + lo)[n][p][c]. CTA = (image, 64-channel group); 8 warps stride pixels,
-// lane = 2 channels (one 4-byte load per plane, 128 B per warp per pixel). Zero-weight pixels are skipped.
+// pooled[n][c] = sum_p w[n][p] * (hi + lo)[n][p][c]. CTA = (image, 64-channel group); each warp takes chunks of
+// 32 consecutive pixels: one coalesced load of their weights, a ballot of the non-zero ones (masks are ~1-5 %
+// dense), then per surviving pixel lane = 2 channels (one 4-byte load per plane, 128 B per warp).
 __global__ void __launch_bounds__(256) masked_pool_kernel(const __nv_bfloat16* __restrict__ hi,
                                                           const __nv_bfloat16* __restrict__ lo,
                                                           const float* __restrict__ wts, int wts_stride, int P, int C,
@@ -139,18 +168,24 @@ __global__ void __launch_bounds__(256) masked_pool_kernel(const __nv_bfloat16* _
   const float* w = wts + static_cast<long long>(n) * wts_stride;
   const long long base = static_cast<long long>(n) * P * C + cg * 64 + lane * 2;
   float2 acc = make_float2(0.f, 0.f);
-  for (int p = warp; p < P; p += 8) {
-    const float wp = __ldg(w + p);
-    if (wp == 0.0f) continue;
-    const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + base + static_cast<long long>(p) * C));
-    float x0 = bf16_lo_to_f32(h), x1 = bf16_hi_to_f32(h);
-    if (lo != nullptr) {
-      const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + base + static_cast<long long>(p) * C));
-      x0 += bf16_lo_to_f32(l);
-      x1 += bf16_hi_to_f32(l);
+  for (int p0 = warp * 32; p0 < P; p0 += 8 * 32) {
+    const float mine = (p0 + lane < P) ? __ldg(w + p0 + lane) : 0.0f;
+    unsigned live = __ballot_sync(0xffffffffu, mine != 0.0f);
+    while (live != 0u) {
+      const int src = __ffs(live) - 1;
+      live &= live - 1;
+      const float wp = __shfl_sync(0xffffffffu, mine, src);
+      const long long off = base + static_cast<long long>(p0 + src) * C;
+      const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + off));
+      float x0 = bf16_lo_to_f32(h), x1 = bf16_hi_to_f32(h);
+      if (lo != nullptr) {
+        const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + off));
+        x0 += bf16_lo_to_f32(l);
+        x1 += bf16_hi_to_f32(l);
+      }
+      acc.x = fmaf(wp, x0, acc.x);
+      acc.y = fmaf(wp, x1, acc.y);
     }
-    acc.x = fmaf(wp, x0, acc.x);
-    acc.y = fmaf(wp, x1, acc.y);
   }
   acc_s[warp][lane] = acc;
   __syncthreads();
@@ -221,7 +256,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
 
 int launch_stem_pack(const void* images, int dtype, int n_images, __nv_bfloat16* p_hi, __nv_bfloat16* p_lo,
                      const float mean[3], const float stdv[3], int split, cudaStream_t stream) {
-  const long long total = static_cast<long long>(n_images) * kStemPadH * kStemPadW;
+  const long long total = static_cast<long long>(n_images) * kStemPadH * (kStemPadW / 4);
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   const float3 m = make_float3(mean[0], mean[1], mean[2]);

@@ -594,6 +594,7 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   if (!cfg.has_encoder) return fail("engine was created without an encoder");
   if (n <= 0) return 0;
   if (n > cfg.max_images) return fail("milan_encode: n_images %d exceeds max_images %d", n, cfg.max_images);
+  if (reinterpret_cast<uintptr_t>(d_images) % 16 != 0) return fail("milan_encode: d_images must be 16-byte aligned");
   std::vector<Plan>* plans = nullptr;
   if (build_encoder_plans(n, &plans)) return 1;
   const int F = cfg.feature_size;
