@@ -29,6 +29,13 @@ typedef struct MilanEngine MilanEngine;
 enum { MILAN_PRECISION_SPLIT = 0, /* bf16 hi/lo split operands, 3 MMAs per k-block: fp32-class results */
        MILAN_PRECISION_FAST = 1   /* plain bf16 operands */ };
 enum { MILAN_DTYPE_U8 = 0, MILAN_DTYPE_F32 = 1 };
+/* Backbone of the image encoder (torchvision graphs; src/milan/encoders.py:214-216,326-351). */
+enum { MILAN_ENCODER_RESNET101 = 0, MILAN_ENCODER_RESNET50 = 1, MILAN_ENCODER_RESNET18 = 2,
+       MILAN_ENCODER_RESNET34 = 3 };
+/* PyramidConvEncoder: masked spatial pooling of conv1 + layer1..4 -> one vector per image
+ * (src/milan/encoders.py:286-320). SpatialConvEncoder: images * masks -> layer4 map -> 49 vectors per image
+ * (src/milan/encoders.py:193-214). */
+enum { MILAN_ENCODER_PYRAMID = 0, MILAN_ENCODER_SPATIAL = 1 };
 
 /* Model dimensions (reference: Decoder.__init__, src/milan/decoders.py:233-323; LanguageModel.__init__,
  * src/milan/lms.py:20-56; PyramidConvEncoder('resnet101'), src/milan/encoders.py:251-284,346-350). */
@@ -50,6 +57,8 @@ typedef struct MilanConfig {
   int32_t max_beam;          /* <= 64 */
   int32_t max_keys;          /* exemplars per neuron, 15 */
   int32_t max_length;        /* decode length, 15 */
+  int32_t encoder_arch;      /* MILAN_ENCODER_RESNET*; 0 = resnet101, the encoder of every shipped checkpoint */
+  int32_t encoder_kind;      /* MILAN_ENCODER_PYRAMID (feature_size 3904 / 1024) or _SPATIAL (resnet18: 512) */
 } MilanConfig;
 
 const char* milan_version(void);
@@ -71,7 +80,8 @@ int milan_engine_finalize(MilanEngine* engine);
 
 /* PyramidConvEncoder.forward (src/milan/encoders.py:286-320) for n_images images.
  * d_images: (n,3,224,224) uint8 [0,255] or float32 [0,1]; d_masks: (n,1,224,224) uint8/float32, or NULL for
- * all-ones masks; d_features_out: (n, feature_size). d_images must be 16-byte aligned (vector loads). */
+ * all-ones masks; d_features_out: (n, feature_size) for a pyramid encoder, (n, 49, feature_size) for a spatial one.
+ * d_images (and d_masks of a spatial encoder) must be 16-byte aligned (vector loads). */
 int milan_encode(MilanEngine* engine, const void* d_images, const void* d_masks, int32_t n_images, int32_t dtype,
                  float* d_features_out, void* stream);
 

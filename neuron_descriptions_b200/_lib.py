@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, 'libmilan_b200.so')
 PRECISION_SPLIT, PRECISION_FAST = 0, 1
 DTYPE_U8, DTYPE_F32 = 0, 1
 STRATEGY_GREEDY, STRATEGY_BEAM, STRATEGY_RERANK = 0, 1, 2
+ENCODER_ARCHS = {'resnet101': 0, 'resnet50': 1, 'resnet18': 2, 'resnet34': 3}
+ENCODER_KINDS = {'pyramid': 0, 'spatial': 1}
 
 
 class MilanConfig(ctypes.Structure):
@@ -20,7 +22,7 @@ class MilanConfig(ctypes.Structure):
     _fields_ = [(name, c_int32) for name in (
         'vocab_size', 'embedding_size', 'hidden_size', 'attention_size', 'feature_size', 'start_index',
         'stop_index', 'has_encoder', 'has_lm', 'lm_embedding_size', 'lm_hidden_size', 'precision', 'max_images',
-        'max_neurons', 'max_beam', 'max_keys', 'max_length')]
+        'max_neurons', 'max_beam', 'max_keys', 'max_length', 'encoder_arch', 'encoder_kind')]
 
 
 # name -> (restype, argtypes); must list every function declared in include/milan_b200.h

@@ -424,6 +424,8 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
   MILAN_DISPATCH(128, false, EPI_BF16, true, 64)
   MILAN_DISPATCH(64, true, EPI_BF16, false, 64)
   MILAN_DISPATCH(64, false, EPI_BF16, false, 64)
+  MILAN_DISPATCH(64, true, EPI_BF16, true, 64)    // BasicBlock conv2 of layer1 (resnet18/34): 64 outputs + residual
+  MILAN_DISPATCH(64, false, EPI_BF16, true, 64)
   MILAN_DISPATCH(64, true, EPI_BF16, false, 32)   // stem: 64-byte k-blocks (SWIZZLE_64B)
   MILAN_DISPATCH(64, false, EPI_BF16, false, 32)
   MILAN_DISPATCH(128, true, EPI_F32, false, 64)

@@ -731,6 +731,14 @@ int launch_attend(const AttendArgs& a, cudaStream_t stream) {
   attn_scores_kernel<<<a.R, 256, smem1, stream>>>(a, a.attn_ws);
   note_launch();
   const size_t smem2 = static_cast<size_t>(a.rows_per_feature) * a.n_keys * sizeof(float);
+  static size_t configured2 = 0;
+  if (smem2 > 48 * 1024 && smem2 > configured2) {  // many keys (spatial encoder: k * 49) x beam rows
+    if (smem2 > 227 * 1024) return static_cast<int>(cudaErrorInvalidValue);
+    cudaError_t e = cudaFuncSetAttribute(attn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem2));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured2 = smem2;
+  }
   dim3 grid(a.R / a.rows_per_feature, (a.F / 2 + 255) / 256);
   attn_apply_kernel<<<grid, 256, smem2, stream>>>(a, a.attn_ws);
   return last_err();

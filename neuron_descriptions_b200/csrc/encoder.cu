@@ -42,6 +42,19 @@ __device__ __forceinline__ void load_pixels4<float>(const float* p, float (&v)[4
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
 
+template <typename T>
+__device__ __forceinline__ void load_masks4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void load_masks4<uint8_t>(const uint8_t* p, float (&v)[4]) {
+  const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+template <>
+__device__ __forceinline__ void load_masks4<float>(const float* p, float (&v)[4]) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+
 // Normalise + repack NCHW images into the zero-padded NHWC4 bf16 layout the stem GEMM reads through its 5-D
 // overlapping-window tensor map: [n][232][232][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
 // One thread per 4 consecutive padded pixels (the x padding of 4 keeps every group fully inside or fully outside
@@ -50,7 +63,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) stem_pack_kernel(const T* __restrict__ images, int n_images,
                                                         __nv_bfloat16* __restrict__ p_hi,
                                                         __nv_bfloat16* __restrict__ p_lo, float3 mean, float3 stdv,
-                                                        int split) {
+                                                        int split, const T* __restrict__ masks) {
   constexpr int PH = kStemPadH, PW4 = kStemPadW / 4;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n_images) * PH * PW4;
@@ -69,6 +82,14 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const T* __restrict__ im
       load_pixels4<T>(img + c * kImg * kImg, v[c]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[c][j] = __fdiv_rn(__fsub_rn(v[c][j], m[c]), s[c]);
+    }
+    if (masks != nullptr) {  // SpatialConvEncoder: images * masks after normalisation (encoders.py:208-211)
+      float mk[4];
+      load_masks4<T>(masks + static_cast<long long>(n) * kImg * kImg + static_cast<long long>(ih) * kImg + iw0, mk);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[c][j] = __fmul_rn(v[c][j], mk[j]);
     }
   }
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
@@ -252,10 +273,33 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
   if (y_lo != nullptr) *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+__global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                     long long n2, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const uint32_t h = reinterpret_cast<const uint32_t*>(hi)[i];
+  float x0 = bf16_lo_to_f32(h), x1 = bf16_hi_to_f32(h);
+  if (lo != nullptr) {
+    const uint32_t l = reinterpret_cast<const uint32_t*>(lo)[i];
+    x0 += bf16_lo_to_f32(l);
+    x1 += bf16_hi_to_f32(l);
+  }
+  reinterpret_cast<float2*>(out)[i] = make_float2(x0, x1);
+}
+
 }  // namespace
 
+int launch_planes_to_f32(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out,
+                         cudaStream_t stream) {
+  const long long n2 = n / 2;
+  if (n2 == 0) return 0;
+  planes_to_f32_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, stream>>>(hi, lo, n2, out);
+  note_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
 int launch_stem_pack(const void* images, int dtype, int n_images, __nv_bfloat16* p_hi, __nv_bfloat16* p_lo,
-                     const float mean[3], const float stdv[3], int split, cudaStream_t stream) {
+                     const float mean[3], const float stdv[3], int split, cudaStream_t stream, const void* masks) {
   const long long total = static_cast<long long>(n_images) * kStemPadH * (kStemPadW / 4);
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
@@ -263,10 +307,10 @@ int launch_stem_pack(const void* images, int dtype, int n_images, __nv_bfloat16*
   const float3 s = make_float3(stdv[0], stdv[1], stdv[2]);
   if (dtype == 0) {
     stem_pack_kernel<uint8_t><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        static_cast<const uint8_t*>(images), n_images, p_hi, p_lo, m, s, split);
+        static_cast<const uint8_t*>(images), n_images, p_hi, p_lo, m, s, split, static_cast<const uint8_t*>(masks));
   } else {
     stem_pack_kernel<float><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        static_cast<const float*>(images), n_images, p_hi, p_lo, m, s, split);
+        static_cast<const float*>(images), n_images, p_hi, p_lo, m, s, split, static_cast<const float*>(masks));
   }
   note_launch();
   return static_cast<int>(cudaGetLastError());

@@ -89,9 +89,24 @@ struct Plan {
 };
 
 constexpr int kRes[4] = {56, 28, 14, 7};
-constexpr int kBlocks[4] = {3, 4, 23, 3};
 constexpr int kPlanes[4] = {64, 128, 256, 512};
 constexpr double kBnEps = 1e-5;
+constexpr int kSpatialKeys = 49;  // SpatialConvEncoder: 7x7 positions of layer4 (src/milan/encoders.py:235)
+
+// torchvision ResNet variants (Bottleneck v1.5 with the stride on the 3x3, or BasicBlock), indexed by
+// MILAN_ENCODER_RESNET* (include/milan_b200.h).
+struct EncoderArch {
+  const char* name;
+  bool bottleneck;
+  int blocks[4];
+};
+constexpr EncoderArch kArchs[] = {
+    {"resnet101", true, {3, 4, 23, 3}},
+    {"resnet50", true, {3, 4, 6, 3}},
+    {"resnet18", false, {2, 2, 2, 2}},
+    {"resnet34", false, {3, 4, 6, 3}},
+};
+constexpr int kNumArchs = sizeof(kArchs) / sizeof(kArchs[0]);
 
 }  // namespace
 
@@ -109,7 +124,12 @@ struct MilanEngine {
   float* bn1_alpha = nullptr;
   float* bn1_beta = nullptr;
   float mean[3] = {0, 0, 0}, stdv[3] = {1, 1, 1};
-  std::vector<ConvLayer> convs;  // 103 convs after the stem, execution order
+  EncoderArch arch = kArchs[0];
+  int expansion = 4;             // stage output channels = planes * expansion
+  bool spatial = false;          // SpatialConvEncoder: mask the image, emit the layer4 map
+  bool has_decoder = true;       // false: encoder-only engine (no decoder tensors were provided)
+  int enc_out_per_image = 0;     // floats milan_encode writes per image
+  std::vector<ConvLayer> convs;  // convs after the stem, execution order (103 for resnet101)
   // ---- encoder workspace (hi/lo planes)
   __nv_bfloat16 *stemA[2] = {}, *c1raw[2] = {}, *bufX[2] = {}, *bufY[2] = {}, *bufT1[2] = {}, *bufT2[2] = {},
                 *bufDS[2] = {};
@@ -301,19 +321,24 @@ int MilanEngine::finalize_encoder() {
   };
   int inplanes = 64;
   for (int li = 0; li < 4; ++li) {
-    for (int bi = 0; bi < kBlocks[li]; ++bi) {
+    for (int bi = 0; bi < arch.blocks[li]; ++bi) {
       const int planes = kPlanes[li];
       const int stride = (bi == 0 && li > 0) ? 2 : 1;
       char buf[64];
       snprintf(buf, sizeof buf, "layer%d.%d", li + 1, bi);
       const std::string b(buf);
-      if (add_conv(b + ".conv1", b + ".bn1", inplanes, planes, 1, 1)) return 1;
-      if (add_conv(b + ".conv2", b + ".bn2", planes, planes, 3, stride)) return 1;
-      if (add_conv(b + ".conv3", b + ".bn3", planes, planes * 4, 1, 1)) return 1;
-      if (bi == 0) {
-        if (add_conv(b + ".downsample.0", b + ".downsample.1", inplanes, planes * 4, 1, stride)) return 1;
+      if (arch.bottleneck) {
+        if (add_conv(b + ".conv1", b + ".bn1", inplanes, planes, 1, 1)) return 1;
+        if (add_conv(b + ".conv2", b + ".bn2", planes, planes, 3, stride)) return 1;
+        if (add_conv(b + ".conv3", b + ".bn3", planes, planes * 4, 1, 1)) return 1;
+      } else {
+        if (add_conv(b + ".conv1", b + ".bn1", inplanes, planes, 3, stride)) return 1;
+        if (add_conv(b + ".conv2", b + ".bn2", planes, planes, 3, 1)) return 1;
       }
-      inplanes = planes * 4;
+      if (stride != 1 || inplanes != planes * expansion) {
+        if (add_conv(b + ".downsample.0", b + ".downsample.1", inplanes, planes * expansion, 1, stride)) return 1;
+      }
+      inplanes = planes * expansion;
     }
   }
   return 0;
@@ -430,16 +455,19 @@ int MilanEngine::alloc_workspace() {
     const size_t n = cfg.max_images;
     if (dalloc2(stemA, n * kStemPadH * kStemPadW * 4)) return 1;
     if (dalloc2(c1raw, n * 12544 * 64)) return 1;
-    if (dalloc2(bufX, n * 3136 * 256)) return 1;
-    if (dalloc2(bufY, n * 3136 * 256)) return 1;
-    if (dalloc2(bufT1, n * 3136 * 128)) return 1;
-    if (dalloc2(bufT2, n * 3136 * 64)) return 1;
-    if (dalloc2(bufDS, n * 3136 * 256)) return 1;
+    // largest tensors: stage outputs at 56x56 (64 * expansion channels), bottleneck conv1 of layer2.0 (128 @ 56x56)
+    const size_t stage = 3136 * 64 * static_cast<size_t>(expansion);
+    if (dalloc2(bufX, n * stage)) return 1;
+    if (dalloc2(bufY, n * stage)) return 1;
+    if (dalloc2(bufT1, n * 3136 * (arch.bottleneck ? 128 : 64))) return 1;
+    if (arch.bottleneck && dalloc2(bufT2, n * 3136 * 64)) return 1;
+    if (dalloc2(bufDS, n * stage)) return 1;
     if (dalloc(&mask_wts, n * kMaskPyramidSize)) return 1;
-    if (dalloc(&feat_enc, static_cast<size_t>(std::max<int>(cfg.max_images, cfg.max_neurons * Kk)) * F)) return 1;
+    if (dalloc(&feat_enc, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
     if (dalloc(&d_img_stage, n * 3 * 224 * 224)) return 1;
     if (dalloc(&d_mask_stage, n * 224 * 224)) return 1;
   }
+  if (!has_decoder) return 0;
   Bmax = cfg.max_neurons;
   Rmax = cfg.max_neurons * cfg.max_beam;
   FRcap = static_cast<size_t>(Rmax) * Kk;  // feature rows: milan_step may bring one feature set per row
@@ -549,39 +577,47 @@ int MilanEngine::build_encoder_plans(int n, std::vector<Plan>** out) {
   __nv_bfloat16** y = bufY;
   size_t ci = 0;
   int res_in = 56;
+  auto mk = [&](const ConvLayer& L, int res, __nv_bfloat16** in, __nv_bfloat16** outb, __nv_bfloat16** res_b,
+                int relu) -> int {
+    Plan pl;
+    ConvDesc d{n, res, res, L.cin, L.cout, L.ksize, L.stride};
+    ConvIO io{};
+    io.in_hi = in[0]; io.in_lo = in[1];
+    io.w_hi = L.w.hi; io.w_lo = L.w.lo;
+    io.bias = L.bias;
+    if (res_b != nullptr) { io.res_hi = res_b[0]; io.res_lo = res_b[1]; }
+    io.out_hi = outb[0]; io.out_lo = outb[1];
+    io.relu = relu;
+    if (build_conv_params(&pl.p, d, io, sp, &pl.block_n)) return fail("plan %s: %s", L.name.c_str(), tmap_last_error());
+    plans.push_back(pl);
+    return 0;
+  };
   for (int li = 0; li < 4; ++li) {
-    for (int bi = 0; bi < kBlocks[li]; ++bi) {
-      const bool has_ds = (bi == 0);
-      const ConvLayer& c1 = convs[ci];
-      const ConvLayer& c2 = convs[ci + 1];
-      const ConvLayer& c3 = convs[ci + 2];
-      const int res_out = res_in / c2.stride;
-      auto mk = [&](const ConvLayer& L, int res, __nv_bfloat16** in, __nv_bfloat16** outb, __nv_bfloat16** res_b,
-                    int relu) -> int {
-        Plan pl;
-        ConvDesc d{n, res, res, L.cin, L.cout, L.ksize, L.stride};
-        ConvIO io{};
-        io.in_hi = in[0]; io.in_lo = in[1];
-        io.w_hi = L.w.hi; io.w_lo = L.w.lo;
-        io.bias = L.bias;
-        if (res_b != nullptr) { io.res_hi = res_b[0]; io.res_lo = res_b[1]; }
-        io.out_hi = outb[0]; io.out_lo = outb[1];
-        io.relu = relu;
-        if (build_conv_params(&pl.p, d, io, sp, &pl.block_n)) return fail("plan %s: %s", L.name.c_str(), tmap_last_error());
-        plans.push_back(pl);
-        return 0;
-      };
-      if (mk(c1, res_in, x, bufT1, nullptr, 1)) return 1;
-      if (mk(c2, res_in, bufT1, bufT2, nullptr, 1)) return 1;
+    for (int bi = 0; bi < arch.blocks[li]; ++bi) {
+      const int main_convs = arch.bottleneck ? 3 : 2;
+      const ConvLayer& strided = convs[ci + (arch.bottleneck ? 1 : 0)];
+      const int res_out = res_in / strided.stride;
+      const bool has_ds = ci + main_convs < convs.size() && convs[ci + main_convs].name.find("downsample") != std::string::npos;
       __nv_bfloat16** identity = x;
-      if (has_ds) {
-        const ConvLayer& ds = convs[ci + 3];
-        if (mk(ds, res_in, x, bufDS, nullptr, 0)) return 1;
-        identity = bufDS;
+      if (arch.bottleneck) {
+        if (mk(convs[ci], res_in, x, bufT1, nullptr, 1)) return 1;
+        if (mk(convs[ci + 1], res_in, bufT1, bufT2, nullptr, 1)) return 1;
+        if (has_ds) {
+          if (mk(convs[ci + 3], res_in, x, bufDS, nullptr, 0)) return 1;
+          identity = bufDS;
+        }
+        if (mk(convs[ci + 2], res_out, bufT2, y, identity, 1)) return 1;
+      } else {
+        // BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity)
+        if (mk(convs[ci], res_in, x, bufT1, nullptr, 1)) return 1;
+        if (has_ds) {
+          if (mk(convs[ci + 2], res_in, x, bufDS, nullptr, 0)) return 1;
+          identity = bufDS;
+        }
+        if (mk(convs[ci + 1], res_out, bufT1, y, identity, 1)) return 1;
       }
-      if (mk(c3, res_out, bufT2, y, identity, 1)) return 1;
       std::swap(x, y);
-      ci += has_ds ? 4 : 3;
+      ci += main_convs + (has_ds ? 1 : 0);
       res_in = res_out;
     }
   }
@@ -600,36 +636,47 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   const int F = cfg.feature_size;
   const int sp = split ? 1 : 0;
   if (profiling) conv_events_used = 0;
-  RC(launch_stem_pack(d_images, dtype, n, stemA[0], stemA[1], mean, stdv, sp, st));
-  if (d_masks == nullptr) {
-    if (ones_masks == nullptr) {
-      uint8_t* p = nullptr;
-      if (dalloc(&p, static_cast<size_t>(cfg.max_images) * 224 * 224)) return 1;
-      CU(cudaMemset(p, 1, static_cast<size_t>(cfg.max_images) * 224 * 224));
-      ones_masks = p;
+  if (reinterpret_cast<uintptr_t>(d_masks) % 16 != 0 && spatial)
+    return fail("milan_encode: d_masks must be 16-byte aligned for a spatial encoder");
+  RC(launch_stem_pack(d_images, dtype, n, stemA[0], stemA[1], mean, stdv, sp, st, spatial ? d_masks : nullptr));
+  if (!spatial) {
+    if (d_masks == nullptr) {
+      if (ones_masks == nullptr) {
+        uint8_t* p = nullptr;
+        if (dalloc(&p, static_cast<size_t>(cfg.max_images) * 224 * 224)) return 1;
+        CU(cudaMemset(p, 1, static_cast<size_t>(cfg.max_images) * 224 * 224));
+        ones_masks = p;
+      }
+      RC(launch_mask_pyramid(ones_masks, MILAN_DTYPE_U8, n, mask_wts, st));
+    } else {
+      RC(launch_mask_pyramid(d_masks, dtype, n, mask_wts, st));
     }
-    RC(launch_mask_pyramid(ones_masks, MILAN_DTYPE_U8, n, mask_wts, st));
-  } else {
-    RC(launch_mask_pyramid(d_masks, dtype, n, mask_wts, st));
   }
   size_t pi = 0;
   if (run_conv((*plans)[pi++], st)) return 1;  // stem
-  RC(launch_masked_pool(c1raw[0], c1raw[1], mask_wts + kMaskLevelOffset[0], kMaskPyramidSize, n, 12544, 64, d_out, F, st));
+  if (!spatial)
+    RC(launch_masked_pool(c1raw[0], c1raw[1], mask_wts + kMaskLevelOffset[0], kMaskPyramidSize, n, 12544, 64, d_out, F, st));
   RC(launch_bn_relu_maxpool(c1raw[0], c1raw[1], bn1_alpha, bn1_beta, n, bufX[0], bufX[1], st));
   __nv_bfloat16** x = bufX;
   __nv_bfloat16** y = bufY;
   int feat_off = 64;
   for (int li = 0; li < 4; ++li) {
-    for (int bi = 0; bi < kBlocks[li]; ++bi) {
-      const int nconv = bi == 0 ? 4 : 3;
+    for (int bi = 0; bi < arch.blocks[li]; ++bi) {
+      const bool has_ds = (bi == 0) && (li > 0 || expansion != 1);
+      const int nconv = (arch.bottleneck ? 3 : 2) + (has_ds ? 1 : 0);
       for (int j = 0; j < nconv; ++j)
         if (run_conv((*plans)[pi++], st)) return 1;
       std::swap(x, y);
     }
-    const int C = kPlanes[li] * 4, P = kRes[li] * kRes[li];
-    RC(launch_masked_pool(x[0], x[1], mask_wts + kMaskLevelOffset[li + 1], kMaskPyramidSize, n, P, C, d_out + feat_off, F, st));
-    feat_off += C;
+    const int C = kPlanes[li] * expansion, P = kRes[li] * kRes[li];
+    if (!spatial) {
+      RC(launch_masked_pool(x[0], x[1], mask_wts + kMaskLevelOffset[li + 1], kMaskPyramidSize, n, P, C, d_out + feat_off, F, st));
+      feat_off += C;
+    } else if (li == 3) {
+      RC(launch_planes_to_f32(x[0], x[1], static_cast<long long>(n) * P * C, d_out, st));
+    }
   }
+  if (pi != plans->size()) return fail("internal: encoder plan count mismatch (%zu of %zu)", pi, plans->size());
   return 0;
 }
 
@@ -919,11 +966,28 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail("device %s is sm_%d%d; this engine is built for sm_100a only", prop.name, prop.major, prop.minor);
   if (config->max_beam > kMaxBeam) return fail("max_beam %d exceeds %d", config->max_beam, kMaxBeam);
+  if (config->encoder_arch < 0 || config->encoder_arch >= kNumArchs)
+    return fail("encoder not supported: encoder_arch %d", config->encoder_arch);
+  if (config->encoder_kind != MILAN_ENCODER_PYRAMID && config->encoder_kind != MILAN_ENCODER_SPATIAL)
+    return fail("encoder not supported: encoder_kind %d", config->encoder_kind);
+  const EncoderArch& arch = kArchs[config->encoder_arch];
+  const int expansion = arch.bottleneck ? 4 : 1;
+  const bool spatial = config->encoder_kind == MILAN_ENCODER_SPATIAL;
+  if (config->has_encoder) {
+    const int want = spatial ? 512 * expansion : 64 + (64 + 128 + 256 + 512) * expansion;
+    if (config->feature_size != want)
+      return fail("feature_size %d does not match the %s %s encoder (%d)", config->feature_size, arch.name,
+                  spatial ? "spatial" : "pyramid", want);
+  }
   auto* eng = new MilanEngine();
   eng->cfg = *config;
   eng->device = device;
   eng->num_sms = prop.multiProcessorCount;
   eng->split = config->precision == MILAN_PRECISION_SPLIT;
+  eng->arch = arch;
+  eng->expansion = expansion;
+  eng->spatial = spatial;
+  eng->enc_out_per_image = (spatial ? kSpatialKeys : 1) * config->feature_size;
   *out = eng;
   return 0;
 }
@@ -958,7 +1022,9 @@ int milan_engine_finalize(MilanEngine* engine) {
   if (engine->finalized) return 0;
   CU(cudaSetDevice(engine->device));
   if (engine->cfg.has_encoder && engine->finalize_encoder()) return 1;
-  if (engine->finalize_decoder()) return 1;
+  // An engine given encoder tensors only (standalone Encoder use, src/milan/encoders.py) has no decoder half.
+  engine->has_decoder = !engine->cfg.has_encoder || engine->get("lstm.weight_ih") != nullptr;
+  if (engine->has_decoder && engine->finalize_decoder()) return 1;
   if (engine->alloc_workspace()) return 1;
   engine->pending.clear();
   engine->finalized = true;
@@ -971,6 +1037,8 @@ int milan_engine_finalize(MilanEngine* engine) {
   if ((e) == nullptr) return fail("null engine");                  \
   if (!(e)->finalized) return fail("engine not finalized");        \
   CU(cudaSetDevice((e)->device));
+#define CHECK_DECODER(e) \
+  if (!(e)->has_decoder) return fail("engine was created without decoder weights (encoder-only)");
 
 int milan_encode(MilanEngine* engine, const void* d_images, const void* d_masks, int32_t n_images, int32_t dtype,
                  float* d_features_out, void* stream) {
@@ -983,7 +1051,7 @@ int milan_encode(MilanEngine* engine, const void* d_images, const void* d_masks,
     const int n = std::min(n_images - done, engine->cfg.max_images);
     const uint8_t* img = static_cast<const uint8_t*>(d_images) + done * img_stride;
     const uint8_t* msk = d_masks ? static_cast<const uint8_t*>(d_masks) + done * msk_stride : nullptr;
-    if (engine->encode(img, msk, n, dtype, d_features_out + static_cast<size_t>(done) * engine->cfg.feature_size, st))
+    if (engine->encode(img, msk, n, dtype, d_features_out + static_cast<size_t>(done) * engine->enc_out_per_image, st))
       return 1;
     if (engine->collect_conv_events(st)) return 1;
     done += n;
@@ -994,6 +1062,7 @@ int milan_encode(MilanEngine* engine, const void* d_images, const void* d_masks,
 int milan_init_state(MilanEngine* engine, const float* d_features, int32_t B, int32_t n_keys, float* d_h,
                      float* d_c, void* stream) {
   CHECK_READY(engine);
+  CHECK_DECODER(engine);
   if (B > engine->Rmax || static_cast<size_t>(B) * n_keys > engine->FRcap) return fail("init_state: B=%d exceeds capacity", B);
   return init_state_impl(engine, d_features, B, n_keys, d_h, d_c, static_cast<cudaStream_t>(stream));
 }
@@ -1002,6 +1071,7 @@ int milan_step(MilanEngine* engine, const float* d_features, int32_t n_keys, con
                float* d_c, float* d_h_lm, float* d_c_lm, int32_t R, int32_t rows_per_feature, float temperature,
                float* d_predictions_out, float* d_attentions_out, void* stream) {
   CHECK_READY(engine);
+  CHECK_DECODER(engine);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MilanEngine* e = engine;
   const int V = e->cfg.vocab_size, H = e->cfg.hidden_size, E = e->cfg.embedding_size, F = e->cfg.feature_size;
@@ -1044,6 +1114,7 @@ int milan_decode_greedy(MilanEngine* engine, const float* d_features, int32_t B,
                         int32_t mi, float temperature, const int64_t* d_forced, int64_t* d_tokens_out,
                         float* d_scores_out, float* d_predictions_out, float* d_attentions_out, void* stream) {
   CHECK_READY(engine);
+  CHECK_DECODER(engine);
   return engine->decode_greedy(d_features, B, n_keys, length, mi, temperature,
                                reinterpret_cast<const long long*>(d_forced),
                                reinterpret_cast<long long*>(d_tokens_out), d_scores_out, d_predictions_out,
@@ -1055,6 +1126,7 @@ int milan_decode_beam(MilanEngine* engine, const float* d_features, int32_t B, i
                       int64_t* d_beam_tokens_out, float* d_beam_scores_out, int32_t* d_group_steps_out,
                       int64_t* d_tokens_out, float* d_scores_out, float* d_lm_scores_out, void* stream) {
   CHECK_READY(engine);
+  CHECK_DECODER(engine);
   return engine->decode_beam(d_features, B, n_keys, length, beam, group_size, rerank, mi, temperature,
                              reinterpret_cast<long long*>(d_beam_tokens_out), d_beam_scores_out, d_group_steps_out,
                              reinterpret_cast<long long*>(d_tokens_out), d_scores_out, d_lm_scores_out,
@@ -1063,6 +1135,7 @@ int milan_decode_beam(MilanEngine* engine, const float* d_features, int32_t B, i
 
 int milan_lm_score(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int32_t T1, float* d_out, void* stream) {
   CHECK_READY(engine);
+  CHECK_DECODER(engine);
   MilanEngine* e = engine;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!e->cfg.has_lm) return fail("engine has no LM");
@@ -1085,10 +1158,12 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
                         float temperature, int64_t* h_tokens_out, float* h_scores_out, int32_t* h_steps_out,
                         void* stream) {
   CHECK_READY(engine);
+  CHECK_DECODER(engine);
   MilanEngine* e = engine;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!e->cfg.has_encoder) return fail("engine was created without an encoder");
-  if (k > e->cfg.max_keys) return fail("k=%d exceeds max_keys %d", k, e->cfg.max_keys);
+  const int n_keys = k * (e->spatial ? kSpatialKeys : 1);  // Decoder.encode: view(batch, -1, feature_size)
+  if (n_keys > e->cfg.max_keys) return fail("k=%d (%d keys) exceeds max_keys %d", k, n_keys, e->cfg.max_keys);
   if (group_size <= 0) group_size = 16;
   const int F = e->cfg.feature_size;
   // neurons per chunk: bounded by encoder image capacity and decoder capacity; whole reference groups only
@@ -1111,10 +1186,10 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
     if (e->profiling) CU(cudaEventRecord(ev[1], st));
     const int groups = (nb + group_size - 1) / group_size;
     if (strategy == 0) {
-      if (e->decode_greedy(e->feat_enc, nb, k, length, mi, temperature, nullptr, d_tok, e->out_scores, nullptr, nullptr, st))
+      if (e->decode_greedy(e->feat_enc, nb, n_keys, length, mi, temperature, nullptr, d_tok, e->out_scores, nullptr, nullptr, st))
         return 1;
     } else {
-      if (e->decode_beam(e->feat_enc, nb, k, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0, temperature,
+      if (e->decode_beam(e->feat_enc, nb, n_keys, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0, temperature,
                          nullptr, nullptr,
                          nullptr, d_tok, e->out_scores, nullptr, st))
         return 1;

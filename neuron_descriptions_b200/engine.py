@@ -35,7 +35,11 @@ class Engine:
                  max_neurons: int = 32,
                  max_beam: int = 50,
                  max_keys: int = 15,
-                 max_length: int = 15):
+                 max_length: int = 15,
+                 encoder_arch: str = 'resnet101',
+                 encoder_kind: str = 'pyramid',
+                 max_images: Optional[int] = None,
+                 decoder: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError('milan_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
         self.lib = _lib.load()
@@ -46,14 +50,20 @@ class Engine:
         self.device = torch.device('cuda', index)
         has_encoder = any(key.startswith('encoder.encoder.model.') for key in state_dict)
         has_lm = any(key.startswith('lm.') for key in state_dict)
+        if encoder_arch not in _lib.ENCODER_ARCHS or encoder_kind not in _lib.ENCODER_KINDS:
+            raise ValueError(f'encoder not supported: {encoder_kind}/{encoder_arch}')
+        self.keys_per_image = 49 if encoder_kind == 'spatial' else 1
+        if max_images is None:
+            max_images = max(1, max_neurons * max_keys // self.keys_per_image)
         cfg = _lib.MilanConfig(
             vocab_size=vocab_size, embedding_size=embedding_size, hidden_size=hidden_size,
             attention_size=attention_size or min(hidden_size, feature_size), feature_size=feature_size,
             start_index=vocab_size - 4, stop_index=vocab_size - 3, has_encoder=int(has_encoder), has_lm=int(has_lm),
             lm_embedding_size=lm_embedding_size, lm_hidden_size=lm_hidden_size,
             precision={'split': _lib.PRECISION_SPLIT, 'fast': _lib.PRECISION_FAST}[precision],
-            max_images=max_neurons * max_keys, max_neurons=max_neurons, max_beam=max_beam, max_keys=max_keys,
-            max_length=max_length)
+            max_images=max_images, max_neurons=max_neurons, max_beam=max_beam, max_keys=max_keys,
+            max_length=max_length, encoder_arch=_lib.ENCODER_ARCHS[encoder_arch],
+            encoder_kind=_lib.ENCODER_KINDS[encoder_kind])
         self.cfg = cfg
         self.precision = precision
         self.has_encoder, self.has_lm = has_encoder, has_lm
@@ -63,6 +73,8 @@ class Engine:
         for name, tensor in state_dict.items():
             if not torch.is_floating_point(tensor):
                 continue  # num_batches_tracked
+            if not decoder and not name.startswith('encoder.'):
+                continue  # encoder-only engine
             host = tensor.detach().to('cpu', torch.float32).contiguous()
             shape = (ctypes.c_int64 * max(host.dim(), 1))(*host.shape)
             _lib.check(self.lib.milan_engine_set_tensor(handle, name.encode(), ctypes.c_void_p(host.data_ptr()), shape,
@@ -89,7 +101,8 @@ class Engine:
 
     # ------------------------------------------------------------------ C ABI wrappers
     def encode(self, images: torch.Tensor, masks: Optional[torch.Tensor]) -> torch.Tensor:
-        """images (n,3,224,224) uint8|float, masks (n,1,224,224) same dtype family -> (n, F)."""
+        """images (n,3,224,224) uint8|float, masks (n,1,224,224) same dtype family -> (n, F) for a pyramid
+        encoder, (n, 49, F) for a spatial one."""
         if images.shape[1:] != (3, 224, 224):
             raise ValueError(f'milan_b200 encoder expects (n,3,224,224) images, got {tuple(images.shape)}')
         if images.dtype == torch.uint8:
@@ -103,7 +116,10 @@ class Engine:
             if masks is not None:
                 masks = self._f32(masks)
         n = images.shape[0]
-        out = self._new(n, self.cfg.feature_size)
+        if self.keys_per_image > 1:
+            out = self._new(n, self.keys_per_image, self.cfg.feature_size)
+        else:
+            out = self._new(n, self.cfg.feature_size)
         _lib.check(self.lib.milan_encode(self.handle, _ptr(images), _ptr(masks), n, dtype, _ptr(out),
                                          _stream(self.device)))
         return out

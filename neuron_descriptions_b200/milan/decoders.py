@@ -108,7 +108,9 @@ class Decoder:
         self.max_neurons = max_neurons
         self._state_dict: Dict[str, torch.Tensor] = {}
         self._engine: Optional[Engine] = None
-        self._capacity = {'max_beam': max(50, beam_size), 'max_length': max(15, length), 'max_keys': 15}
+        keys_per_image = 49 if getattr(encoder, 'KIND', 'pyramid') == 'spatial' else 1
+        self._capacity = {'max_beam': max(50, beam_size), 'max_length': max(15, length),
+                          'max_keys': 15 * keys_per_image}
 
     # ------------------------------------------------------------------ module-ish plumbing
     @property
@@ -170,7 +172,8 @@ class Decoder:
                               attention_size=self.attention_hidden_size, feature_size=self.feature_size,
                               lm_embedding_size=self.lm.embedding_size if self.lm else 128,
                               lm_hidden_size=self.lm.hidden_size if self.lm else 512, precision=self.precision,
-                              max_neurons=self.max_neurons, **self._capacity)
+                              max_neurons=self.max_neurons, encoder_arch=getattr(self.encoder, 'config', 'resnet101'),
+                              encoder_kind=getattr(self.encoder, 'KIND', 'pyramid'), **self._capacity)
         if hasattr(self.encoder, 'bind'):
             self.encoder.bind(self._engine)
         if self.lm is not None:
@@ -325,6 +328,41 @@ class Decoder:
         predictions, attentions, h, c, h_lm, c_lm = self.engine.step(features, tokens, h, c, h_lm, c_lm, temperature)
         return DecoderStep(predictions=predictions, attentions=attentions,
                            state=DecoderState(h=h, c=c, h_lm=h_lm, c_lm=c_lm))
+
+    # ------------------------------------------------------------------ score
+    def score(self, captions: StrSequence, images_or_features: torch.Tensor, masks: Optional[torch.Tensor] = None,
+              device=None, **kwargs: Any) -> torch.Tensor:
+        """`Decoder.score`, `src/milan/decoders.py:636-711`: force-decode the captions and total their
+        log-probabilities (`mi=False`) or mutual informations (`mi=True`). Needs an indexer with a tokenizer."""
+        for forbidden in ('strategy', 'length'):
+            if forbidden in kwargs:
+                raise ValueError(f'option disallowed: {forbidden}')
+        if masks is not None and len(masks) != len(images_or_features):
+            raise ValueError('images_or_features and masks must have the same batch size; '
+                             f'got {len(images_or_features)} and {len(masks)}')
+        if len(images_or_features) == 1:
+            images_or_features = images_or_features.expand(len(captions), *images_or_features.shape[1:])
+            if masks is not None:
+                masks = masks.expand(len(captions), *masks.shape[1:])
+        elif len(images_or_features) != len(captions):
+            raise ValueError('images_or_features must have batch size 1 or '
+                             f'{len(captions)}; got {len(images_or_features)}')
+        if device is not None:
+            self.to(device)
+        targets = torch.tensor(self.indexer(captions))
+        targets = targets[:, 1:]
+        _, length = targets.shape
+        totals = []
+        indexed = self.indexer(captions, start=False, stop=True, pad=False, unk=True)
+        chunk = self.engine.cfg.max_neurons
+        for lo in range(0, len(captions), chunk):
+            hi = min(lo + chunk, len(captions))
+            outputs = self(images_or_features[lo:hi], masks=None if masks is None else masks[lo:hi],
+                           strategy=targets[lo:hi], length=length, **kwargs)
+            predictions = outputs.predictions.cpu()
+            for scores, indices in zip(predictions, indexed[lo:hi]):
+                totals.append(scores[torch.arange(len(indices)), torch.tensor(indices, dtype=torch.long)].sum().item())
+        return torch.tensor(totals, device=self.engine.device if device is not None else None)
 
     # ------------------------------------------------------------------ predict
     def predict(self,

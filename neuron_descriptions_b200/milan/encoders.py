@@ -1,6 +1,8 @@
 """Facade of `src/milan/encoders.py`: the same constructor / `forward` / `map` surface, computed by the CUDA
-engine. Only `PyramidConvEncoder('resnet101')` — the encoder of every shipped MILAN checkpoint
-(`scripts/train_milan.py:29-32,88`) — is implemented natively."""
+engine. `PyramidConvEncoder('resnet101')` is the encoder of every shipped MILAN checkpoint
+(`scripts/train_milan.py:29-32,88`); the other ResNet configs of the reference (`resnet18`, `resnet50` pyramids,
+`SpatialConvEncoder('resnet18')`; `src/milan/encoders.py:214-216,326-351`) run on the same kernels with a
+different layer table. The `alexnet` pyramid (11x11 / 5x5 convolutions) is not implemented."""
 from typing import Any, Mapping, Optional, Tuple
 
 import torch
@@ -41,27 +43,59 @@ class Encoder:
         return data.TensorDataset(torch.cat(features))
 
 
-class PyramidConvEncoder(Encoder):
-    """`src/milan/encoders.py:243-351`, config 'resnet101' only. Bound to an engine by the owning `Decoder`."""
+class _EngineEncoder(Encoder):
+    """Common part of the two encoder kinds: config validation, engine binding, standalone use.
 
-    def __init__(self, config: str = 'resnet50', **kwargs: Any):
-        configs = PyramidConvEncoder.configs()
+    Inside a `Decoder` the encoder shares the decoder's engine (`bind`). Used on its own (as the reference's
+    encoder tests do) it builds a private encoder-only engine from `load_state_dict` weights on `.to('cuda')`.
+    """
+
+    KIND = KIND_PYRAMID
+    NATIVE = ()
+
+    def __init__(self, config: str, **kwargs: Any):
+        configs = type(self).configs()
         if config not in configs:
             raise ValueError(f'encoder not supported: {config}')
-        if config != 'resnet101':
-            raise NotImplementedError(f'milan_b200 implements the resnet101 pyramid encoder natively; got {config!r}')
+        if config not in self.NATIVE:
+            raise NotImplementedError(f'milan_b200 implements {self.NATIVE} natively for {type(self).__name__}; '
+                                      f'got {config!r}')
         self.config = config
         self.kwargs = dict(kwargs)
         self.kwargs.setdefault('pretrained', True)  # kept for checkpoint round-trips; nothing is downloaded
-        _, self.layers, feature_size = configs[config]
-        self.feature_shape = (feature_size,)
         self._engine = None
+        self._own_engine = None
+        self._state_dict = None
+        self.max_images = 64
 
-    def bind(self, engine) -> 'PyramidConvEncoder':
+    def bind(self, engine) -> 'Encoder':
         self._engine = engine
         return self
 
+    def load_state_dict(self, state_dict: Mapping[str, torch.Tensor], strict: bool = False):
+        """Weights with the reference's key names (`mean`, `std`, `encoder.model.*`: `nn.Module.state_dict()` of
+        the reference encoder), for standalone use."""
+        self._state_dict = {'encoder.' + key: value.detach().cpu() for key, value in state_dict.items()}
+        if self._own_engine is not None:
+            self._own_engine.close()
+            self._own_engine = None
+        return self
+
     def to(self, device):
+        if device is None or self._state_dict is None:
+            return self
+        device = torch.device(device)
+        if device.type != 'cuda':
+            return self
+        if self._own_engine is None or self._own_engine.device != torch.device('cuda', device.index or 0):
+            from neuron_descriptions_b200.engine import Engine
+            if self._own_engine is not None:
+                self._own_engine.close()
+            # encoder-only engine: the decoder dimensions are placeholders (no decoder weights are loaded)
+            self._own_engine = Engine(self._state_dict, vocab_size=68, device=device,
+                                      feature_size=self.feature_shape[-1], encoder_arch=self.config,
+                                      encoder_kind=self.KIND, max_neurons=1, max_beam=1, max_keys=1,
+                                      max_length=1, max_images=self.max_images, decoder=False)
         return self
 
     def eval(self):
@@ -69,15 +103,28 @@ class PyramidConvEncoder(Encoder):
 
     def forward(self, images: torch.Tensor, masks: Optional[torch.Tensor] = None, normalize: bool = True,
                 **_: Any) -> torch.Tensor:
-        if self._engine is None:
-            raise RuntimeError('encoder is not bound to a CUDA engine: call Decoder.to("cuda") first '
-                               '(milan_b200 has no CPU path)')
+        engine = self._engine or self._own_engine
+        if engine is None:
+            raise RuntimeError('encoder is not bound to a CUDA engine: call Decoder.to("cuda") (or, standalone, '
+                               'load_state_dict(...).to("cuda")) first; milan_b200 has no CPU path')
         if not normalize:
             raise NotImplementedError('normalize=False is not supported by the fused stem')
-        return self._engine.encode(images, masks)
+        return engine.encode(images, masks)
 
     def properties(self) -> Mapping[str, Any]:
         return {'config': self.config, **self.kwargs}
+
+
+class PyramidConvEncoder(_EngineEncoder):
+    """`src/milan/encoders.py:243-351`: masked spatial pooling of conv1 + layer1..4 -> one vector per image."""
+
+    KIND = KIND_PYRAMID
+    NATIVE = ('resnet18', 'resnet50', 'resnet101')
+
+    def __init__(self, config: str = 'resnet50', **kwargs: Any):
+        super().__init__(config, **kwargs)
+        _, self.layers, feature_size = self.configs()[config]
+        self.feature_shape = (feature_size,)
 
     @staticmethod
     def configs():
@@ -91,11 +138,28 @@ class PyramidConvEncoder(Encoder):
         }
 
 
-class SpatialConvEncoder(Encoder):
-    """`src/milan/encoders.py:159-236`: not used by any shipped checkpoint; not implemented natively."""
+class SpatialConvEncoder(_EngineEncoder):
+    """`src/milan/encoders.py:159-236`: images * masks -> resnet18 layer4 -> (n, 49, 512)."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError('SpatialConvEncoder is outside the describe-neurons hot path (SURVEY.md #2)')
+    KIND = KIND_SPATIAL
+    NATIVE = ('resnet18',)
+
+    def __init__(self, config: str = 'resnet18', **kwargs: Any):
+        super().__init__(config, **kwargs)
+        _, layers, n_features, feature_size = self.configs()[config]
+        self.layer, = layers
+        self.feature_shape = (n_features, feature_size)
+
+    def map(self, *args: Any, **kwargs: Any):
+        """`SpatialConvEncoder.map` (`src/milan/encoders.py:218-226`): defaults for single-image datasets."""
+        kwargs.setdefault('mask', False)
+        kwargs.setdefault('image_index', 0)
+        return super().map(*args, **kwargs)
+
+    @staticmethod
+    def configs():
+        """`src/milan/encoders.py:232-236`."""
+        return {'resnet18': (None, ('layer4',), 49, 512)}
 
 
 def parse(key: str):

@@ -1,9 +1,14 @@
 """Host-side vocabulary / detokenisation mirror of `src/utils/lang.py` (only what decoding needs).
 
-`Indexer.reconstruct` / `unindex` follow `src/utils/lang.py:573-612,678-730`; special ids follow `:242-260`.
-Tokenisation (`Indexer.__call__`, needs spaCy) is out of scope for the describe-neurons path:
-an `Indexer` built with `tokenize=None` raises if asked to index text.
+`Indexer.reconstruct` / `unindex` follow `src/utils/lang.py:573-612,678-730`; special ids follow `:242-260`;
+`Indexer.index` / `__call__` follow `:393-515` (needed by `Decoder.score`). The reference tokenises with spaCy
+(`lang.Tokenizer`, `:14-71`), which is not available offline and whose pipeline bytes inside real checkpoints
+cannot be rebuilt without it: `tokenize` is therefore any callable `Sequence[str] -> Sequence[Sequence[str]]`;
+`BasicTokenizer` is a dependency-free stand-in (lower-cased word split, punctuation dropped, NO lemmatisation
+and NO stop-word removal -- it is an approximation of the spaCy pipeline, not a replacement). An `Indexer`
+built with `tokenize=None` (every checkpoint loaded here) raises if asked to index raw text.
 """
+import re
 import collections
 import dataclasses
 import functools
@@ -114,10 +119,50 @@ class Indexer:
             return 0 <= token < len(self)
         return token in self.unique
 
-    def __call__(self, *args, **kwargs):
-        raise NotImplementedError(
-            'text -> ids indexing needs the spaCy tokenizer of the reference (src/utils/lang.py:460-515); '
-            'it is outside the describe-neurons hot path this engine covers')
+    def __call__(self, texts, **kwargs):
+        """`Indexer.__call__`, `src/utils/lang.py:379-391`: tokenize then `index`."""
+        if self.tokenize is None:
+            raise NotImplementedError(
+                'this Indexer has no tokenizer (checkpoints are loaded without the reference\'s spaCy pipeline, '
+                'src/utils/lang.py:14-71); pass tokenize=<callable> (e.g. lang.BasicTokenizer()) or call '
+                '.index() with pre-tokenized text')
+        tokenized = self.tokenize([texts] if isinstance(texts, str) else texts)
+        indexed = self.index(tokenized, **kwargs)
+        return indexed[0] if isinstance(texts, str) else indexed
+
+    def index(self, tokenized, start: Optional[bool] = None, stop: Optional[bool] = None,
+              pad: Optional[bool] = None, unk: Optional[bool] = None, length: Optional[int] = None):
+        """`Indexer.index`, `src/utils/lang.py:460-515`: tokens -> ids with start/stop/pad/unk handling."""
+        if not tokenized:
+            return ()
+        singleton = isinstance(tokenized[0], str)
+        start = self.start if start is None else start
+        stop = self.stop if stop is None else stop
+        pad = self.pad if pad is None else pad
+        unk = self.unk if unk is None else unk
+        length = length or self.length or max(len(toks) for toks in tokenized)
+        for special in (start, stop):
+            if special:
+                length += 1
+        indexed = []
+        for tokens in [tokenized] if singleton else tokenized:
+            indices = []
+            if start:
+                indices.append(self.start_index)
+            if unk:
+                indices += [self.vocab.ids.get(tok, self.unk_index) for tok in tokens]
+            else:
+                indices += [self.vocab[tok] for tok in tokens if tok in self.vocab]
+            if stop:
+                if len(indices) >= length:
+                    indices = indices[:length - 1]
+                indices.append(self.stop_index)
+            if len(indices) < length and pad:
+                indices += [self.pad_index] * (length - len(indices))
+            elif len(indices) > length:
+                indices = indices[:length]
+            indexed.append(tuple(indices))
+        return indexed[0] if singleton else tuple(indexed)
 
     def unindex(self, indexed, specials: bool = True, start: bool = True, stop: bool = True, pad: bool = True,
                 unk: bool = True):
@@ -178,6 +223,24 @@ class Indexer:
     def properties(self):
         return {'vocab': self.vocab, 'tokenize': self.tokenize, 'start': self.start, 'stop': self.stop,
                 'pad': self.pad, 'unk': self.unk, 'length': self.length}
+
+
+class BasicTokenizer:
+    """Dependency-free stand-in for `lang.Tokenizer` (`src/utils/lang.py:14-71`): lower-cased word / number
+    tokens, punctuation dropped. No lemmatisation or stop-word list (those need spaCy's `en_core_web_sm`)."""
+
+    _WORD = re.compile(r"[A-Za-z0-9]+(?:'[a-z]+)?")
+
+    def __init__(self, lowercase: bool = True):
+        self.lowercase = lowercase
+
+    def __call__(self, texts):
+        singleton = isinstance(texts, str)
+        out = []
+        for text in [texts] if singleton else texts:
+            tokens = self._WORD.findall(text)
+            out.append(tuple(tok.lower() if self.lowercase else tok for tok in tokens))
+        return out[0] if singleton else tuple(out)
 
 
 def indexer_from_payload(payload: Mapping[str, Any]) -> Indexer:

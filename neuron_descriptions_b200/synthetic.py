@@ -16,6 +16,9 @@ import torch
 
 RESNET101_BLOCKS = (3, 4, 23, 3)
 RESNET101_PLANES = (64, 128, 256, 512)
+# torchvision ResNet variants: name -> (bottleneck?, blocks per stage)
+RESNET_ARCHS = {'resnet101': (True, (3, 4, 23, 3)), 'resnet50': (True, (3, 4, 6, 3)),
+                'resnet18': (False, (2, 2, 2, 2)), 'resnet34': (False, (3, 4, 6, 3))}
 FEATURE_SIZE = 64 + 256 + 512 + 1024 + 2048  # 3904, src/milan/encoders.py:346-350
 IMAGENET_MEAN = (0.485, 0.456, 0.406)  # src/deps/netdissect/renormalize.py:87
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -42,28 +45,49 @@ def _bn(gen, sd, prefix, c, gamma_lo, gamma_hi):
     sd[prefix + '.num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
 
 
-def synthetic_resnet101_state(seed: int = 0) -> Dict[str, torch.Tensor]:
-    """torchvision-resnet101-shaped weights with non-trivial BN statistics (so BN folding is exercised)."""
+def synthetic_resnet_state(arch: str = 'resnet101', seed: int = 0) -> Dict[str, torch.Tensor]:
+    """torchvision-ResNet-shaped weights with non-trivial BN statistics (so BN folding is exercised)."""
+    bottleneck, stage_blocks = RESNET_ARCHS[arch]
+    expansion = 4 if bottleneck else 1
     gen = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     sd['conv1.weight'] = _conv(gen, 64, 3, 7)
     _bn(gen, sd, 'bn1', 64, 0.5, 1.0)
     inplanes = 64
-    for li, (blocks, planes) in enumerate(zip(RESNET101_BLOCKS, RESNET101_PLANES), start=1):
+    for li, (blocks, planes) in enumerate(zip(stage_blocks, RESNET101_PLANES), start=1):
         for bi in range(blocks):
             pre = f'layer{li}.{bi}'
-            sd[pre + '.conv1.weight'] = _conv(gen, planes, inplanes, 1)
-            _bn(gen, sd, pre + '.bn1', planes, 0.5, 1.0)
-            sd[pre + '.conv2.weight'] = _conv(gen, planes, planes, 3)
-            _bn(gen, sd, pre + '.bn2', planes, 0.5, 1.0)
-            sd[pre + '.conv3.weight'] = _conv(gen, planes * 4, planes, 1)
-            _bn(gen, sd, pre + '.bn3', planes * 4, 0.1, 0.3)
-            if bi == 0:
-                sd[pre + '.downsample.0.weight'] = _conv(gen, planes * 4, inplanes, 1)
-                _bn(gen, sd, pre + '.downsample.1', planes * 4, 0.3, 0.6)
-            inplanes = planes * 4
-    sd['fc.weight'] = torch.randn(1000, 2048, generator=gen) * 0.01  # unused by the pyramid encoder
+            stride = 2 if (bi == 0 and li > 1) else 1
+            if bottleneck:
+                sd[pre + '.conv1.weight'] = _conv(gen, planes, inplanes, 1)
+                _bn(gen, sd, pre + '.bn1', planes, 0.5, 1.0)
+                sd[pre + '.conv2.weight'] = _conv(gen, planes, planes, 3)
+                _bn(gen, sd, pre + '.bn2', planes, 0.5, 1.0)
+                sd[pre + '.conv3.weight'] = _conv(gen, planes * 4, planes, 1)
+                _bn(gen, sd, pre + '.bn3', planes * 4, 0.1, 0.3)
+            else:
+                sd[pre + '.conv1.weight'] = _conv(gen, planes, inplanes, 3)
+                _bn(gen, sd, pre + '.bn1', planes, 0.5, 1.0)
+                sd[pre + '.conv2.weight'] = _conv(gen, planes, planes, 3)
+                _bn(gen, sd, pre + '.bn2', planes, 0.2, 0.5)
+            if stride != 1 or inplanes != planes * expansion:
+                sd[pre + '.downsample.0.weight'] = _conv(gen, planes * expansion, inplanes, 1)
+                _bn(gen, sd, pre + '.downsample.1', planes * expansion, 0.3, 0.6)
+            inplanes = planes * expansion
+    sd['fc.weight'] = torch.randn(1000, 512 * expansion, generator=gen) * 0.01  # unused by the encoders
     sd['fc.bias'] = torch.zeros(1000)
+    return sd
+
+
+def synthetic_resnet101_state(seed: int = 0) -> Dict[str, torch.Tensor]:
+    return synthetic_resnet_state('resnet101', seed)
+
+
+def synthetic_encoder_state_dict(arch: str = 'resnet101', seed: int = 0) -> Dict[str, torch.Tensor]:
+    """`state_dict()` of a reference encoder module: `mean`, `std`, `encoder.model.*`."""
+    sd = {'mean': torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1), 'std': torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)}
+    for key, value in synthetic_resnet_state(arch, seed).items():
+        sd['encoder.model.' + key] = value
     return sd
 
 
@@ -89,7 +113,8 @@ def synthetic_state_dict(seed: int = 0,
                          stop_bias: float = 0.0,
                          with_lm: bool = True,
                          feature_size: int = FEATURE_SIZE,
-                         with_encoder: bool = True) -> Dict[str, torch.Tensor]:
+                         with_encoder: bool = True,
+                         encoder_arch: str = 'resnet101') -> Dict[str, torch.Tensor]:
     """Full reference-format `Decoder` state dict.
 
     `sharpen` scales the vocab projection so top-k order is not rounding noise; `stop_bias` is added to the
@@ -105,7 +130,7 @@ def synthetic_state_dict(seed: int = 0,
     if with_encoder:
         sd['encoder.mean'] = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
         sd['encoder.std'] = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
-        for key, value in synthetic_resnet101_state(seed).items():
+        for key, value in synthetic_resnet_state(encoder_arch, seed).items():
             sd['encoder.encoder.model.' + key] = value
     _linear(gen, sd, 'init_h.0', H, F)
     _linear(gen, sd, 'init_c.0', H, F)

@@ -27,8 +27,17 @@ VARIANTS = {  # name -> (sharpen, stop_bias)
 ENC_NEURONS, DEC_NEURONS, K = 2, 6, 15
 
 
-def build_reference_decoder(milan, lang, sd, vocab, with_encoder=True):
-    indexer = lang.Indexer(lang.Vocab(tuple(vocab)), tokenize=None, start=True, stop=True, pad=True, unk=True)
+def whitespace_tokenize(texts):
+    """Stand-in tokenizer for the score golden (spaCy is not installed): any callable works as `Indexer.tokenize`."""
+    return tuple(tuple(text.lower().split()) for text in texts)
+
+
+SCORE_CAPTIONS = ('the dog and w4999', 'cat', 'w100 zzz sky sky grass w2048 w77', 'Red blue ROUND text faces',
+                  'w31 w32 w33 w34 w35 w36 w37 w38 w39 w40 w41 w42', 'unknownword')
+
+
+def build_reference_decoder(milan, lang, sd, vocab, with_encoder=True, tokenize=None):
+    indexer = lang.Indexer(lang.Vocab(tuple(vocab)), tokenize=tokenize, start=True, stop=True, pad=True, unk=True)
     encoder = milan.encoders.PyramidConvEncoder('resnet101', pretrained=False)
     lm = milan.lms.LanguageModel(indexer)
     decoder = milan.decoders.Decoder(indexer, encoder, lm=lm)
@@ -49,12 +58,77 @@ def synthetic_features(n, k, seed):
     return feats
 
 
+def make_score_golden(milan, lang, vocab):
+    """`Decoder.score` (src/milan/decoders.py:636-711) + `Indexer.__call__/index` (src/utils/lang.py:379-515)."""
+    feats = synthetic_features(DEC_NEURONS, K, seed=0)
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0, with_encoder=False)
+    decoder = build_reference_decoder(milan, lang, sd, vocab, with_encoder=False, tokenize=whitespace_tokenize)
+    captions = list(SCORE_CAPTIONS)
+    with torch.no_grad():
+        scores = decoder.score(captions, feats, mi=False)
+        scores_mi = decoder.score(captions, feats)  # mi defaults to True with an LM (decoders.py:385-387)
+        scores_one = decoder.score(captions, feats[:1], mi=False)  # one feature set for every caption
+    indexer = decoder.indexer
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, 'score.npz'),
+        indexed_default=np.array(indexer(captions), dtype=np.int64),
+        indexed_nopad=np.array([list(row) + [-1] * (16 - len(row))
+                                for row in indexer(captions, start=False, stop=True, pad=False, unk=True)],
+                               dtype=np.int64),
+        indexed_len4=np.array(indexer(captions, length=4), dtype=np.int64),
+        indexed_nounk=np.array([list(row) + [-1] * (16 - len(row))
+                                for row in indexer(captions, start=False, stop=False, pad=False, unk=False)],
+                               dtype=np.int64),
+        indexed_single=np.array(indexer(captions[2]), dtype=np.int64),
+        scores=scores.numpy(), scores_mi=scores_mi.numpy(), scores_one=scores_one.numpy())
+    print('score golden:', scores.tolist(), scores_mi.tolist())
+
+
+ENCODER_VARIANTS = (('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18'))
+
+
+def encoder_variant_inputs():
+    """5 exemplar images + masks for the secondary encoder configs (one all-zero mask, one tiny mask)."""
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(1, 5, seed=5, zero_mask_fraction=0.0)
+    masks_u8[0, 1] = 0
+    masks_u8[0, 2] = 0
+    masks_u8[0, 2, :, 100:102, 50:52] = 1
+    return images_u8.view(5, 3, 224, 224), masks_u8.view(5, 1, 224, 224)
+
+
+def make_encoder_variant_goldens(milan):
+    """The reference's `PyramidConvEncoder('resnet18'|'resnet50')` and `SpatialConvEncoder('resnet18')`
+    (`src/milan/encoders.py:159-351`) on seeded weights and exemplars."""
+    images_u8, masks_u8 = encoder_variant_inputs()
+    scale = torch.tensor(1.0 / 255.0, dtype=torch.float64).to(torch.float32)
+    images, masks = images_u8.float().mul(scale), masks_u8.float()
+    out = {}
+    for kind, arch in ENCODER_VARIANTS:
+        cls = milan.encoders.SpatialConvEncoder if kind == 'spatial' else milan.encoders.PyramidConvEncoder
+        encoder = cls(arch, pretrained=False)
+        missing, unexpected = encoder.load_state_dict(synthetic.synthetic_encoder_state_dict(arch, seed=3), strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        encoder.eval()
+        with torch.no_grad():
+            features = encoder(images, masks)
+        assert tuple(features.shape[1:]) == tuple(encoder.feature_shape)
+        out[f'{kind}_{arch}'] = features.numpy()
+        print(f'encoder golden [{kind}/{arch}]:', tuple(features.shape), 'abs max', features.abs().max().item())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'encoder_variants.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     milan, lang = ref_import.import_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     vocab = synthetic.synthetic_vocab(5000)
+    if '--only-score' in sys.argv:
+        return make_score_golden(milan, lang, vocab)
+    if '--only-encoders' in sys.argv:
+        return make_encoder_variant_goldens(milan)
+    make_score_golden(milan, lang, vocab)
+    make_encoder_variant_goldens(milan)
 
     # ---- encoder golden: reference PyramidConvEncoder('resnet101') on seeded exemplars.
     sd = synthetic.synthetic_state_dict(seed=0, sharpen=3.0)

@@ -40,24 +40,47 @@ def _bottleneck(x: torch.Tensor, sd: State, prefix: str, stride: int) -> torch.T
     return F.relu(out + identity)
 
 
-def resnet101_retained(images: torch.Tensor, sd: State, prefix: str = 'encoder.encoder.model.') -> List[torch.Tensor]:
+def _basic_block(x: torch.Tensor, sd: State, prefix: str, stride: int) -> torch.Tensor:
+    """torchvision BasicBlock (resnet18/34), eval mode."""
+    identity = x
+    out = F.relu(_bn(F.conv2d(x, sd[prefix + '.conv1.weight'], stride=stride, padding=1), sd, prefix + '.bn1'))
+    out = _bn(F.conv2d(out, sd[prefix + '.conv2.weight'], padding=1), sd, prefix + '.bn2')
+    if prefix + '.downsample.0.weight' in sd:
+        identity = _bn(F.conv2d(x, sd[prefix + '.downsample.0.weight'], stride=stride), sd,
+                       prefix + '.downsample.1')
+    return F.relu(out + identity)
+
+
+RESNET_ARCHS = {'resnet101': (True, (3, 4, 23, 3)), 'resnet50': (True, (3, 4, 6, 3)),
+                'resnet18': (False, (2, 2, 2, 2)), 'resnet34': (False, (3, 4, 6, 3))}
+
+
+def resnet_retained(images: torch.Tensor, sd: State, prefix: str = 'encoder.encoder.model.',
+                    arch: str = 'resnet101') -> List[torch.Tensor]:
     """Outputs of modules ('conv1','layer1','layer2','layer3','layer4') as nethook retains them.
 
     Follows `src/milan/encoders.py:273-276,298-299` + `src/deps/netdissect/nethook.py:226-235`: 'conv1' is the
-    RAW 7x7 conv output (before bn1/ReLU); layerN are post-residual-ReLU stage outputs.
+    RAW 7x7 conv output (before bn1/ReLU); layerN are post-residual-ReLU stage outputs. `arch` picks the
+    torchvision graph of `PyramidConvEncoder.configs()` (`src/milan/encoders.py:326-351`).
     """
+    bottleneck, stage_blocks = RESNET_ARCHS[arch]
+    block = _bottleneck if bottleneck else _basic_block
     sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     retained = []
     x = F.conv2d(images, sub['conv1.weight'], stride=2, padding=3)
     retained.append(x)
     x = F.relu(_bn(x, sub, 'bn1'))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-    for li, blocks in enumerate((3, 4, 23, 3), start=1):
+    for li, blocks in enumerate(stage_blocks, start=1):
         for bi in range(blocks):
             stride = 2 if (bi == 0 and li > 1) else 1
-            x = _bottleneck(x, sub, f'layer{li}.{bi}', stride)
+            x = block(x, sub, f'layer{li}.{bi}', stride)
         retained.append(x)
     return retained
+
+
+def resnet101_retained(images: torch.Tensor, sd: State, prefix: str = 'encoder.encoder.model.') -> List[torch.Tensor]:
+    return resnet_retained(images, sd, prefix, 'resnet101')
 
 
 def masked_pool(features: Sequence[torch.Tensor], masks: torch.Tensor) -> torch.Tensor:
@@ -73,22 +96,38 @@ def masked_pool(features: Sequence[torch.Tensor], masks: torch.Tensor) -> torch.
     return torch.cat(masked, dim=-1)
 
 
-def pyramid_encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: State) -> torch.Tensor:
+def pyramid_encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: State,
+                   arch: str = 'resnet101') -> torch.Tensor:
     """`PyramidConvEncoder.forward`, `src/milan/encoders.py:286-320`. images (N,3,H,W) in [0,1]."""
     if masks is None:
         masks = images.new_ones((len(images), 1, *images.shape[2:]))
     images = (images - sd['encoder.mean']) / sd['encoder.std']
-    return masked_pool(resnet101_retained(images, sd), masks.clone())
+    return masked_pool(resnet_retained(images, sd, arch=arch), masks.clone())
 
 
-def encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: State) -> torch.Tensor:
-    """`Decoder.encode`, `src/milan/decoders.py:525-546`: (B,k,3,H,W) -> (B,k,F)."""
+def spatial_encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: State,
+                   arch: str = 'resnet18') -> torch.Tensor:
+    """`SpatialConvEncoder.forward`, `src/milan/encoders.py:193-214`: (N,3,H,W) -> (N, 49, 512)."""
+    if masks is None:
+        masks = images.new_ones((len(images), 1, *images.shape[2:]))
+    images = (images - sd['encoder.mean']) / sd['encoder.std']
+    features = resnet_retained(images * masks, sd, arch=arch)[-1]
+    features = features.permute(0, 2, 3, 1)
+    return features.reshape(len(images), -1, features.shape[-1])
+
+
+def encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: State, arch: str = 'resnet101',
+           kind: str = 'pyramid') -> torch.Tensor:
+    """`Decoder.encode`, `src/milan/decoders.py:525-546`: (B,k,3,H,W) -> (B,n_keys,F)."""
     batch_size = len(images)
     images = images.reshape(-1, *images.shape[-3:])
     if masks is not None:
         masks = masks.reshape(-1, *masks.shape[-3:])
-    features = pyramid_encode(images, masks, sd)
-    return features.view(batch_size, -1, features.shape[-1])
+    if kind == 'spatial':
+        features = spatial_encode(images, masks, sd, arch)
+    else:
+        features = pyramid_encode(images, masks, sd, arch)
+    return features.reshape(batch_size, -1, features.shape[-1])
 
 
 # ----------------------------------------------------------------------------------------------- decoder
@@ -229,7 +268,7 @@ def decode(features: torch.Tensor, sd: State, vocab: Sequence[str], strategy: st
     """`Decoder.forward` from precomputed features, `src/milan/decoders.py:379-523`."""
     has_lm = 'lm.embedding.weight' in sd
     if mi is None:
-        mi = has_lm and strategy != 'rerank'
+        mi = has_lm and (not isinstance(strategy, str) or strategy != 'rerank')
     n_vocab = len(vocab)
     start_index, stop_index = n_vocab, n_vocab + 1
     batch_size = len(features)
@@ -286,6 +325,47 @@ def decode(features: torch.Tensor, sd: State, vocab: Sequence[str], strategy: st
             scores = scores[idx_b, idx_s].view(batch_size)
     captions = tuple(reconstruct(seq, vocab) for seq in tokens.tolist())
     return DecoderOutput(captions, scores, tokens, predictions, attentions, beam_scores, beam_tokens)
+
+
+def index_tokens(tokenized: Sequence[Sequence[str]], vocab: Sequence[str], start: bool = True, stop: bool = True,
+                 pad: bool = True, unk: bool = True, length: Optional[int] = None) -> Tuple[Tuple[int, ...], ...]:
+    """`Indexer.index`, `src/utils/lang.py:460-515`, for an indexer whose defaults are all True / no length."""
+    ids = {token: index for index, token in enumerate(vocab)}
+    n = len(vocab)
+    start_index, stop_index, pad_index, unk_index = n, n + 1, n + 2, n + 3
+    length = length or max(len(toks) for toks in tokenized)
+    length += int(start) + int(stop)
+    indexed = []
+    for tokens in tokenized:
+        indices = [start_index] if start else []
+        if unk:
+            indices += [ids.get(tok, unk_index) for tok in tokens]
+        else:
+            indices += [ids[tok] for tok in tokens if tok in ids]
+        if stop:
+            if len(indices) >= length:
+                indices = indices[:length - 1]
+            indices.append(stop_index)
+        if len(indices) < length and pad:
+            indices += [pad_index] * (length - len(indices))
+        elif len(indices) > length:
+            indices = indices[:length]
+        indexed.append(tuple(indices))
+    return tuple(indexed)
+
+
+@torch.no_grad()
+def score(tokenized: Sequence[Sequence[str]], features: torch.Tensor, sd: State, vocab: Sequence[str],
+          mi: Optional[bool] = None, temperature: float = 0.2) -> torch.Tensor:
+    """`Decoder.score`, `src/milan/decoders.py:636-711`, from pre-tokenized captions and features."""
+    if len(features) == 1:
+        features = features.expand(len(tokenized), *features.shape[1:])
+    targets = torch.tensor(index_tokens(tokenized, vocab))[:, 1:]
+    outputs = decode(features, sd, vocab, strategy=targets, length=targets.shape[1], mi=mi, temperature=temperature)
+    indexed = index_tokens(tokenized, vocab, start=False, stop=True, pad=False, unk=True)
+    totals = [scores[torch.arange(len(indices)), torch.tensor(indices)].sum().item()
+              for scores, indices in zip(outputs.predictions, indexed)]
+    return torch.tensor(totals)
 
 
 @torch.no_grad()

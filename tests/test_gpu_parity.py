@@ -290,6 +290,30 @@ def test_facade_matches_reference_surface(full_sd):
         decoder(images_f, masks_f, strategy=torch.zeros(3, 4, dtype=torch.long))
 
 
+def test_score_matches_reference_golden(golden_dir):
+    """`Decoder.score` (src/milan/decoders.py:636-711) through the facade vs the reference's own output."""
+    from neuron_descriptions_b200 import milan
+    from neuron_descriptions_b200.milan import lang
+    from oracle.make_golden import SCORE_CAPTIONS, whitespace_tokenize
+    g = np.load(os.path.join(golden_dir, 'score.npz'))
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0, with_encoder=False)
+    indexer = lang.Indexer(lang.Vocab(VOCAB), tokenize=whitespace_tokenize, start=True, stop=True, pad=True, unk=True)
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer), max_neurons=4)  # 6 captions -> two engine chunks
+    decoder.load_state_dict(sd)
+    decoder.to('cuda:0')
+    feats = synthetic_features(6, 15, seed=0)
+    captions = list(SCORE_CAPTIONS)
+    np.testing.assert_allclose(decoder.score(captions, feats, mi=False).cpu().numpy(), g['scores'], atol=LOGP_TOL)
+    np.testing.assert_allclose(decoder.score(captions, feats).cpu().numpy(), g['scores_mi'], atol=LOGP_TOL)
+    np.testing.assert_allclose(decoder.score(captions, feats[:1], mi=False).cpu().numpy(), g['scores_one'],
+                               atol=LOGP_TOL)
+    with pytest.raises(ValueError, match='option disallowed'):
+        decoder.score(captions, feats, length=3)
+    with pytest.raises(ValueError, match='must have batch size 1 or'):
+        decoder.score(captions, feats[:2])
+
+
 def test_edge_cases_vs_oracle():
     """Ragged / extreme sizes: one neuron, beam 1 and the maximum beam, length 1, more keys than the register tile
     of the attention kernel, empty inputs."""

@@ -1,0 +1,69 @@
+"""CPU: the host-side `lang.Indexer` mirror (ids <-> text) and the oracle's `score` restatement against goldens
+produced by the UNMODIFIED reference (`oracle/make_golden.py::make_score_golden`; reference code:
+`src/utils/lang.py:379-515,573-730`, `src/milan/decoders.py:636-711`)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neuron_descriptions_b200 import synthetic
+from neuron_descriptions_b200.milan import lang
+from oracle import milan_oracle as O
+from oracle.make_golden import DEC_NEURONS, K, SCORE_CAPTIONS, synthetic_features, whitespace_tokenize
+
+VOCAB = synthetic.synthetic_vocab(5000)
+
+
+def _indexer(tokenize=whitespace_tokenize):
+    return lang.Indexer(lang.Vocab(VOCAB), tokenize=tokenize, start=True, stop=True, pad=True, unk=True)
+
+
+def _ragged(rows):
+    return np.array([list(row) + [-1] * (16 - len(row)) for row in rows], dtype=np.int64)
+
+
+def test_indexer_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'score.npz'))
+    indexer = _indexer()
+    captions = list(SCORE_CAPTIONS)
+    np.testing.assert_array_equal(np.array(indexer(captions)), g['indexed_default'])
+    np.testing.assert_array_equal(_ragged(indexer(captions, start=False, stop=True, pad=False, unk=True)),
+                                  g['indexed_nopad'])
+    np.testing.assert_array_equal(np.array(indexer(captions, length=4)), g['indexed_len4'])
+    np.testing.assert_array_equal(_ragged(indexer(captions, start=False, stop=False, pad=False, unk=False)),
+                                  g['indexed_nounk'])
+    np.testing.assert_array_equal(np.array(indexer(captions[2])), g['indexed_single'])
+    # the oracle's own restatement agrees too
+    np.testing.assert_array_equal(np.array(O.index_tokens(whitespace_tokenize(captions), VOCAB)),
+                                  g['indexed_default'])
+
+
+def test_indexer_round_trip_and_errors():
+    indexer = _indexer()
+    ids = indexer('dog and zzz cat')
+    assert ids[0] == indexer.start_index and ids[-1] == indexer.stop_index and ids[3] == indexer.unk_index
+    assert indexer.unindex(ids, specials=False) == ('dog', 'and', 'cat')
+    assert indexer.reconstruct(ids) == 'Dog and cat'
+    assert indexer.index(()) == ()
+    with pytest.raises(NotImplementedError, match='no tokenizer'):
+        _indexer(tokenize=None)('dog cat')
+    with pytest.raises(ValueError, match='unknown index'):
+        indexer.unindex([len(indexer) + 1])
+
+
+def test_basic_tokenizer():
+    tokenize = lang.BasicTokenizer()
+    assert tokenize('Dogs, and the Cat\'s toys!') == ('dogs', 'and', 'the', "cat's", 'toys')
+    assert tokenize(['A b', '']) == (('a', 'b'), ())
+
+
+def test_oracle_score_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'score.npz'))
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0, with_encoder=False)
+    feats = synthetic_features(DEC_NEURONS, K, seed=0)
+    tokenized = whitespace_tokenize(SCORE_CAPTIONS)
+    np.testing.assert_allclose(O.score(tokenized, feats, sd, VOCAB, mi=False).numpy(), g['scores'], atol=2e-4)
+    np.testing.assert_allclose(O.score(tokenized, feats, sd, VOCAB).numpy(), g['scores_mi'], atol=2e-4)
+    np.testing.assert_allclose(O.score(tokenized, feats[:1], sd, VOCAB, mi=False).numpy(), g['scores_one'],
+                               atol=2e-4)

@@ -37,6 +37,26 @@ def test_encoder_matches_reference_golden(golden_dir):
     assert feats[0, 1].abs().max().item() > 0.0
 
 
+@pytest.mark.parametrize('kind,arch', [('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18')])
+def test_encoder_variants_match_reference_golden(golden_dir, kind, arch):
+    """The secondary encoder configs (`src/milan/encoders.py:214-216,326-351`) of the oracle vs the reference."""
+    from oracle.make_golden import encoder_variant_inputs
+    g = _load(golden_dir, 'encoder_variants.npz')
+    images_u8, masks_u8 = encoder_variant_inputs()
+    images, masks = O.to_float_inputs(images_u8, masks_u8)
+    sd = {'encoder.' + k: v for k, v in synthetic.synthetic_encoder_state_dict(arch, seed=3).items()}
+    with torch.no_grad():
+        if kind == 'spatial':
+            feats = O.spatial_encode(images, masks, sd, arch)
+        else:
+            feats = O.pyramid_encode(images, masks, sd, arch)
+    ref = torch.from_numpy(g[f'{kind}_{arch}'])
+    torch.testing.assert_close(feats, ref, rtol=2e-4, atol=2e-5)
+    if kind == 'pyramid':
+        assert feats[1].abs().max().item() == 0.0  # all-zero mask
+        assert feats[2].abs().max().item() > 0.0
+
+
 @pytest.mark.parametrize('name', sorted(VARIANTS))
 def test_decoder_matches_reference_golden(golden_dir, name):
     g = _load(golden_dir, f'decoder_{name}.npz')
