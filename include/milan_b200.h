@@ -31,7 +31,7 @@ enum { MILAN_PRECISION_SPLIT = 0, /* bf16 hi/lo split operands, 3 MMAs per k-blo
 enum { MILAN_DTYPE_U8 = 0, MILAN_DTYPE_F32 = 1 };
 /* Backbone of the image encoder (torchvision graphs; src/milan/encoders.py:214-216,326-351). */
 enum { MILAN_ENCODER_RESNET101 = 0, MILAN_ENCODER_RESNET50 = 1, MILAN_ENCODER_RESNET18 = 2,
-       MILAN_ENCODER_RESNET34 = 3 };
+       MILAN_ENCODER_RESNET34 = 3, MILAN_ENCODER_ALEXNET = 4 /* pyramid only, feature_size 1152 */ };
 /* PyramidConvEncoder: masked spatial pooling of conv1 + layer1..4 -> one vector per image
  * (src/milan/encoders.py:286-320). SpatialConvEncoder: images * masks -> layer4 map -> 49 vectors per image
  * (src/milan/encoders.py:193-214). */

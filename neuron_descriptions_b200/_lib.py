@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmilan_b200.so')
 PRECISION_SPLIT, PRECISION_FAST = 0, 1
 DTYPE_U8, DTYPE_F32 = 0, 1
 STRATEGY_GREEDY, STRATEGY_BEAM, STRATEGY_RERANK = 0, 1, 2
-ENCODER_ARCHS = {'resnet101': 0, 'resnet50': 1, 'resnet18': 2, 'resnet34': 3}
+ENCODER_ARCHS = {'resnet101': 0, 'resnet50': 1, 'resnet18': 2, 'resnet34': 3, 'alexnet': 4}
 ENCODER_KINDS = {'pyramid': 0, 'spatial': 1}
 
 

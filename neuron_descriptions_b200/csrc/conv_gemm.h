@@ -22,7 +22,7 @@
 
 namespace milan {
 
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 25;  // up to 5x5 filters (alexnet features.3)
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
 
@@ -96,7 +96,7 @@ namespace milan {
 struct ConvDesc {
   int N, H, W;   // input extents
   int Cin, Cout;
-  int ksize;     // 1 or 3
+  int ksize;     // 1, 3 or 5 (pad = ksize/2)
   int stride;    // 1 or 2
 };
 

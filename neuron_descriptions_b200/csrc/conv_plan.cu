@@ -14,7 +14,7 @@ constexpr int kDecoderKbPerChunk = 2;
 int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n) {
   memset(p, 0, sizeof(*p));
   if (d.Cin % kGemmBlockK != 0) return -2;
-  if (!(d.ksize == 1 || d.ksize == 3) || !(d.stride == 1 || d.stride == 2)) return -3;
+  if (!(d.ksize == 1 || d.ksize == 3 || d.ksize == 5) || !(d.stride == 1 || d.stride == 2)) return -3;
   if (d.stride == 2 && ((d.H | d.W) & 1)) return -4;
   const int Ho = d.H / d.stride, Wo = d.W / d.stride;
   const int bn_tile = (d.Cout <= 64) ? 64 : 128;

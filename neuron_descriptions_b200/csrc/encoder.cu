@@ -273,6 +273,123 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat1
   if (y_lo != nullptr) *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ---------------------------------------------------------------- AlexNet pyramid pieces
+template <typename T>
+__global__ void __launch_bounds__(256) alexnet_im2col_kernel(const T* __restrict__ images, int n_images,
+                                                             __nv_bfloat16* __restrict__ a_hi,
+                                                             __nv_bfloat16* __restrict__ a_lo, float3 mean,
+                                                             float3 stdv, int split) {
+  constexpr int O = 55, K2 = kAlexK0 / 2;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_images) * O * O * K2;
+  if (idx >= total) return;
+  const int k2 = idx % K2;
+  const long long row = idx / K2;
+  const int ow = row % O;
+  const int oh = (row / O) % O;
+  const int n = row / (O * O);
+  const float m[3] = {mean.x, mean.y, mean.z};
+  const float sd[3] = {stdv.x, stdv.y, stdv.z};
+  float v[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = 2 * k2 + j;
+    v[j] = 0.0f;
+    if (k < 363) {
+      const int c = k / 121, r = (k / 11) % 11, t = k % 11;
+      const int ih = oh * 4 + r - 2, iw = ow * 4 + t - 2;
+      if (ih >= 0 && ih < kImg && iw >= 0 && iw < kImg) {
+        const T* px = images + ((static_cast<long long>(n) * 3 + c) * kImg + ih) * kImg + iw;
+        float x;
+        if (sizeof(T) == 1) x = __fmul_rn(static_cast<float>(*px), 0.00392156862745098f);
+        else x = static_cast<float>(*px);
+        v[j] = __fdiv_rn(__fsub_rn(x, m[c]), sd[c]);
+      }
+    }
+  }
+  uint32_t h, l;
+  split_bf16x2(v[0], v[1], h, l);
+  reinterpret_cast<uint32_t*>(a_hi)[idx] = h;
+  if (split) reinterpret_cast<uint32_t*>(a_lo)[idx] = l;
+}
+
+// One CTA per image. Source index / weights follow ATen's area_pixel_compute_source_index for
+// align_corners=False: src = max(0, scale * (dst + 0.5) - 0.5), scale = in / out (float).
+template <typename T>
+__global__ void __launch_bounds__(256) mask_resize_kernel(const T* __restrict__ masks, int S,
+                                                          float* __restrict__ out, int out_stride) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const T* m = masks + static_cast<long long>(n) * kImg * kImg;
+  float* o = out + static_cast<long long>(n) * out_stride;
+  const float scale = static_cast<float>(kImg) / static_cast<float>(S);
+  float local_sum = 0.0f, local_max = 0.0f;
+  for (int p = threadIdx.x; p < S * S; p += blockDim.x) {
+    const int i = p / S, j = p - i * S;
+    float sy = __fsub_rn(__fmul_rn(scale, static_cast<float>(i) + 0.5f), 0.5f);
+    float sx = __fsub_rn(__fmul_rn(scale, static_cast<float>(j) + 0.5f), 0.5f);
+    sy = sy < 0.0f ? 0.0f : sy;
+    sx = sx < 0.0f ? 0.0f : sx;
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = y0 + (y0 < kImg - 1 ? 1 : 0), x1 = x0 + (x0 < kImg - 1 ? 1 : 0);
+    const float ly1 = sy - static_cast<float>(y0), lx1 = sx - static_cast<float>(x0);
+    const float ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+    const float p00 = load_mask(m + y0 * kImg + x0), p01 = load_mask(m + y0 * kImg + x1);
+    const float p10 = load_mask(m + y1 * kImg + x0), p11 = load_mask(m + y1 * kImg + x1);
+    const float v = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01))),
+                              __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11))));
+    o[p] = v;
+    local_sum += v;
+    local_max = fmaxf(local_max, fabsf(v));
+  }
+  const float total = block_reduce_sum(local_sum, red);
+  const float amax = block_reduce_max(local_max, red);
+  if (amax > 1e-8f) {
+    for (int p = threadIdx.x; p < S * S; p += blockDim.x) o[p] = o[p] / total;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x_hi,
+                                                           const __nv_bfloat16* __restrict__ x_lo, int n_images,
+                                                           int H, int W, int C, __nv_bfloat16* __restrict__ y_hi,
+                                                           __nv_bfloat16* __restrict__ y_lo) {
+  const int Ho = (H - 3) / 2 + 1, Wo = (W - 3) / 2 + 1, G = C / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_images) * Ho * Wo * G;
+  if (idx >= total) return;
+  const int cg = idx % G;
+  const long long pix = idx / G;
+  const int ow = pix % Wo;
+  const int oh = (pix / Wo) % Ho;
+  const int n = pix / (static_cast<long long>(Wo) * Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const long long off = ((static_cast<long long>(n) * H + oh * 2 + r) * W + ow * 2 + t) * C + cg * 8;
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
+      float v[8] = {bf16_lo_to_f32(h.x), bf16_hi_to_f32(h.x), bf16_lo_to_f32(h.y), bf16_hi_to_f32(h.y),
+                    bf16_lo_to_f32(h.z), bf16_hi_to_f32(h.z), bf16_lo_to_f32(h.w), bf16_hi_to_f32(h.w)};
+      if (x_lo != nullptr) {
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+        v[0] += bf16_lo_to_f32(l.x); v[1] += bf16_hi_to_f32(l.x); v[2] += bf16_lo_to_f32(l.y); v[3] += bf16_hi_to_f32(l.y);
+        v[4] += bf16_lo_to_f32(l.z); v[5] += bf16_hi_to_f32(l.z); v[6] += bf16_lo_to_f32(l.w); v[7] += bf16_hi_to_f32(l.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16x2(m[2 * j], m[2 * j + 1], hi[j], lo[j]);
+  const long long o = pix * C + cg * 8;
+  *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (y_lo != nullptr) *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 __global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                      long long n2, float* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -288,6 +405,42 @@ __global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const
 }
 
 }  // namespace
+
+int launch_alexnet_im2col(const void* images, int dtype, int n_images, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                          const float mean[3], const float stdv[3], int split, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n_images) * 55 * 55 * (kAlexK0 / 2);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  const float3 m = make_float3(mean[0], mean[1], mean[2]);
+  const float3 s = make_float3(stdv[0], stdv[1], stdv[2]);
+  if (dtype == 0)
+    alexnet_im2col_kernel<uint8_t><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(images), n_images, a_hi,
+                                                               a_lo, m, s, split);
+  else
+    alexnet_im2col_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(images), n_images, a_hi, a_lo,
+                                                             m, s, split);
+  note_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_mask_resize(const void* masks, int dtype, int n_images, int S, float* out, int out_stride,
+                       cudaStream_t stream) {
+  if (dtype == 0)
+    mask_resize_kernel<uint8_t><<<n_images, 256, 0, stream>>>(static_cast<const uint8_t*>(masks), S, out, out_stride);
+  else
+    mask_resize_kernel<float><<<n_images, 256, 0, stream>>>(static_cast<const float*>(masks), S, out, out_stride);
+  note_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_maxpool3x3s2(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int n_images, int H, int W, int C,
+                        __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t stream) {
+  const int Ho = (H - 3) / 2 + 1, Wo = (W - 3) / 2 + 1;
+  const long long total = static_cast<long long>(n_images) * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x_hi, x_lo, n_images, H, W, C,
+                                                                                      y_hi, y_lo);
+  note_launch();
+  return static_cast<int>(cudaGetLastError());
+}
 
 int launch_planes_to_f32(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long n, float* out,
                          cudaStream_t stream) {

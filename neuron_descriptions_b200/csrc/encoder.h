@@ -27,4 +27,18 @@ int launch_bn_relu_maxpool(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo,
                            const float* beta, int n_images, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
                            cudaStream_t stream);
 
+
+// ---- AlexNet pyramid (PyramidConvEncoder('alexnet'), src/milan/encoders.py:328-334)
+constexpr int kAlexK0 = 384;  // 3*11*11 = 363 im2col columns of features.0, zero-padded to a multiple of 64
+// Normalise + im2col of the 11x11 stride-4 pad-2 first convolution: A[n*55*55 + oh*55 + ow][(c*11 + r)*11 + s].
+int launch_alexnet_im2col(const void* images, int dtype, int n_images, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                          const float mean[3], const float stdv[3], int split, cudaStream_t stream);
+// Bilinear (align_corners=False, no antialias) resize of (n,1,224,224) masks to SxS for any S, then the
+// per-image sum-normalisation with the all-zero exception (src/milan/encoders.py:303-314). out: [n][stride].
+int launch_mask_resize(const void* masks, int dtype, int n_images, int S, float* out, int out_stride,
+                       cudaStream_t stream);
+// 3x3 stride-2 max-pool without padding on NHWC hi/lo planes (torchvision alexnet features.2 / .5); C % 8 == 0.
+int launch_maxpool3x3s2(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, int n_images, int H, int W, int C,
+                        __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, cudaStream_t stream);
+
 }  // namespace milan

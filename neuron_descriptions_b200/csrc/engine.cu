@@ -105,7 +105,18 @@ constexpr EncoderArch kArchs[] = {
     {"resnet50", true, {3, 4, 6, 3}},
     {"resnet18", false, {2, 2, 2, 2}},
     {"resnet34", false, {3, 4, 6, 3}},
+    {"alexnet", false, {0, 0, 0, 0}},  // torchvision alexnet `features`: its own pipeline (encode_alexnet)
 };
+// AlexNet pyramid (src/milan/encoders.py:328-334): retained modules features.{0,3,6,8,10}; because their ReLUs
+// are in-place and nethook retains `output.detach()` (a view, nethook.py:226-235), the retained maps are the
+// POST-ReLU activations. Geometry: (in resolution, Cin, Cout, ksize) per conv; features.0 runs as an im2col GEMM.
+struct AlexConv { const char* name; int res, cin, cout, ksize; };
+constexpr AlexConv kAlexConvs[5] = {{"features.0", 55, kAlexK0, 64, 1}, {"features.3", 27, 64, 192, 5},
+                                    {"features.6", 13, 192, 384, 3}, {"features.8", 13, 384, 256, 3},
+                                    {"features.10", 13, 256, 256, 3}};
+constexpr int kAlexMaskSizes[3] = {55, 27, 13};
+constexpr int kAlexMaskOffset[3] = {0, 3025, 3025 + 729};
+constexpr int kAlexMaskStride = 3025 + 729 + 169;
 constexpr int kNumArchs = sizeof(kArchs) / sizeof(kArchs[0]);
 
 }  // namespace
@@ -128,6 +139,8 @@ struct MilanEngine {
   int expansion = 4;             // stage output channels = planes * expansion
   bool spatial = false;          // SpatialConvEncoder: mask the image, emit the layer4 map
   bool has_decoder = true;       // false: encoder-only engine (no decoder tensors were provided)
+  bool alexnet = false;
+  __nv_bfloat16 *axA0[2] = {}, *axAct[5][2] = {}, *axPool[2][2] = {};  // alexnet: im2col, conv outputs, max-pools
   int enc_out_per_image = 0;     // floats milan_encode writes per image
   std::vector<ConvLayer> convs;  // convs after the stem, execution order (103 for resnet101)
   // ---- encoder workspace (hi/lo planes)
@@ -224,6 +237,9 @@ struct MilanEngine {
   }
 
   int finalize_encoder();
+  int finalize_encoder_alexnet();
+  int build_alexnet_plans(int n, std::vector<Plan>** out);
+  int encode_alexnet(const void* d_images, const void* d_masks, int n, int dtype, float* d_out, cudaStream_t st);
   int finalize_decoder();
   int alloc_workspace();
   int build_encoder_plans(int n, std::vector<Plan>** out);
@@ -262,6 +278,7 @@ int MilanEngine::finalize_encoder() {
   } else {
     return fail("missing tensor encoder.std");
   }
+  if (alexnet) return finalize_encoder_alexnet();
   // stem: [64][3][7][7] -> [64][256] in the window order of build_stem_params; no BN fold (raw conv1 is pooled).
   const HostTensor* w = get(pre + "conv1.weight");
   if (w == nullptr || w->numel() != 64 * 3 * 49) return fail("missing/invalid %sconv1.weight", pre.c_str());
@@ -340,6 +357,100 @@ int MilanEngine::finalize_encoder() {
       }
       inplanes = planes * expansion;
     }
+  }
+  return 0;
+}
+
+int MilanEngine::finalize_encoder_alexnet() {
+  const std::string pre = "encoder.encoder.model.";
+  for (const AlexConv& a : kAlexConvs) {
+    const bool first = a.ksize == 1;  // features.0: [64][3][11][11], natural (c, r, s) order = im2col column order
+    const int taps = first ? 1 : a.ksize * a.ksize;
+    const int cin_w = first ? 3 * 11 * 11 : a.cin;
+    const HostTensor* cw = get(pre + a.name + ".weight");
+    const HostTensor* cb = get(pre + a.name + ".bias");
+    if (cw == nullptr || cw->numel() != static_cast<int64_t>(a.cout) * cin_w * taps)
+      return fail("missing/invalid %s%s.weight", pre.c_str(), a.name);
+    if (cb == nullptr || cb->numel() != a.cout) return fail("missing/invalid %s%s.bias", pre.c_str(), a.name);
+    std::vector<float> packed(static_cast<size_t>(a.cout) * taps * a.cin, 0.f);
+    for (int co = 0; co < a.cout; ++co) {
+      if (first) {
+        for (int k = 0; k < cin_w; ++k) packed[static_cast<size_t>(co) * a.cin + k] = cw->data[static_cast<size_t>(co) * cin_w + k];
+      } else {
+        for (int ci = 0; ci < a.cin; ++ci)
+          for (int t = 0; t < taps; ++t)
+            packed[(static_cast<size_t>(co) * taps + t) * a.cin + ci] = cw->data[(static_cast<size_t>(co) * a.cin + ci) * taps + t];
+      }
+    }
+    ConvLayer L;
+    L.name = a.name;
+    L.cin = a.cin; L.cout = a.cout; L.ksize = a.ksize; L.stride = 1;
+    if (upload_split(&L.w, packed, a.cout, taps * a.cin)) return 1;
+    if (upload_f32(&L.bias, cb->data, (a.cout + 127) / 128 * 128)) return 1;
+    convs.push_back(L);
+  }
+  return 0;
+}
+
+int MilanEngine::build_alexnet_plans(int n, std::vector<Plan>** out) {
+  auto it = enc_plans.find(n);
+  if (it != enc_plans.end()) {
+    *out = &it->second;
+    return 0;
+  }
+  std::vector<Plan> plans;
+  const int sp = split ? 1 : 0;
+  for (int i = 0; i < 5; ++i) {
+    const AlexConv& a = kAlexConvs[i];
+    const ConvLayer& L = convs[i];
+    __nv_bfloat16** in = i == 0 ? axA0 : (i == 1 ? axPool[0] : (i == 2 ? axPool[1] : axAct[i - 1]));
+    Plan pl;
+    ConvDesc d{n, a.res, a.res, L.cin, L.cout, L.ksize, 1};
+    ConvIO io{};
+    io.in_hi = in[0]; io.in_lo = in[1];
+    io.w_hi = L.w.hi; io.w_lo = L.w.lo;
+    io.bias = L.bias;
+    io.out_hi = axAct[i][0]; io.out_lo = axAct[i][1];
+    io.relu = 1;  // in-place ReLU reaches the retained tensor (see kAlexConvs)
+    if (build_conv_params(&pl.p, d, io, sp, &pl.block_n)) return fail("plan %s: %s", L.name.c_str(), tmap_last_error());
+    plans.push_back(pl);
+  }
+  auto ins = enc_plans.emplace(n, std::move(plans));
+  *out = &ins.first->second;
+  return 0;
+}
+
+// PyramidConvEncoder('alexnet').forward (src/milan/encoders.py:286-320 with the layer table of :328-334).
+int MilanEngine::encode_alexnet(const void* d_images, const void* d_masks, int n, int dtype, float* d_out,
+                                cudaStream_t st) {
+  std::vector<Plan>* plans = nullptr;
+  if (build_alexnet_plans(n, &plans)) return 1;
+  const int F = cfg.feature_size, sp = split ? 1 : 0;
+  if (profiling) conv_events_used = 0;
+  const void* masks = d_masks;
+  int mask_dtype = dtype;
+  if (masks == nullptr) {
+    if (ones_masks == nullptr) {
+      uint8_t* p = nullptr;
+      if (dalloc(&p, static_cast<size_t>(cfg.max_images) * 224 * 224)) return 1;
+      CU(cudaMemset(p, 1, static_cast<size_t>(cfg.max_images) * 224 * 224));
+      ones_masks = p;
+    }
+    masks = ones_masks;
+    mask_dtype = MILAN_DTYPE_U8;
+  }
+  for (int l = 0; l < 3; ++l)
+    RC(launch_mask_resize(masks, mask_dtype, n, kAlexMaskSizes[l], mask_wts + kAlexMaskOffset[l], kAlexMaskStride, st));
+  RC(launch_alexnet_im2col(d_images, dtype, n, axA0[0], axA0[1], mean, stdv, sp, st));
+  int feat_off = 0;
+  for (int i = 0; i < 5; ++i) {
+    const AlexConv& a = kAlexConvs[i];
+    if (run_conv((*plans)[i], st)) return 1;
+    const int level = i < 2 ? i : 2;
+    RC(launch_masked_pool(axAct[i][0], axAct[i][1], mask_wts + kAlexMaskOffset[level], kAlexMaskStride, n, a.res * a.res,
+                          a.cout, d_out + feat_off, F, st));
+    feat_off += a.cout;
+    if (i < 2) RC(launch_maxpool3x3s2(axAct[i][0], axAct[i][1], n, a.res, a.res, a.cout, axPool[i][0], axPool[i][1], st));
   }
   return 0;
 }
@@ -451,7 +562,18 @@ int MilanEngine::alloc_workspace() {
   const int V = cfg.vocab_size, E = cfg.embedding_size, H = cfg.hidden_size, A = cfg.attention_size,
             F = cfg.feature_size, Kk = cfg.max_keys, L = cfg.max_length;
   (void)V;
-  if (cfg.has_encoder) {
+  if (cfg.has_encoder && alexnet) {
+    const size_t n = cfg.max_images;
+    if (dalloc2(axA0, n * 3025 * kAlexK0)) return 1;
+    for (int i = 0; i < 5; ++i)
+      if (dalloc2(axAct[i], n * kAlexConvs[i].res * kAlexConvs[i].res * kAlexConvs[i].cout)) return 1;
+    if (dalloc2(axPool[0], n * 27 * 27 * 64)) return 1;
+    if (dalloc2(axPool[1], n * 13 * 13 * 192)) return 1;
+    if (dalloc(&mask_wts, n * kAlexMaskStride)) return 1;
+    if (dalloc(&feat_enc, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
+    if (dalloc(&d_img_stage, n * 3 * 224 * 224)) return 1;
+    if (dalloc(&d_mask_stage, n * 224 * 224)) return 1;
+  } else if (cfg.has_encoder) {
     const size_t n = cfg.max_images;
     if (dalloc2(stemA, n * kStemPadH * kStemPadW * 4)) return 1;
     if (dalloc2(c1raw, n * 12544 * 64)) return 1;
@@ -631,6 +753,7 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   if (n <= 0) return 0;
   if (n > cfg.max_images) return fail("milan_encode: n_images %d exceeds max_images %d", n, cfg.max_images);
   if (reinterpret_cast<uintptr_t>(d_images) % 16 != 0) return fail("milan_encode: d_images must be 16-byte aligned");
+  if (alexnet) return encode_alexnet(d_images, d_masks, n, dtype, d_out, st);
   std::vector<Plan>* plans = nullptr;
   if (build_encoder_plans(n, &plans)) return 1;
   const int F = cfg.feature_size;
@@ -973,8 +1096,11 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   const EncoderArch& arch = kArchs[config->encoder_arch];
   const int expansion = arch.bottleneck ? 4 : 1;
   const bool spatial = config->encoder_kind == MILAN_ENCODER_SPATIAL;
+  const bool alexnet = config->encoder_arch == MILAN_ENCODER_ALEXNET;
+  if (alexnet && spatial) return fail("encoder not supported: spatial alexnet");
   if (config->has_encoder) {
-    const int want = spatial ? 512 * expansion : 64 + (64 + 128 + 256 + 512) * expansion;
+    const int want = alexnet ? 64 + 192 + 384 + 256 + 256
+                             : (spatial ? 512 * expansion : 64 + (64 + 128 + 256 + 512) * expansion);
     if (config->feature_size != want)
       return fail("feature_size %d does not match the %s %s encoder (%d)", config->feature_size, arch.name,
                   spatial ? "spatial" : "pyramid", want);
@@ -987,6 +1113,7 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   eng->arch = arch;
   eng->expansion = expansion;
   eng->spatial = spatial;
+  eng->alexnet = alexnet;
   eng->enc_out_per_image = (spatial ? kSpatialKeys : 1) * config->feature_size;
   *out = eng;
   return 0;

@@ -2,7 +2,7 @@
 engine. `PyramidConvEncoder('resnet101')` is the encoder of every shipped MILAN checkpoint
 (`scripts/train_milan.py:29-32,88`); the other ResNet configs of the reference (`resnet18`, `resnet50` pyramids,
 `SpatialConvEncoder('resnet18')`; `src/milan/encoders.py:214-216,326-351`) run on the same kernels with a
-different layer table. The `alexnet` pyramid (11x11 / 5x5 convolutions) is not implemented."""
+different layer table, and the `alexnet` pyramid runs its first convolution as an im2col GEMM."""
 from typing import Any, Mapping, Optional, Tuple
 
 import torch
@@ -119,7 +119,7 @@ class PyramidConvEncoder(_EngineEncoder):
     """`src/milan/encoders.py:243-351`: masked spatial pooling of conv1 + layer1..4 -> one vector per image."""
 
     KIND = KIND_PYRAMID
-    NATIVE = ('resnet18', 'resnet50', 'resnet101')
+    NATIVE = ('alexnet', 'resnet18', 'resnet50', 'resnet101')
 
     def __init__(self, config: str = 'resnet50', **kwargs: Any):
         super().__init__(config, **kwargs)

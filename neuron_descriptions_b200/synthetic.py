@@ -79,6 +79,18 @@ def synthetic_resnet_state(arch: str = 'resnet101', seed: int = 0) -> Dict[str, 
     return sd
 
 
+def synthetic_alexnet_state(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """torchvision-alexnet-shaped `features` weights (convs with biases, no BN); the classifier is omitted
+    (the reference loads with strict=False and the pyramid encoder never reads it)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for name, cout, cin, k in (('features.0', 64, 3, 11), ('features.3', 192, 64, 5), ('features.6', 384, 192, 3),
+                               ('features.8', 256, 384, 3), ('features.10', 256, 256, 3)):
+        sd[name + '.weight'] = torch.randn(cout, cin, k, k, generator=gen) * math.sqrt(2.0 / (k * k * cin))
+        sd[name + '.bias'] = torch.randn(cout, generator=gen) * 0.1
+    return sd
+
+
 def synthetic_resnet101_state(seed: int = 0) -> Dict[str, torch.Tensor]:
     return synthetic_resnet_state('resnet101', seed)
 
@@ -86,7 +98,8 @@ def synthetic_resnet101_state(seed: int = 0) -> Dict[str, torch.Tensor]:
 def synthetic_encoder_state_dict(arch: str = 'resnet101', seed: int = 0) -> Dict[str, torch.Tensor]:
     """`state_dict()` of a reference encoder module: `mean`, `std`, `encoder.model.*`."""
     sd = {'mean': torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1), 'std': torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)}
-    for key, value in synthetic_resnet_state(arch, seed).items():
+    backbone = synthetic_alexnet_state(seed) if arch == 'alexnet' else synthetic_resnet_state(arch, seed)
+    for key, value in backbone.items():
         sd['encoder.model.' + key] = value
     return sd
 

@@ -84,7 +84,7 @@ def make_score_golden(milan, lang, vocab):
     print('score golden:', scores.tolist(), scores_mi.tolist())
 
 
-ENCODER_VARIANTS = (('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18'))
+ENCODER_VARIANTS = (('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18'), ('pyramid', 'alexnet'))
 
 
 def encoder_variant_inputs():
@@ -107,7 +107,7 @@ def make_encoder_variant_goldens(milan):
         cls = milan.encoders.SpatialConvEncoder if kind == 'spatial' else milan.encoders.PyramidConvEncoder
         encoder = cls(arch, pretrained=False)
         missing, unexpected = encoder.load_state_dict(synthetic.synthetic_encoder_state_dict(arch, seed=3), strict=False)
-        assert not missing and not unexpected, (missing, unexpected)
+        assert not unexpected and all('classifier' in key for key in missing), (missing, unexpected)
         encoder.eval()
         with torch.no_grad():
             features = encoder(images, masks)

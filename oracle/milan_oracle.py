@@ -83,6 +83,27 @@ def resnet101_retained(images: torch.Tensor, sd: State, prefix: str = 'encoder.e
     return resnet_retained(images, sd, prefix, 'resnet101')
 
 
+def alexnet_retained(images: torch.Tensor, sd: State, prefix: str = 'encoder.encoder.model.') -> List[torch.Tensor]:
+    """Outputs of torchvision alexnet `features.{0,3,6,8,10}` as nethook retains them (`encoders.py:328-334`).
+
+    nethook stores `output.detach()` (`nethook.py:226-235`), which shares storage with the conv output, and every
+    following `nn.ReLU(inplace=True)` of torchvision's alexnet then rectifies that storage: the retained maps are
+    the POST-ReLU activations (verified against the reference in `oracle/make_golden.py`).
+    """
+    sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    retained = []
+    x = F.relu(F.conv2d(images, sub['features.0.weight'], sub['features.0.bias'], stride=4, padding=2))
+    retained.append(x)
+    x = F.max_pool2d(x, kernel_size=3, stride=2)
+    x = F.relu(F.conv2d(x, sub['features.3.weight'], sub['features.3.bias'], padding=2))
+    retained.append(x)
+    x = F.max_pool2d(x, kernel_size=3, stride=2)
+    for name in ('features.6', 'features.8', 'features.10'):
+        x = F.relu(F.conv2d(x, sub[name + '.weight'], sub[name + '.bias'], padding=1))
+        retained.append(x)
+    return retained
+
+
 def masked_pool(features: Sequence[torch.Tensor], masks: torch.Tensor) -> torch.Tensor:
     """`src/milan/encoders.py:301-320`: bilinear mask downsample, per-image sum-normalise, weighted pool."""
     masked = []
@@ -102,7 +123,8 @@ def pyramid_encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: Stat
     if masks is None:
         masks = images.new_ones((len(images), 1, *images.shape[2:]))
     images = (images - sd['encoder.mean']) / sd['encoder.std']
-    return masked_pool(resnet_retained(images, sd, arch=arch), masks.clone())
+    retained = alexnet_retained(images, sd) if arch == 'alexnet' else resnet_retained(images, sd, arch=arch)
+    return masked_pool(retained, masks.clone())
 
 
 def spatial_encode(images: torch.Tensor, masks: Optional[torch.Tensor], sd: State,

@@ -46,7 +46,7 @@ def test_pyramid_conv_encoder_init_bad_config():
         encoders.SpatialConvEncoder(config=bad)
 
 
-@pytest.mark.parametrize('config', ('resnet18', 'resnet50'))
+@pytest.mark.parametrize('config', ('resnet18', 'alexnet', 'resnet50'))
 def test_pyramid_conv_encoder_forward(config, images, masks):
     encoder = _encoder('pyramid', config)
     actual = encoder(images, masks)
@@ -54,7 +54,7 @@ def test_pyramid_conv_encoder_forward(config, images, masks):
     assert not torch.isnan(actual).any()
 
 
-@pytest.mark.parametrize('config', ('resnet18', 'resnet50'))
+@pytest.mark.parametrize('config', ('resnet18', 'alexnet', 'resnet50'))
 def test_pyramid_conv_encoder_forward_invalid_mask(config, images, masks):
     encoder = _encoder('pyramid', config)
     masks[-2:] = 0
@@ -65,7 +65,7 @@ def test_pyramid_conv_encoder_forward_invalid_mask(config, images, masks):
     assert not torch.isnan(actual).any()
 
 
-@pytest.mark.parametrize('config', ('resnet18',))
+@pytest.mark.parametrize('config', ('resnet18', 'alexnet'))
 def test_pyramid_conv_encoder_forward_all_invalid_masks(config, images, masks):
     encoder = _encoder('pyramid', config)
     actual = encoder(images, torch.zeros_like(masks))
@@ -73,7 +73,8 @@ def test_pyramid_conv_encoder_forward_all_invalid_masks(config, images, masks):
     assert actual.eq(0).all()
 
 
-@pytest.mark.parametrize('kind,config', [('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18')])
+@pytest.mark.parametrize('kind,config', [('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18'),
+                                       ('pyramid', 'alexnet')])
 def test_encoder_variants_match_reference_golden(golden_dir, kind, config):
     g = np.load(os.path.join(golden_dir, 'encoder_variants.npz'))
     images_u8, masks_u8 = encoder_variant_inputs()

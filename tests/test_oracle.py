@@ -37,7 +37,8 @@ def test_encoder_matches_reference_golden(golden_dir):
     assert feats[0, 1].abs().max().item() > 0.0
 
 
-@pytest.mark.parametrize('kind,arch', [('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18')])
+@pytest.mark.parametrize('kind,arch', [('pyramid', 'resnet18'), ('pyramid', 'resnet50'), ('spatial', 'resnet18'),
+                                       ('pyramid', 'alexnet')])
 def test_encoder_variants_match_reference_golden(golden_dir, kind, arch):
     """The secondary encoder configs (`src/milan/encoders.py:214-216,326-351`) of the oracle vs the reference."""
     from oracle.make_golden import encoder_variant_inputs
