@@ -174,7 +174,14 @@ struct MilanEngine {
   std::map<std::pair<int, long long>, Plan> gemm_plans;  // (which, M)
   int host_T = 0;
   // ---- host staging for milan_describe_host
-  uint8_t *d_img_stage = nullptr, *d_mask_stage = nullptr;
+  // two staging sets: the exemplars of chunk i+1 are copied (copy_stream) while chunk i is encoded / decoded
+  uint8_t *d_img_stage[2] = {nullptr, nullptr}, *d_mask_stage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  long long* d_tokens_all = nullptr;  // describe_host results of every chunk (one D2H at the end)
+  float* d_scores_all = nullptr;
+  int* d_steps_all = nullptr;
+  size_t results_cap = 0;
   // ---- profiling
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
@@ -571,8 +578,10 @@ int MilanEngine::alloc_workspace() {
     if (dalloc2(axPool[1], n * 13 * 13 * 192)) return 1;
     if (dalloc(&mask_wts, n * kAlexMaskStride)) return 1;
     if (dalloc(&feat_enc, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
-    if (dalloc(&d_img_stage, n * 3 * 224 * 224)) return 1;
-    if (dalloc(&d_mask_stage, n * 224 * 224)) return 1;
+    for (int b = 0; b < 2; ++b) {
+      if (dalloc(&d_img_stage[b], n * 3 * 224 * 224)) return 1;
+      if (dalloc(&d_mask_stage[b], n * 224 * 224)) return 1;
+    }
   } else if (cfg.has_encoder) {
     const size_t n = cfg.max_images;
     if (dalloc2(stemA, n * kStemPadH * kStemPadW * 4)) return 1;
@@ -586,8 +595,10 @@ int MilanEngine::alloc_workspace() {
     if (dalloc2(bufDS, n * stage)) return 1;
     if (dalloc(&mask_wts, n * kMaskPyramidSize)) return 1;
     if (dalloc(&feat_enc, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
-    if (dalloc(&d_img_stage, n * 3 * 224 * 224)) return 1;
-    if (dalloc(&d_mask_stage, n * 224 * 224)) return 1;
+    for (int b = 0; b < 2; ++b) {
+      if (dalloc(&d_img_stage[b], n * 3 * 224 * 224)) return 1;
+      if (dalloc(&d_mask_stage[b], n * 224 * 224)) return 1;
+    }
   }
   if (!has_decoder) return 0;
   Bmax = cfg.max_neurons;
@@ -1128,6 +1139,13 @@ void milan_engine_destroy(MilanEngine* engine) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
   }
+  if (engine->copy_stream != nullptr) {
+    cudaStreamDestroy(engine->copy_stream);
+    for (int b = 0; b < 2; ++b) {
+      cudaEventDestroy(engine->ev_copied[b]);
+      cudaEventDestroy(engine->ev_consumed[b]);
+    }
+  }
   delete engine;
 }
 
@@ -1292,7 +1310,6 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
   const int n_keys = k * (e->spatial ? kSpatialKeys : 1);  // Decoder.encode: view(batch, -1, feature_size)
   if (n_keys > e->cfg.max_keys) return fail("k=%d (%d keys) exceeds max_keys %d", k, n_keys, e->cfg.max_keys);
   if (group_size <= 0) group_size = 16;
-  const int F = e->cfg.feature_size;
   // neurons per chunk: bounded by encoder image capacity and decoder capacity; whole reference groups only
   int chunk = std::min(e->cfg.max_images / k, e->cfg.max_neurons);
   if (chunk >= group_size) chunk = chunk / group_size * group_size;
@@ -1300,46 +1317,83 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
   if (strategy != 0 && chunk % group_size != 0 && chunk < n_neurons)
     return fail("engine capacity (%d neurons/chunk) smaller than group_size %d", chunk, group_size);
   const size_t img_bytes = static_cast<size_t>(k) * 3 * 224 * 224, msk_bytes = static_cast<size_t>(k) * 224 * 224;
-  long long* d_tok = e->out_tokens;
-  std::vector<int> steps(e->Bmax + 1);
+  if (n_neurons <= 0) return 0;
+  // ---- lazily created pipeline resources
+  if (e->copy_stream == nullptr) {
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CU(cudaEventCreateWithFlags(&e->ev_copied[b], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ev_consumed[b], cudaEventDisableTiming));
+    }
+  }
+  if (static_cast<size_t>(n_neurons) > e->results_cap) {
+    const size_t cap = static_cast<size_t>(n_neurons);
+    if (e->dalloc(&e->d_tokens_all, cap * e->cfg.max_length)) return 1;
+    if (e->dalloc(&e->d_scores_all, cap)) return 1;
+    if (e->dalloc(&e->d_steps_all, cap)) return 1;
+    e->results_cap = cap;
+  }
+  const int n_chunks = (n_neurons + chunk - 1) / chunk;
+  const int groups_per_chunk = (chunk + group_size - 1) / group_size;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   if (e->profiling) for (auto& x : ev) CU(cudaEventCreate(&x));
-  for (int done = 0; done < n_neurons; done += chunk) {
+  // Exemplars of chunk c -> staging set c % 2 on the copy stream, once the encoder has consumed what the set held
+  // (chunk c - 2). The host buffers are read asynchronously only if they are pinned; pageable memory still works.
+  auto issue_copy = [&](int c) -> int {
+    const int b = c & 1;
+    const int done = c * chunk;
     const int nb = std::min(chunk, n_neurons - done);
-    CU(cudaMemcpyAsync(e->d_img_stage, h_images + done * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_mask_stage, h_masks + done * msk_bytes, nb * msk_bytes, cudaMemcpyHostToDevice, st));
+    if (c >= 2) CU(cudaStreamWaitEvent(e->copy_stream, e->ev_consumed[b], 0));
+    CU(cudaMemcpyAsync(e->d_img_stage[b], h_images + done * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice,
+                       e->copy_stream));
+    CU(cudaMemcpyAsync(e->d_mask_stage[b], h_masks + done * msk_bytes, nb * msk_bytes, cudaMemcpyHostToDevice,
+                       e->copy_stream));
+    CU(cudaEventRecord(e->ev_copied[b], e->copy_stream));
+    return 0;
+  };
+  if (issue_copy(0)) return 1;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b = c & 1;
+    const int done = c * chunk;
+    const int nb = std::min(chunk, n_neurons - done);
+    if (c + 1 < n_chunks && issue_copy(c + 1)) return 1;
+    CU(cudaStreamWaitEvent(st, e->ev_copied[b], 0));
     if (e->profiling) CU(cudaEventRecord(ev[0], st));
-    if (e->encode(e->d_img_stage, e->d_mask_stage, nb * k, MILAN_DTYPE_U8, e->feat_enc, st)) return 1;
+    if (e->encode(e->d_img_stage[b], e->d_mask_stage[b], nb * k, MILAN_DTYPE_U8, e->feat_enc, st)) return 1;
+    CU(cudaEventRecord(e->ev_consumed[b], st));
     if (e->profiling) CU(cudaEventRecord(ev[1], st));
-    const int groups = (nb + group_size - 1) / group_size;
+    long long* d_tok = e->d_tokens_all + static_cast<size_t>(done) * length;
+    float* d_sc = e->d_scores_all + done;
     if (strategy == 0) {
-      if (e->decode_greedy(e->feat_enc, nb, n_keys, length, mi, temperature, nullptr, d_tok, e->out_scores, nullptr, nullptr, st))
+      if (e->decode_greedy(e->feat_enc, nb, n_keys, length, mi, temperature, nullptr, d_tok, d_sc, nullptr, nullptr, st))
         return 1;
     } else {
-      if (e->decode_beam(e->feat_enc, nb, n_keys, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0, temperature,
-                         nullptr, nullptr,
-                         nullptr, d_tok, e->out_scores, nullptr, st))
+      if (e->decode_beam(e->feat_enc, nb, n_keys, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0,
+                         temperature, nullptr, nullptr, e->d_steps_all + c * groups_per_chunk, d_tok, d_sc, nullptr, st))
         return 1;
     }
-    if (e->profiling) CU(cudaEventRecord(ev[2], st));
-    CU(cudaMemcpyAsync(h_tokens_out + static_cast<size_t>(done) * length, d_tok, sizeof(long long) * nb * length,
-                       cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_scores_out + done, e->out_scores, sizeof(float) * nb,
-                       cudaMemcpyDeviceToHost, st));
-    if (strategy != 0) CU(cudaMemcpyAsync(steps.data(), e->group_T, sizeof(int) * groups, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < nb; ++i) h_steps_out[done + i] = strategy == 0 ? length : steps[i / group_size];
     if (e->profiling) {
-      float a = 0, b = 0;
+      CU(cudaEventRecord(ev[2], st));
+      CU(cudaStreamSynchronize(st));
+      float a = 0, bms = 0;
       CU(cudaEventElapsedTime(&a, ev[0], ev[1]));
-      CU(cudaEventElapsedTime(&b, ev[1], ev[2]));
+      CU(cudaEventElapsedTime(&bms, ev[1], ev[2]));
       e->prof_enc_ms += a;
-      e->prof_dec_ms += b;
+      e->prof_dec_ms += bms;
       if (e->collect_conv_events(st)) return 1;
     }
   }
+  // ---- one device->host read of everything, then a single synchronisation
+  std::vector<int> steps(static_cast<size_t>(n_chunks) * groups_per_chunk, length);
+  CU(cudaMemcpyAsync(h_tokens_out, e->d_tokens_all, sizeof(long long) * static_cast<size_t>(n_neurons) * length,
+                     cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_scores_out, e->d_scores_all, sizeof(float) * n_neurons, cudaMemcpyDeviceToHost, st));
+  if (strategy != 0)
+    CU(cudaMemcpyAsync(steps.data(), e->d_steps_all, sizeof(int) * steps.size(), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < n_neurons; ++i)
+    h_steps_out[i] = strategy == 0 ? length : steps[(i / chunk) * groups_per_chunk + (i % chunk) / group_size];
   if (e->profiling) for (auto& x : ev) cudaEventDestroy(x);
-  (void)F;
   return 0;
 }
 

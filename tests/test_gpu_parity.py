@@ -254,6 +254,27 @@ def test_describe_host_end_to_end(full_engine, full_sd):
                   'describe/greedy')
 
 
+def test_describe_host_pipelined_chunks(full_sd):
+    """Several chunks through the double-buffered copy/compute pipeline of milan_describe_host give exactly the
+    results of the same chunks described one call at a time (ragged last chunk, pinned and pageable inputs)."""
+    engine = _engine(full_sd, max_neurons=4, max_beam=8, max_keys=3)
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(11, 3, seed=21)  # chunks of 4, 4, 3 neurons
+    kwargs = dict(strategy='rerank', beam=8, group_size=2)
+    tokens, scores, steps = engine.describe_host(images_u8.pin_memory(), masks_u8.pin_memory(), **kwargs)
+    tokens_p, scores_p, steps_p = engine.describe_host(images_u8, masks_u8, **kwargs)  # pageable host memory
+    assert torch.equal(tokens, tokens_p) and torch.equal(scores, scores_p) and torch.equal(steps, steps_p)
+    for lo in range(0, 11, 4):
+        t, s, st = engine.describe_host(images_u8[lo:lo + 4].contiguous(), masks_u8[lo:lo + 4].contiguous(), **kwargs)
+        assert torch.equal(tokens[lo:lo + 4], t) and torch.equal(scores[lo:lo + 4], s) and torch.equal(steps[lo:lo + 4], st)
+    tokens_g, scores_g, steps_g = engine.describe_host(images_u8, masks_u8, strategy='greedy', mi=False)
+    feats = engine.encode(images_u8.view(-1, 3, 224, 224), masks_u8.view(-1, 1, 224, 224)).view(11, 3, -1)
+    for lo in range(0, 11, 4):
+        t, s, _, _ = engine.decode_greedy(feats[lo:lo + 4], 15, False, 0.2)
+        assert torch.equal(tokens_g[lo:lo + 4], t.cpu()) and torch.equal(scores_g[lo:lo + 4], s.cpu())
+    assert (steps_g == 15).all()
+    engine.close()
+
+
 def test_facade_matches_reference_surface(full_sd):
     """Decoder facade: predict() on a dataset of TopImages-like samples, forward kwargs and error behaviour."""
     from neuron_descriptions_b200 import milan
