@@ -221,22 +221,22 @@ __global__ void __launch_bounds__(256) masked_pool_kernel(const __nv_bfloat16* _
 }
 
 // y[n][oh][ow][c] = max_{3x3, stride 2, pad 1} relu(alpha[c] * x + beta[c]);  C = 64, thread = 8 channels
-// (one 16-byte load per plane and window tap; 8 threads cover a pixel's 128-byte channel row).
+// (one 16-byte load per plane and window tap; 8 threads cover a pixel's 128-byte channel row). A CTA owns a
+// 4 x 8 tile of output pixels so the input rows / columns shared by neighbouring windows are re-read from L1
+// (9 x 17 input pixels per 32 outputs instead of 9 per output through L2).
 __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ x_hi,
                                                               const __nv_bfloat16* __restrict__ x_lo,
                                                               const float* __restrict__ alpha,
                                                               const float* __restrict__ beta, int n_images,
                                                               __nv_bfloat16* __restrict__ y_hi,
                                                               __nv_bfloat16* __restrict__ y_lo) {
-  constexpr int C = 64, IN = 112, OUT = 56, G = C / 8;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n_images) * OUT * OUT * G;
-  if (idx >= total) return;
-  const int cg = idx % G;
-  const long long pix = idx / G;
-  const int ow = pix % OUT;
-  const int oh = (pix / OUT) % OUT;
-  const int n = pix / (OUT * OUT);
+  constexpr int C = 64, IN = 112, OUT = 56, TW = 8, TH = 4, TX = OUT / TW, TY = OUT / TH;
+  const int cg = threadIdx.x & 7;
+  const int ow = (blockIdx.x % TX) * TW + ((threadIdx.x >> 3) & 7);
+  const int oh = ((blockIdx.x / TX) % TY) * TH + (threadIdx.x >> 6);
+  const int n = blockIdx.x / (TX * TY);
+  if (n >= n_images) return;
+  const long long pix = (static_cast<long long>(n) * OUT + oh) * OUT + ow;
   float a[8], b[8], m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -490,9 +490,8 @@ int launch_masked_pool(const __nv_bfloat16* hi, const __nv_bfloat16* lo, const f
 int launch_bn_relu_maxpool(const __nv_bfloat16* x_hi, const __nv_bfloat16* x_lo, const float* alpha,
                            const float* beta, int n_images, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
                            cudaStream_t stream) {
-  const long long total = static_cast<long long>(n_images) * 56 * 56 * 8;
-  const int threads = 256;
-  const long long blocks = (total + threads - 1) / threads;
+  const int threads = 256;  // one CTA = 4 x 8 output pixels x 8 channel groups
+  const long long blocks = static_cast<long long>(n_images) * (56 / 8) * (56 / 4);
   bn_relu_maxpool_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x_hi, x_lo, alpha, beta, n_images,
                                                                                y_hi, y_lo);
   note_launch();
