@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int cin_blocks = p.cin / BK;
-  const int num_kb = p.num_taps * cin_blocks;
+  int num_kb = 0;
+  for (int t = 0; t < p.num_taps; ++t) num_kb += p.tap_cb[t] > 0 ? p.tap_cb[t] : cin_blocks;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
   const int kb_per_chunk = (p.kb_per_chunk > 0 && p.kb_per_chunk < num_kb) ? p.kb_per_chunk : num_kb;
@@ -128,11 +129,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.box_w, h0 = th * p.box_h, n0 = tn * p.box_n;
+        int kcoord = 0;  // running K coordinate into the weight matrix
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int plane = p.tap_plane[tap];
           const int cw = w0 + p.tap_dw[tap];
           const int ch = h0 + p.tap_dh[tap];
-          for (int cb = 0; cb < cin_blocks; ++cb) {
+          const int tap_blocks = p.tap_cb[tap] > 0 ? p.tap_cb[tap] : cin_blocks;
+          for (int cb = 0; cb < tap_blocks; ++cb, kcoord += BK) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * L::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
@@ -146,7 +149,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
             }
             uint8_t* sb = st + L::kPlanes * kABytes;
-            const int kcoord = (tap * cin_blocks + cb) * BK;
             tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
             if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
             if (++stage == kStages) { stage = 0; phase ^= 1; }

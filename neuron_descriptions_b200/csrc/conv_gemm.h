@@ -49,6 +49,7 @@ struct alignas(64) ConvGemmParams {
   int cin;                   // channels per tap (multiple of 64)
   int num_taps;
   int8_t tap_plane[kMaxTaps], tap_dw[kMaxTaps], tap_dh[kMaxTaps];
+  int16_t tap_cb[kMaxTaps];  // k-blocks of tap t (0 = cin / block_k): taps may read tensors of different depth
   uint32_t a_box_bytes;      // bytes one A box delivers
   const float* bias;         // [cout] or nullptr
   const __nv_bfloat16* res_hi;
@@ -118,6 +119,22 @@ struct ConvIO {
 // Fills `p` (tensor maps, tiling, taps) for the convolution; returns 0 on success. *block_n receives the
 // N-tile width the kernel must be launched with.
 int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, int split, int* block_n);
+
+// Two 1x1 convolutions summed in ONE accumulator: out = W_a * a + W_b * b(strided) + bias (+ReLU). This is the tail
+// of the first bottleneck of a ResNet stage, relu(bn3(conv3(t)) + bn_ds(downsample(x))) (torchvision Bottleneck,
+// called at src/milan/encoders.py:298): the downsample branch never round-trips HBM as a separate tensor.
+// `a` is [N][Ho][Wo][Ca] (the 3x3 conv's output), `b` is [N][Ho*stride][Wo*stride][Cb] sampled at (stride*h,
+// stride*w); w is [Cout][Ca + Cb] (both filters BN-folded, concatenated along K), bias the sum of both shifts.
+struct DualConvIO {
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;
+  const __nv_bfloat16* b_hi; const __nv_bfloat16* b_lo;
+  const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;
+  const float* bias;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int relu;
+};
+int build_dual_1x1_params(ConvGemmParams* p, int N, int Ho, int Wo, int Ca, int Cb, int Cout, int stride,
+                          const DualConvIO& io, int split, int* block_n);
 
 // The 7x7 stride-2 stem as an implicit GEMM without im2col: the input is the zero-padded NHWC4 image
 // [N][232][232][4] (pixel (ih, iw) at (ih + 3, iw + 4); channel 3 = 0) and the k-block of filter row r is the

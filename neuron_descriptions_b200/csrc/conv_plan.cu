@@ -141,6 +141,78 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
   return 0;
 }
 
+int build_dual_1x1_params(ConvGemmParams* p, int N, int Ho, int Wo, int Ca, int Cb, int Cout, int stride,
+                          const DualConvIO& io, int split, int* block_n) {
+  memset(p, 0, sizeof(*p));
+  if (Ca % kGemmBlockK != 0 || Cb % kGemmBlockK != 0) return -2;
+  if (!(stride == 1 || stride == 2)) return -3;
+  const int bn_tile = (Cout <= 64) ? 64 : 128;
+  *block_n = bn_tile;
+  const uint64_t esz = 2;
+  const int np = split ? 2 : 1;
+  const __nv_bfloat16* a_planes[2] = {io.a_hi, io.a_lo};
+  const __nv_bfloat16* b_planes[2] = {io.b_hi, io.b_lo};
+  const __nv_bfloat16* w_planes[2] = {io.w_hi, io.w_lo};
+  const __nv_bfloat16* outs[2] = {io.out_hi, io.out_lo};
+  p->cin = Ca;  // default depth; tap 1 overrides it through tap_cb
+  p->cout = Cout;
+  p->n_tiles = (Cout + bn_tile - 1) / bn_tile;
+  p->bias = io.bias;
+  p->out_hi = io.out_hi;
+  p->out_lo = io.out_lo;
+  p->ldc = Cout;
+  p->relu = io.relu;
+  p->num_taps = 2;
+  p->tap_plane[0] = 0; p->tap_plane[1] = 1;
+  p->tap_cb[0] = static_cast<int16_t>(Ca / kGemmBlockK);
+  p->tap_cb[1] = static_cast<int16_t>(Cb / kGemmBlockK);
+  p->kb_per_chunk = split ? kEncoderKbPerChunk : 0;
+  int rc = 0;
+  if (stride == 1) {  // both operands are flat [M][C] matrices
+    const uint64_t M = static_cast<uint64_t>(N) * Ho * Wo;
+    p->box_w = kGemmBlockM; p->box_h = 1; p->box_n = 1;
+    p->tiles_w = static_cast<int>((M + kGemmBlockM - 1) / kGemmBlockM);
+    p->tiles_h = 1; p->tiles_n = 1;
+    p->out_w = static_cast<int>(M); p->out_h = 1; p->out_n = 1;
+    for (int hl = 0; hl < np; ++hl) {
+      const uint64_t pa = static_cast<uint64_t>(Ca) * esz, pb = static_cast<uint64_t>(Cb) * esz, po = static_cast<uint64_t>(Cout) * esz;
+      if ((rc = make_tmap_4d(&p->tmap_a[hl][0], a_planes[hl], Ca, M, 1, 1, pa, pa * M, pa * M, kGemmBlockM, 1, 1))) return rc;
+      if ((rc = make_tmap_4d(&p->tmap_a[hl][1], b_planes[hl], Cb, M, 1, 1, pb, pb * M, pb * M, kGemmBlockM, 1, 1))) return rc;
+      if ((rc = make_tmap_4d(&p->tmap_out[hl], outs[hl], Cout, M, 1, 1, po, po * M, po * M, kGemmBlockM, 1, 1))) return rc;
+    }
+  } else {  // 4-D boxes over the output raster; b is read through its (even row, even column) parity plane
+    int bw, bh, bn;
+    choose_box(Wo, Ho, N, &bw, &bh, &bn);
+    p->box_w = bw; p->box_h = bh; p->box_n = bn;
+    p->tiles_w = (Wo + bw - 1) / bw;
+    p->tiles_h = (Ho + bh - 1) / bh;
+    p->tiles_n = (N + bn - 1) / bn;
+    p->out_w = Wo; p->out_h = Ho; p->out_n = N;
+    const int Hi = Ho * 2, Wi = Wo * 2;
+    for (int hl = 0; hl < np; ++hl) {
+      const uint64_t pa = static_cast<uint64_t>(Ca) * esz, pb = static_cast<uint64_t>(Cb) * esz, po = static_cast<uint64_t>(Cout) * esz;
+      if ((rc = make_tmap_4d(&p->tmap_a[hl][0], a_planes[hl], Ca, Wo, Ho, N, pa, pa * Wo, pa * Wo * Ho, bw, bh, bn))) return rc;
+      if ((rc = make_tmap_4d(&p->tmap_a[hl][1], b_planes[hl], Cb, Wo, Ho, N, 2 * pb, 2 * pb * Wi, pb * Wi * Hi, bw, bh, bn))) return rc;
+      if ((rc = make_tmap_4d(&p->tmap_out[hl], outs[hl], Cout, Wo, Ho, N, po, po * Wo, po * Wo * Ho, bw, bh, bn))) return rc;
+    }
+  }
+  for (int hl = 0; hl < np; ++hl) {
+    p->tmap_a[hl][2] = p->tmap_a[hl][0];
+    p->tmap_a[hl][3] = p->tmap_a[hl][0];
+    const uint64_t ktot = static_cast<uint64_t>(Ca) + Cb;
+    if ((rc = make_tmap_2d(&p->tmap_b[hl], w_planes[hl], ktot, Cout, ktot * esz, bn_tile))) return rc;
+  }
+  p->a_box_bytes = static_cast<uint32_t>(p->box_w) * p->box_h * p->box_n * kGemmBlockK * 2;
+  if (!split) {
+    p->tmap_b[1] = p->tmap_b[0];
+    p->tmap_out[1] = p->tmap_out[0];
+    for (int pl = 0; pl < 4; ++pl) p->tmap_a[1][pl] = p->tmap_a[0][pl];
+  }
+  p->tmap_res[0] = p->tmap_out[0];
+  p->tmap_res[1] = p->tmap_out[1];
+  return 0;
+}
+
 void pack_stem_weights(const float* w, float* packed) {
   // k = r*32 + sp*4 + c  <-  w[co][c][r][s = sp - 1]; zero for sp = 0 and c = 3.
   for (int co = 0; co < 64; ++co) {

@@ -78,6 +78,7 @@ struct SplitMat {  // K-major [rows][cols] bf16 planes on the device
 struct ConvLayer {
   std::string name;
   int cin, cout, ksize, stride;
+  int dual_cb = 0;  // > 0: conv3 + downsample fused (build_dual_1x1_params); cin = planes, dual_cb = block input depth
   SplitMat w;
   float* bias = nullptr;  // folded BN shift, padded to 128
 };
@@ -140,6 +141,7 @@ struct MilanEngine {
   bool spatial = false;          // SpatialConvEncoder: mask the image, emit the layer4 map
   bool has_decoder = true;       // false: encoder-only engine (no decoder tensors were provided)
   bool alexnet = false;
+  bool fuse_downsample = true;   // MILAN_FUSE_DOWNSAMPLE=0 keeps conv3 and downsample as separate kernels (A/B runs)
   __nv_bfloat16 *axA0[2] = {}, *axAct[5][2] = {}, *axPool[2][2] = {};  // alexnet: im2col, conv outputs, max-pools
   int enc_out_per_image = 0;     // floats milan_encode writes per image
   std::vector<ConvLayer> convs;  // convs after the stem, execution order (103 for resnet101)
@@ -343,6 +345,38 @@ int MilanEngine::finalize_encoder() {
     convs.push_back(L);
     return 0;
   };
+  // First bottleneck of every stage: relu(bn3(conv3(t)) + bn_ds(downsample(x))) as ONE GEMM over K = planes + inplanes
+  // ([W3*s3 | Wds*sds], bias = shift3 + shift_ds): the downsample output never exists as a tensor.
+  auto add_dual = [&](const std::string& blk, int planes, int inplanes, int stride) -> int {
+    const int cout = planes * 4;
+    const HostTensor* w3 = get(pre + blk + ".conv3.weight");
+    const HostTensor* wd = get(pre + blk + ".downsample.0.weight");
+    if (w3 == nullptr || w3->numel() != static_cast<int64_t>(cout) * planes)
+      return fail("missing/invalid %s%s.conv3.weight", pre.c_str(), blk.c_str());
+    if (wd == nullptr || wd->numel() != static_cast<int64_t>(cout) * inplanes)
+      return fail("missing/invalid %s%s.downsample.0.weight", pre.c_str(), blk.c_str());
+    std::vector<double> s3, h3, sd_, hd;
+    if (bn_fold(pre + blk + ".bn3", cout, &s3, &h3)) return 1;
+    if (bn_fold(pre + blk + ".downsample.1", cout, &sd_, &hd)) return 1;
+    const int K = planes + inplanes;
+    std::vector<float> packed(static_cast<size_t>(cout) * K);
+    std::vector<float> bias(cout);
+    for (int co = 0; co < cout; ++co) {
+      for (int ci = 0; ci < planes; ++ci)
+        packed[static_cast<size_t>(co) * K + ci] = static_cast<float>(w3->data[static_cast<size_t>(co) * planes + ci] * s3[co]);
+      for (int ci = 0; ci < inplanes; ++ci)
+        packed[static_cast<size_t>(co) * K + planes + ci] =
+            static_cast<float>(wd->data[static_cast<size_t>(co) * inplanes + ci] * sd_[co]);
+      bias[co] = static_cast<float>(h3[co] + hd[co]);
+    }
+    ConvLayer L;
+    L.name = blk + ".conv3+downsample";
+    L.cin = planes; L.cout = cout; L.ksize = 1; L.stride = stride; L.dual_cb = inplanes;
+    if (upload_split(&L.w, packed, cout, K)) return 1;
+    if (upload_f32(&L.bias, bias, (cout + 127) / 128 * 128)) return 1;
+    convs.push_back(L);
+    return 0;
+  };
   int inplanes = 64;
   for (int li = 0; li < 4; ++li) {
     for (int bi = 0; bi < arch.blocks[li]; ++bi) {
@@ -351,6 +385,13 @@ int MilanEngine::finalize_encoder() {
       char buf[64];
       snprintf(buf, sizeof buf, "layer%d.%d", li + 1, bi);
       const std::string b(buf);
+      if (arch.bottleneck && bi == 0 && fuse_downsample) {
+        if (add_conv(b + ".conv1", b + ".bn1", inplanes, planes, 1, 1)) return 1;
+        if (add_conv(b + ".conv2", b + ".bn2", planes, planes, 3, stride)) return 1;
+        if (add_dual(b, planes, inplanes, stride)) return 1;
+        inplanes = planes * expansion;
+        continue;
+      }
       if (arch.bottleneck) {
         if (add_conv(b + ".conv1", b + ".bn1", inplanes, planes, 1, 1)) return 1;
         if (add_conv(b + ".conv2", b + ".bn2", planes, planes, 3, stride)) return 1;
@@ -730,9 +771,26 @@ int MilanEngine::build_encoder_plans(int n, std::vector<Plan>** out) {
       const int main_convs = arch.bottleneck ? 3 : 2;
       const ConvLayer& strided = convs[ci + (arch.bottleneck ? 1 : 0)];
       const int res_out = res_in / strided.stride;
-      const bool has_ds = ci + main_convs < convs.size() && convs[ci + main_convs].name.find("downsample") != std::string::npos;
+      const bool dual = arch.bottleneck && convs[ci + 2].dual_cb > 0;
+      const bool has_ds = !dual && ci + main_convs < convs.size() &&
+                          convs[ci + main_convs].name.find("downsample") != std::string::npos;
       __nv_bfloat16** identity = x;
-      if (arch.bottleneck) {
+      if (dual) {
+        if (mk(convs[ci], res_in, x, bufT1, nullptr, 1)) return 1;
+        if (mk(convs[ci + 1], res_in, bufT1, bufT2, nullptr, 1)) return 1;
+        const ConvLayer& L = convs[ci + 2];
+        Plan pl;
+        DualConvIO io{};
+        io.a_hi = bufT2[0]; io.a_lo = bufT2[1];
+        io.b_hi = x[0]; io.b_lo = x[1];
+        io.w_hi = L.w.hi; io.w_lo = L.w.lo;
+        io.bias = L.bias;
+        io.out_hi = y[0]; io.out_lo = y[1];
+        io.relu = 1;
+        if (build_dual_1x1_params(&pl.p, n, res_out, res_out, L.cin, L.dual_cb, L.cout, L.stride, io, sp, &pl.block_n))
+          return fail("plan %s: %s", L.name.c_str(), tmap_last_error());
+        plans.push_back(pl);
+      } else if (arch.bottleneck) {
         if (mk(convs[ci], res_in, x, bufT1, nullptr, 1)) return 1;
         if (mk(convs[ci + 1], res_in, bufT1, bufT2, nullptr, 1)) return 1;
         if (has_ds) {
@@ -796,7 +854,8 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   int feat_off = 64;
   for (int li = 0; li < 4; ++li) {
     for (int bi = 0; bi < arch.blocks[li]; ++bi) {
-      const bool has_ds = (bi == 0) && (li > 0 || expansion != 1);
+      const bool dual = arch.bottleneck && bi == 0 && fuse_downsample;
+      const bool has_ds = !dual && (bi == 0) && (li > 0 || expansion != 1);
       const int nconv = (arch.bottleneck ? 3 : 2) + (has_ds ? 1 : 0);
       for (int j = 0; j < nconv; ++j)
         if (run_conv((*plans)[pi++], st)) return 1;
@@ -1125,6 +1184,7 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   eng->expansion = expansion;
   eng->spatial = spatial;
   eng->alexnet = alexnet;
+  if (const char* env = getenv("MILAN_FUSE_DOWNSAMPLE")) eng->fuse_downsample = atoi(env) != 0;
   eng->enc_out_per_image = (spatial ? kSpatialKeys : 1) * config->feature_size;
   *out = eng;
   return 0;

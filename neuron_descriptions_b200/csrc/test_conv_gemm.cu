@@ -281,6 +281,86 @@ static int run_stem(int N, int split, int num_sms) {
   return ok ? 0 : 1;
 }
 
+// out = relu(W_a a + W_b b(strided) + bias): the fused conv3 + downsample tail of a stage's first bottleneck.
+static int run_dual(const char* name, int N, int Ho, int Wo, int Ca, int Cb, int Cout, int stride, int num_sms) {
+  std::mt19937 rng(77 + Ca + Cb + stride);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  const int Hi = Ho * stride, Wi = Wo * stride;
+  const size_t a_elems = static_cast<size_t>(N) * Ho * Wo * Ca, b_elems = static_cast<size_t>(N) * Hi * Wi * Cb;
+  const size_t w_elems = static_cast<size_t>(Cout) * (Ca + Cb), out_elems = static_cast<size_t>(N) * Ho * Wo * Cout;
+  std::vector<float> a(a_elems), b(b_elems), w(w_elems), bias((Cout + 127) / 128 * 128, 0.f);
+  for (auto& v : a) v = nd(rng);
+  for (auto& v : b) v = nd(rng);
+  for (auto& v : w) v = nd(rng) / std::sqrt(static_cast<float>(Ca + Cb));
+  for (int i = 0; i < Cout; ++i) bias[i] = nd(rng) * 0.1f;
+  std::vector<uint16_t> ah, al, bh, bl, wh, wl;
+  split_vec(a, ah, al);
+  split_vec(b, bh, bl);
+  split_vec(w, wh, wl);
+  auto eff = [](const std::vector<uint16_t>& h, const std::vector<uint16_t>& l, size_t i) { return bf2f(h[i]) + bf2f(l[i]); };
+  uint16_t *dah = upload(ah), *dal = upload(al), *dbh = upload(bh), *dbl = upload(bl), *dwh = upload(wh), *dwl = upload(wl);
+  float* dbias = upload(bias);
+  uint16_t *doh, *dol;
+  CK(cudaMalloc(&doh, out_elems * 2 + 256));
+  CK(cudaMalloc(&dol, out_elems * 2 + 256));
+  CK(cudaMemset(doh, 0xFF, out_elems * 2));
+  CK(cudaMemset(dol, 0xFF, out_elems * 2));
+  DualConvIO io{};
+  io.a_hi = reinterpret_cast<__nv_bfloat16*>(dah); io.a_lo = reinterpret_cast<__nv_bfloat16*>(dal);
+  io.b_hi = reinterpret_cast<__nv_bfloat16*>(dbh); io.b_lo = reinterpret_cast<__nv_bfloat16*>(dbl);
+  io.w_hi = reinterpret_cast<__nv_bfloat16*>(dwh); io.w_lo = reinterpret_cast<__nv_bfloat16*>(dwl);
+  io.bias = dbias;
+  io.out_hi = reinterpret_cast<__nv_bfloat16*>(doh); io.out_lo = reinterpret_cast<__nv_bfloat16*>(dol);
+  io.relu = 1;
+  ConvGemmParams p;
+  int block_n = 0;
+  int rc = build_dual_1x1_params(&p, N, Ho, Wo, Ca, Cb, Cout, stride, io, 1, &block_n);
+  if (rc) { printf("[%s] build_dual_1x1_params failed rc=%d: %s\n", name, rc, tmap_last_error()); return 1; }
+  rc = launch_conv_gemm(p, block_n, 1, EPI_BF16, num_sms, 0);
+  if (rc) { printf("[%s] launch failed rc=%d\n", name, rc); return 1; }
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) { printf("[%s] kernel failed: %s\n", name, cudaGetErrorString(se)); return 1; }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < 5; ++i) launch_conv_gemm(p, block_n, 1, EPI_BF16, num_sms, 0);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= 5;
+  std::vector<uint16_t> oh(out_elems), ol(out_elems);
+  CK(cudaMemcpy(oh.data(), doh, out_elems * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ol.data(), dol, out_elems * 2, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0;
+  size_t checked = 0;
+  const size_t step = out_elems > 4000000 ? 97 : 1;
+  for (size_t idx = 0; idx < out_elems; idx += step) {
+    const int co = idx % Cout;
+    const size_t pix = idx / Cout;
+    const int ow = pix % Wo, oh_ = (pix / Wo) % Ho, n = pix / (static_cast<size_t>(Wo) * Ho);
+    double acc = bias[co];
+    for (int c = 0; c < Ca; ++c) acc += static_cast<double>(eff(ah, al, pix * Ca + c)) * eff(wh, wl, static_cast<size_t>(co) * (Ca + Cb) + c);
+    const size_t bpix = (static_cast<size_t>(n) * Hi + oh_ * stride) * Wi + ow * stride;
+    for (int c = 0; c < Cb; ++c) acc += static_cast<double>(eff(bh, bl, bpix * Cb + c)) * eff(wh, wl, static_cast<size_t>(co) * (Ca + Cb) + Ca + c);
+    acc = acc > 0 ? acc : 0;
+    const double got = static_cast<double>(bf2f(oh[idx])) + bf2f(ol[idx]);
+    const double err = std::fabs(got - acc);
+    if (!(err <= 1e30)) max_err = 1e30;
+    if (err > max_err) max_err = err;
+    if (std::fabs(acc) > max_ref) max_ref = std::fabs(acc);
+    ++checked;
+  }
+  const bool ok = max_err <= 2e-4 * (max_ref > 1 ? max_ref : 1);
+  printf("[%s] N=%d %dx%d Ca=%d Cb=%d Cout=%d s=%d box=(%d,%d,%d) : max_err=%.3e (max_ref=%.2f, checked=%zu) %.3f ms "
+         "%.1f TFLOP/s %s\n", name, N, Ho, Wo, Ca, Cb, Cout, stride, p.box_w, p.box_h, p.box_n, max_err, max_ref, checked,
+         ms, 2.0 * out_elems * (Ca + Cb) / ms * 1e-9, ok ? "OK" : "FAIL");
+  cudaFree(dah); cudaFree(dal); cudaFree(dbh); cudaFree(dbl); cudaFree(dwh); cudaFree(dwl); cudaFree(dbias);
+  cudaFree(doh); cudaFree(dol);
+  return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   CK(cudaSetDevice(dev));
@@ -327,6 +407,14 @@ int main(int argc, char** argv) {
     fflush(stdout);
   }
   if (only < 0 || only >= 100) {
+    fails += run_dual("dual_l1", 2, 56, 56, 64, 64, 256, 1, sms);
+    fails += run_dual("dual_l2", 3, 28, 28, 128, 256, 512, 2, sms);
+    fails += run_dual("dual_l3", 5, 14, 14, 256, 512, 1024, 2, sms);
+    fails += run_dual("dual_l4", 7, 7, 7, 512, 1024, 2048, 2, sms);
+    fails += run_dual("perf_dual_l4", 240, 7, 7, 512, 1024, 2048, 2, sms);
+    fails += run_dual("perf_dual_l1", 240, 56, 56, 64, 64, 256, 1, sms);
+    fails += run_dual("perf_dual_l2", 240, 28, 28, 128, 256, 512, 2, sms);
+    fails += run_dual("perf_dual_l3", 240, 14, 14, 256, 512, 1024, 2, sms);
     fails += run_stem(3, 1, sms);
     fails += run_stem(2, 0, sms);
     fails += run_stem(240, 1, sms);
