@@ -31,8 +31,9 @@ METRIC = 'neurons described/sec (k=15, beam=50)'
 UNIT = 'neurons/s'
 K_EXEMPLARS, BEAM, LENGTH, GROUP = 15, 50, 15, 16
 CONV_FLOP_PER_NEURON = 2.0 * 7.79935744e9 * K_EXEMPLARS  # 104 convs through layer4
-# every conv input / residual / output tensor touched once as (hi, lo) bf16 planes
-CONV_BYTES_PER_NEURON = 157.5e9 / 64
+# every conv input / residual / output tensor touched once as (hi, lo) bf16 planes; the four
+# downsample tensors are never materialised (conv3 + downsample run as one GEMM): 157.5 - 11.6 + 2.1 GB per 64 neurons
+CONV_BYTES_PER_NEURON = 148.0e9 / 64
 WORKLOAD = ('alexnet/imagenet 1k neurons, k=15, beam=50 + PMI rerank (synthetic exemplars of that shape, '
             'random-init MILAN resnet101 encoder + attention-LSTM decoder + LSTM LM, V=5004)')
 
@@ -299,7 +300,7 @@ def main():
         },
         'roofline': {
             'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-            'traffic': traffic, 'kernel': 'conv_gemm_kernel (104 encoder convolutions per step)',
+            'traffic': traffic, 'kernel': 'conv_gemm_kernel (the 104 encoder convolutions of a step, 100 launches)',
             'peak_kind': f'{peak_kind} bf16 sustained (kernel timed inside a long step)',
             'algorithmic_flop_per_launch': CONV_FLOP_PER_NEURON * nb * steps / conv_launches,
             'avg_launch_ms': conv_ms / conv_launches, 'conv_share_of_step': conv_ms / ms_res,
