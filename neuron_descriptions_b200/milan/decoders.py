@@ -385,6 +385,9 @@ class Decoder:
         if device is not None:
             self.to(device)
         engine = self.engine
+        fast = self._predict_host_pipeline(dataset, mask, batch_size, features, display_progress_as, kwargs)
+        if fast is not None:
+            return fast
         source = dataset if features is None else features
         total = len(source)
         chunk = max(batch_size, (engine.cfg.max_neurons // batch_size) * batch_size)
@@ -450,6 +453,79 @@ class Decoder:
             pool.shutdown(wait=True)
         self.last_predict_tokens = torch.cat(token_rows) if token_rows else torch.empty(0, length, dtype=torch.long)
         return tuple(captions)
+
+    def _predict_host_pipeline(self, dataset, mask, batch_size, features, display_progress_as, kwargs):
+        """`predict` for the common case — a uint8 exemplar dataset (`batch_u8`), masks on, a string strategy — as
+        slabs of several engine chunks through `milan_describe_host`, whose copy stream moves the exemplars of
+        chunk i+1 while chunk i is encoded / decoded; a worker thread fills the next pinned slab from the mmapped
+        files meanwhile. Returns None when the call needs the general path."""
+        allowed = {'strategy', 'temperature', 'beam_size', 'length', 'mi'}
+        if features is not None or not mask or not hasattr(dataset, 'batch_u8') or set(kwargs) - allowed:
+            return None
+        if getattr(dataset, 'transform_images', None) is not None or getattr(dataset, 'transform_masks', None) is not None:
+            return None
+        strategy = kwargs.get('strategy') or self.strategy
+        if not isinstance(strategy, str) or strategy not in (STRATEGY_GREEDY, STRATEGY_BEAM, STRATEGY_RERANK):
+            return None
+        engine = self.engine
+        if engine.cfg.max_neurons < batch_size or engine.keys_per_image != 1 or len(dataset) == 0:
+            return None
+        length = kwargs.get('length') or self.length
+        beam_size = kwargs.get('beam_size') or self.beam_size
+        temperature = self.temperature if kwargs.get('temperature') is None else kwargs['temperature']
+        mi = kwargs.get('mi')
+        if mi is None:
+            mi = self.lm is not None and strategy != STRATEGY_RERANK
+        if mi and strategy == STRATEGY_RERANK:
+            raise ValueError('cannot set `mi=` decoding when reranking')
+        if (mi or strategy == STRATEGY_RERANK) and self.lm is None:
+            raise ValueError('cannot use MI/rerank decoding without an LM')
+        self._ensure_capacity(length, beam_size if strategy != STRATEGY_GREEDY else 1, getattr(dataset, 'k', 15))
+        engine = self.engine
+        import concurrent.futures
+        total = len(dataset)
+        chunk = (engine.cfg.max_neurons // batch_size) * batch_size
+        slab = 2 * chunk
+        bounds = [(lo, min(lo + slab, total)) for lo in range(0, total, slab)]
+        # pinned staging slabs are expensive to allocate: keep them on the decoder between calls
+        cached = getattr(self, '_predict_staging', None)
+        want = min(slab, total)
+        if cached is None or cached[0][0].shape[0] < want or cached[0][0].shape[1:] != dataset.alloc_batch_u8(0)[0].shape[1:]:
+            cached = [dataset.alloc_batch_u8(want) for _ in range(2)]
+            self._predict_staging = cached
+        staging = cached
+        pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+
+        def load(i):
+            lo, hi = bounds[i]
+            return dataset.batch_u8(lo, hi, out=staging[i % len(staging)])
+
+        pending = pool.submit(load, 0)
+        iterator = range(len(bounds))
+        if display_progress_as is not None:
+            try:
+                from tqdm.auto import tqdm
+                iterator = tqdm(iterator, desc=display_progress_as)
+            except ImportError:
+                pass
+        token_rows = []
+        for i in iterator:
+            images, masks = pending.result()
+            if i + 1 < len(bounds):
+                pending = pool.submit(load, i + 1)
+            with torch.no_grad():
+                tokens, _, steps = engine.describe_host(images, masks, strategy=strategy, mi=mi, length=length,
+                                                        beam=beam_size, group_size=batch_size,
+                                                        temperature=temperature)
+            if strategy != STRATEGY_GREEDY:
+                # the reference returns only the T <= length columns decoded before its per-batch early exit; pad
+                # the rest with <stop> (reconstruct cuts at the first <stop> anyway)
+                keep = torch.arange(length).unsqueeze(0) < steps.to(torch.long).unsqueeze(1)
+                tokens = torch.where(keep, tokens, torch.full_like(tokens, self.indexer.stop_index))
+            token_rows.append(tokens)
+        pool.shutdown(wait=True)
+        self.last_predict_tokens = torch.cat(token_rows)
+        return tuple(self.indexer.reconstruct(self.last_predict_tokens.tolist()))
 
     def fit(self, *args, **kwargs):
         raise NotImplementedError('training (src/milan/decoders.py:873-1070) is out of scope for this engine')
