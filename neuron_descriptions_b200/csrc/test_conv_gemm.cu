@@ -368,6 +368,7 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, dev));
   printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
   const int sms = prop.multiProcessorCount;
+
   std::vector<Case> cases = {
       // name            N   H   W  Cin  Cout ks st relu res split f32
       {"gemm_small",     1,  1, 128,  64,  128, 1, 1, 0, 0, 0, 0},
@@ -379,6 +380,8 @@ int main(int argc, char** argv) {
       {"acc_exact_k4544",1,  1, 256, 4544,  256, 1, 1, 0, 0, 0, 1},
       {"acc_split_k4544",1,  1, 256, 4544,  256, 1, 1, 0, 0, 1, 1},
       {"c1x1_56",        2, 56,  56,  64,  256, 1, 1, 1, 1, 1, 0},
+      {"c1x1_ragged",    1,  1, 300, 256,  256, 1, 1, 1, 1, 1, 0},
+      {"c1x1_ragged_f",  1,  1, 333, 128,  512, 1, 1, 1, 0, 0, 0},
       {"c1x1_cout64",    2, 56,  56, 256,   64, 1, 1, 1, 0, 1, 0},
       {"c3x3_56",        3, 56,  56,  64,   64, 3, 1, 1, 0, 1, 0},
       {"c3x3_28",        5, 28,  28, 128,  128, 3, 1, 1, 0, 1, 0},
