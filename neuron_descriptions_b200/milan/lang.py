@@ -132,37 +132,37 @@ class Indexer:
 
     def index(self, tokenized, start: Optional[bool] = None, stop: Optional[bool] = None,
               pad: Optional[bool] = None, unk: Optional[bool] = None, length: Optional[int] = None):
-        """`Indexer.index`, `src/utils/lang.py:460-515`: tokens -> ids with start/stop/pad/unk handling."""
+        """`Indexer.index`, `src/utils/lang.py:460-515`: tokens -> ids.
+
+        Same observable behaviour as the reference, including its corner cases: `length` counts vocabulary tokens
+        only (one slot is added per enabled start / stop token); without `length` the longest input decides (for a
+        single flat sequence that is the longest TOKEN STRING, as in the reference); with `stop` the sequence is
+        truncated so that `<stop>` always fits; unknown tokens become `<unk>` or are dropped.
+        """
         if not tokenized:
             return ()
-        singleton = isinstance(tokenized[0], str)
-        start = self.start if start is None else start
-        stop = self.stop if stop is None else stop
-        pad = self.pad if pad is None else pad
-        unk = self.unk if unk is None else unk
-        length = length or self.length or max(len(toks) for toks in tokenized)
-        for special in (start, stop):
-            if special:
-                length += 1
-        indexed = []
-        for tokens in [tokenized] if singleton else tokenized:
-            indices = []
-            if start:
-                indices.append(self.start_index)
-            if unk:
-                indices += [self.vocab.ids.get(tok, self.unk_index) for tok in tokens]
+        flat = isinstance(tokenized[0], str)
+        use = {name: (getattr(self, name) if flag is None else flag)
+               for name, flag in (('start', start), ('stop', stop), ('pad', pad), ('unk', unk))}
+        budget = (length or self.length or max(map(len, tokenized))) + int(use['start']) + int(use['stop'])
+        lookup = self.vocab.ids
+
+        def encode(tokens):
+            ids = [self.start_index] if use['start'] else []
+            if use['unk']:
+                ids.extend(lookup.get(token, self.unk_index) for token in tokens)
             else:
-                indices += [self.vocab[tok] for tok in tokens if tok in self.vocab]
-            if stop:
-                if len(indices) >= length:
-                    indices = indices[:length - 1]
-                indices.append(self.stop_index)
-            if len(indices) < length and pad:
-                indices += [self.pad_index] * (length - len(indices))
-            elif len(indices) > length:
-                indices = indices[:length]
-            indexed.append(tuple(indices))
-        return indexed[0] if singleton else tuple(indexed)
+                ids.extend(lookup[token] for token in tokens if token in lookup)
+            if use['stop']:
+                del ids[max(budget - 1, 0):]
+                ids.append(self.stop_index)
+            if use['pad'] and len(ids) < budget:
+                ids.extend([self.pad_index] * (budget - len(ids)))
+            return tuple(ids[:budget])
+
+        if flat:
+            return encode(tokenized)
+        return tuple(encode(tokens) for tokens in tokenized)
 
     def unindex(self, indexed, specials: bool = True, start: bool = True, stop: bool = True, pad: bool = True,
                 unk: bool = True):
