@@ -123,13 +123,23 @@ int milan_lm_score(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int3
 
 /* End-to-end `Decoder.predict` equivalent on HOST buffers (src/milan/decoders.py:809-871 with
  * strategy='rerank' | 'beam' | 'greedy'): h_images (n,k,3,224,224) uint8, h_masks (n,k,1,224,224) uint8 (pinned
- * memory recommended). Copies inputs to the device in chunks, encodes, decodes, copies results back.
+ * memory recommended). Chunks of whole reference batches flow through three streams: the exemplars of chunk i+1 are
+ * copied while chunk i is encoded, and chunk i-1 is decoded (high-priority stream) under that encoder; results are
+ * copied back once at the end.
  * strategy: 0 greedy (mi per `mi`), 1 beam, 2 rerank. Outputs (host): h_tokens_out (n,length) int64,
  * h_scores_out (n), h_steps_out (n) int32 = valid columns of each row (reference T of its group). */
 int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint8_t* h_masks, int32_t n_neurons,
                         int32_t k, int32_t strategy, int32_t mi, int32_t length, int32_t beam, int32_t group_size,
                         float temperature, int64_t* h_tokens_out, float* h_scores_out, int32_t* h_steps_out,
                         void* stream);
+
+/* The same pipeline with the exemplars already RESIDENT on the device: d_images (n,k,3,224,224) uint8, d_masks
+ * (n,k,1,224,224) uint8 (16-byte aligned); outputs on the device: d_tokens_out (n,length) int64 (columns past a
+ * group's early exit hold <stop>), d_scores_out (n). Asynchronous on `stream`; internally the decode of chunk i runs
+ * on an engine-owned high-priority stream under the encoder of chunk i+1, and `stream` waits for it at the end. */
+int milan_describe_device(MilanEngine* engine, const uint8_t* d_images, const uint8_t* d_masks, int32_t n_neurons,
+                          int32_t k, int32_t strategy, int32_t mi, int32_t length, int32_t beam, int32_t group_size,
+                          float temperature, int64_t* d_tokens_out, float* d_scores_out, void* stream);
 
 /* Counters for bench.py: kernels launched by this library since process start; device ms spent in the encoder
  * convolution kernels inside the last milan_describe_host / milan_encode call when profiling is enabled. */

@@ -45,6 +45,8 @@ SIGNATURES = {
     'milan_lm_score': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     'milan_describe_host': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'milan_describe_device': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     'milan_launch_count': (c_int64, []),
     'milan_set_profiling': (c_int32, [c_void_p, c_int32]),
     'milan_get_profile': (c_int32, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float),

@@ -175,11 +175,20 @@ struct MilanEngine {
   long long *tok_cur = nullptr, *tok_next = nullptr, *seqs = nullptr, *lm_inputs = nullptr, *out_tokens = nullptr;
   std::map<std::pair<int, long long>, Plan> gemm_plans;  // (which, M)
   int host_T = 0;
+  int host_chunk = 0, host_groups_per_chunk = 0;  // geometry of the last describe() call
+  bool profiling_append = false;                  // encode(): keep the conv events of earlier chunks
   // ---- host staging for milan_describe_host
   // two staging sets: the exemplars of chunk i+1 are copied (copy_stream) while chunk i is encoded / decoded
   uint8_t *d_img_stage[2] = {nullptr, nullptr}, *d_mask_stage[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  // decode of chunk i runs on its own (high-priority) stream under the encoder of chunk i+1: two feature buffers
+  cudaStream_t dec_stream = nullptr;
+  cudaEvent_t ev_feat_ready[2] = {nullptr, nullptr}, ev_feat_free[2] = {nullptr, nullptr}, ev_dec_done = nullptr;
+  float* feat_enc2 = nullptr;  // second feature buffer (feat_enc is the first)
+  bool overlap_decode = true;  // MILAN_OVERLAP_DECODE=0: encode and decode of a chunk back to back on one stream
+  int describe(const uint8_t* images, const uint8_t* masks, bool host_inputs, int n_neurons, int k, int strategy, int mi,
+               int length, int beam, int group_size, float temperature, cudaStream_t st);
   long long* d_tokens_all = nullptr;  // describe_host results of every chunk (one D2H at the end)
   float* d_scores_all = nullptr;
   int* d_steps_all = nullptr;
@@ -474,7 +483,7 @@ int MilanEngine::encode_alexnet(const void* d_images, const void* d_masks, int n
   std::vector<Plan>* plans = nullptr;
   if (build_alexnet_plans(n, &plans)) return 1;
   const int F = cfg.feature_size, sp = split ? 1 : 0;
-  if (profiling) conv_events_used = 0;
+  if (profiling && !profiling_append) conv_events_used = 0;
   const void* masks = d_masks;
   int mask_dtype = dtype;
   if (masks == nullptr) {
@@ -619,6 +628,7 @@ int MilanEngine::alloc_workspace() {
     if (dalloc2(axPool[1], n * 13 * 13 * 192)) return 1;
     if (dalloc(&mask_wts, n * kAlexMaskStride)) return 1;
     if (dalloc(&feat_enc, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
+    if (dalloc(&feat_enc2, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
     for (int b = 0; b < 2; ++b) {
       if (dalloc(&d_img_stage[b], n * 3 * 224 * 224)) return 1;
       if (dalloc(&d_mask_stage[b], n * 224 * 224)) return 1;
@@ -636,6 +646,7 @@ int MilanEngine::alloc_workspace() {
     if (dalloc2(bufDS, n * stage)) return 1;
     if (dalloc(&mask_wts, n * kMaskPyramidSize)) return 1;
     if (dalloc(&feat_enc, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
+    if (dalloc(&feat_enc2, std::max(n * enc_out_per_image, static_cast<size_t>(cfg.max_neurons) * Kk * F))) return 1;
     for (int b = 0; b < 2; ++b) {
       if (dalloc(&d_img_stage[b], n * 3 * 224 * 224)) return 1;
       if (dalloc(&d_mask_stage[b], n * 224 * 224)) return 1;
@@ -827,7 +838,7 @@ int MilanEngine::encode(const void* d_images, const void* d_masks, int n, int dt
   if (build_encoder_plans(n, &plans)) return 1;
   const int F = cfg.feature_size;
   const int sp = split ? 1 : 0;
-  if (profiling) conv_events_used = 0;
+  if (profiling && !profiling_append) conv_events_used = 0;
   if (reinterpret_cast<uintptr_t>(d_masks) % 16 != 0 && spatial)
     return fail("milan_encode: d_masks must be 16-byte aligned for a spatial encoder");
   RC(launch_stem_pack(d_images, dtype, n, stemA[0], stemA[1], mean, stdv, sp, st, spatial ? d_masks : nullptr));
@@ -1185,6 +1196,7 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   eng->spatial = spatial;
   eng->alexnet = alexnet;
   if (const char* env = getenv("MILAN_FUSE_DOWNSAMPLE")) eng->fuse_downsample = atoi(env) != 0;
+  if (const char* env = getenv("MILAN_OVERLAP_DECODE")) eng->overlap_decode = atoi(env) != 0;
   eng->enc_out_per_image = (spatial ? kSpatialKeys : 1) * config->feature_size;
   *out = eng;
   return 0;
@@ -1201,10 +1213,14 @@ void milan_engine_destroy(MilanEngine* engine) {
   }
   if (engine->copy_stream != nullptr) {
     cudaStreamDestroy(engine->copy_stream);
+    cudaStreamDestroy(engine->dec_stream);
     for (int b = 0; b < 2; ++b) {
       cudaEventDestroy(engine->ev_copied[b]);
       cudaEventDestroy(engine->ev_consumed[b]);
+      cudaEventDestroy(engine->ev_feat_ready[b]);
+      cudaEventDestroy(engine->ev_feat_free[b]);
     }
+    cudaEventDestroy(engine->ev_dec_done);
   }
   delete engine;
 }
@@ -1358,6 +1374,109 @@ int milan_lm_score(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int3
   return 0;
 }
 
+}  // extern "C"
+
+// Shared body of milan_describe_host / milan_describe_device: chunks of whole reference batches through
+//   copy stream (host inputs only): exemplars of chunk c+1 -> staging set (c+1) % 2
+//   `st`                          : encoder of chunk c -> feature buffer c % 2
+//   decode stream (high priority) : beam search / rerank of chunk c-1, under the encoder of chunk c
+// Results of every chunk land in d_tokens_all / d_scores_all / d_steps_all; the caller reads them after `st` (which
+// is made to wait for the decode stream at the end).
+int MilanEngine::describe(const uint8_t* images, const uint8_t* masks, bool host_inputs, int n_neurons, int k,
+                          int strategy, int mi, int length, int beam, int group_size, float temperature,
+                          cudaStream_t st) {
+  MilanEngine* e = this;
+  const int n_keys = k * (spatial ? kSpatialKeys : 1);  // Decoder.encode: view(batch, -1, feature_size)
+  // neurons per chunk: bounded by encoder image capacity and decoder capacity; whole reference groups only
+  int chunk = std::min(cfg.max_images / k, cfg.max_neurons);
+  if (chunk >= group_size) chunk = chunk / group_size * group_size;
+  if (chunk < 1) return fail("max_images %d too small for k=%d", cfg.max_images, k);
+  if (strategy != 0 && chunk % group_size != 0 && chunk < n_neurons)
+    return fail("engine capacity (%d neurons/chunk) smaller than group_size %d", chunk, group_size);
+  const size_t img_bytes = static_cast<size_t>(k) * 3 * 224 * 224, msk_bytes = static_cast<size_t>(k) * 224 * 224;
+  // ---- lazily created pipeline resources
+  if (copy_stream == nullptr) {
+    CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    int lo_prio = 0, hi_prio = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CU(cudaStreamCreateWithPriority(&dec_stream, cudaStreamNonBlocking, hi_prio));
+    for (int b = 0; b < 2; ++b) {
+      CU(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_consumed[b], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_feat_ready[b], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_feat_free[b], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&ev_dec_done, cudaEventDisableTiming));
+  }
+  if (static_cast<size_t>(n_neurons) > results_cap) {
+    const size_t cap = static_cast<size_t>(n_neurons);
+    if (dalloc(&d_tokens_all, cap * cfg.max_length)) return 1;
+    if (dalloc(&d_scores_all, cap)) return 1;
+    if (dalloc(&d_steps_all, cap)) return 1;
+    results_cap = cap;
+  }
+  const int n_chunks = (n_neurons + chunk - 1) / chunk;
+  const int groups_per_chunk = (chunk + group_size - 1) / group_size;
+  // with profiling on the chunks run back to back on `st`, so that the conv kernels' event-timed durations are not
+  // stretched by decode kernels sharing the SMs
+  const bool overlap = overlap_decode && n_chunks > 1 && !profiling;
+  cudaStream_t ds = overlap ? dec_stream : st;
+  float* feats[2] = {feat_enc, feat_enc2};
+  if (profiling) conv_events_used = 0;
+  // Exemplars of chunk c -> staging set c % 2 on the copy stream, once the encoder has consumed what the set held
+  // (chunk c - 2). The host buffers are read asynchronously only if they are pinned; pageable memory still works.
+  auto issue_copy = [&](int c) -> int {
+    const int b = c & 1;
+    const int done = c * chunk;
+    const int nb = std::min(chunk, n_neurons - done);
+    if (c >= 2) CU(cudaStreamWaitEvent(copy_stream, ev_consumed[b], 0));
+    CU(cudaMemcpyAsync(d_img_stage[b], images + done * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, copy_stream));
+    CU(cudaMemcpyAsync(d_mask_stage[b], masks + done * msk_bytes, nb * msk_bytes, cudaMemcpyHostToDevice, copy_stream));
+    CU(cudaEventRecord(ev_copied[b], copy_stream));
+    return 0;
+  };
+  if (host_inputs && issue_copy(0)) return 1;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b = c & 1;
+    const int done = c * chunk;
+    const int nb = std::min(chunk, n_neurons - done);
+    const uint8_t* d_img = host_inputs ? d_img_stage[b] : images + done * img_bytes;
+    const uint8_t* d_msk = host_inputs ? d_mask_stage[b] : masks + done * msk_bytes;
+    if (host_inputs) {
+      if (c + 1 < n_chunks && issue_copy(c + 1)) return 1;
+      CU(cudaStreamWaitEvent(st, ev_copied[b], 0));
+    }
+    if (overlap && c >= 2) CU(cudaStreamWaitEvent(st, ev_feat_free[b], 0));  // decode of chunk c-2 read feats[b]
+    profiling_append = profiling && c > 0;  // one conv-event list across the chunks of this call
+    if (e->encode(d_img, d_msk, nb * k, MILAN_DTYPE_U8, feats[b], st)) return 1;
+    profiling_append = false;
+    if (host_inputs) CU(cudaEventRecord(ev_consumed[b], st));
+    if (overlap) {
+      CU(cudaEventRecord(ev_feat_ready[b], st));
+      CU(cudaStreamWaitEvent(ds, ev_feat_ready[b], 0));
+    }
+    long long* d_tok = d_tokens_all + static_cast<size_t>(done) * length;
+    float* d_sc = d_scores_all + done;
+    if (strategy == 0) {
+      if (decode_greedy(feats[b], nb, n_keys, length, mi, temperature, nullptr, d_tok, d_sc, nullptr, nullptr, ds)) return 1;
+    } else {
+      if (decode_beam(feats[b], nb, n_keys, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0, temperature,
+                      nullptr, nullptr, d_steps_all + c * groups_per_chunk, d_tok, d_sc, nullptr, ds))
+        return 1;
+    }
+    if (overlap) CU(cudaEventRecord(ev_feat_free[b], ds));
+  }
+  if (overlap) {  // later work on `st` (the result copies) follows the last decode
+    CU(cudaEventRecord(ev_dec_done, ds));
+    CU(cudaStreamWaitEvent(st, ev_dec_done, 0));
+  }
+  host_chunk = chunk;
+  host_groups_per_chunk = groups_per_chunk;
+  return 0;
+}
+
+extern "C" {
+
 int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint8_t* h_masks, int32_t n_neurons,
                         int32_t k, int32_t strategy, int32_t mi, int32_t length, int32_t beam, int32_t group_size,
                         float temperature, int64_t* h_tokens_out, float* h_scores_out, int32_t* h_steps_out,
@@ -1367,84 +1486,14 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
   MilanEngine* e = engine;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!e->cfg.has_encoder) return fail("engine was created without an encoder");
-  const int n_keys = k * (e->spatial ? kSpatialKeys : 1);  // Decoder.encode: view(batch, -1, feature_size)
+  const int n_keys = k * (e->spatial ? kSpatialKeys : 1);
   if (n_keys > e->cfg.max_keys) return fail("k=%d (%d keys) exceeds max_keys %d", k, n_keys, e->cfg.max_keys);
   if (group_size <= 0) group_size = 16;
-  // neurons per chunk: bounded by encoder image capacity and decoder capacity; whole reference groups only
-  int chunk = std::min(e->cfg.max_images / k, e->cfg.max_neurons);
-  if (chunk >= group_size) chunk = chunk / group_size * group_size;
-  if (chunk < 1) return fail("max_images %d too small for k=%d", e->cfg.max_images, k);
-  if (strategy != 0 && chunk % group_size != 0 && chunk < n_neurons)
-    return fail("engine capacity (%d neurons/chunk) smaller than group_size %d", chunk, group_size);
-  const size_t img_bytes = static_cast<size_t>(k) * 3 * 224 * 224, msk_bytes = static_cast<size_t>(k) * 224 * 224;
   if (n_neurons <= 0) return 0;
-  // ---- lazily created pipeline resources
-  if (e->copy_stream == nullptr) {
-    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
-      CU(cudaEventCreateWithFlags(&e->ev_copied[b], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&e->ev_consumed[b], cudaEventDisableTiming));
-    }
-  }
-  if (static_cast<size_t>(n_neurons) > e->results_cap) {
-    const size_t cap = static_cast<size_t>(n_neurons);
-    if (e->dalloc(&e->d_tokens_all, cap * e->cfg.max_length)) return 1;
-    if (e->dalloc(&e->d_scores_all, cap)) return 1;
-    if (e->dalloc(&e->d_steps_all, cap)) return 1;
-    e->results_cap = cap;
-  }
-  const int n_chunks = (n_neurons + chunk - 1) / chunk;
-  const int groups_per_chunk = (chunk + group_size - 1) / group_size;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  if (e->profiling) for (auto& x : ev) CU(cudaEventCreate(&x));
-  // Exemplars of chunk c -> staging set c % 2 on the copy stream, once the encoder has consumed what the set held
-  // (chunk c - 2). The host buffers are read asynchronously only if they are pinned; pageable memory still works.
-  auto issue_copy = [&](int c) -> int {
-    const int b = c & 1;
-    const int done = c * chunk;
-    const int nb = std::min(chunk, n_neurons - done);
-    if (c >= 2) CU(cudaStreamWaitEvent(e->copy_stream, e->ev_consumed[b], 0));
-    CU(cudaMemcpyAsync(e->d_img_stage[b], h_images + done * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice,
-                       e->copy_stream));
-    CU(cudaMemcpyAsync(e->d_mask_stage[b], h_masks + done * msk_bytes, nb * msk_bytes, cudaMemcpyHostToDevice,
-                       e->copy_stream));
-    CU(cudaEventRecord(e->ev_copied[b], e->copy_stream));
-    return 0;
-  };
-  if (issue_copy(0)) return 1;
-  for (int c = 0; c < n_chunks; ++c) {
-    const int b = c & 1;
-    const int done = c * chunk;
-    const int nb = std::min(chunk, n_neurons - done);
-    if (c + 1 < n_chunks && issue_copy(c + 1)) return 1;
-    CU(cudaStreamWaitEvent(st, e->ev_copied[b], 0));
-    if (e->profiling) CU(cudaEventRecord(ev[0], st));
-    if (e->encode(e->d_img_stage[b], e->d_mask_stage[b], nb * k, MILAN_DTYPE_U8, e->feat_enc, st)) return 1;
-    CU(cudaEventRecord(e->ev_consumed[b], st));
-    if (e->profiling) CU(cudaEventRecord(ev[1], st));
-    long long* d_tok = e->d_tokens_all + static_cast<size_t>(done) * length;
-    float* d_sc = e->d_scores_all + done;
-    if (strategy == 0) {
-      if (e->decode_greedy(e->feat_enc, nb, n_keys, length, mi, temperature, nullptr, d_tok, d_sc, nullptr, nullptr, st))
-        return 1;
-    } else {
-      if (e->decode_beam(e->feat_enc, nb, n_keys, length, beam, group_size, strategy == 2, strategy == 1 ? mi : 0,
-                         temperature, nullptr, nullptr, e->d_steps_all + c * groups_per_chunk, d_tok, d_sc, nullptr, st))
-        return 1;
-    }
-    if (e->profiling) {
-      CU(cudaEventRecord(ev[2], st));
-      CU(cudaStreamSynchronize(st));
-      float a = 0, bms = 0;
-      CU(cudaEventElapsedTime(&a, ev[0], ev[1]));
-      CU(cudaEventElapsedTime(&bms, ev[1], ev[2]));
-      e->prof_enc_ms += a;
-      e->prof_dec_ms += bms;
-      if (e->collect_conv_events(st)) return 1;
-    }
-  }
+  if (e->describe(h_images, h_masks, true, n_neurons, k, strategy, mi, length, beam, group_size, temperature, st)) return 1;
   // ---- one device->host read of everything, then a single synchronisation
-  std::vector<int> steps(static_cast<size_t>(n_chunks) * groups_per_chunk, length);
+  const int n_chunks = (n_neurons + e->host_chunk - 1) / e->host_chunk;
+  std::vector<int> steps(static_cast<size_t>(n_chunks) * e->host_groups_per_chunk, length);
   CU(cudaMemcpyAsync(h_tokens_out, e->d_tokens_all, sizeof(long long) * static_cast<size_t>(n_neurons) * length,
                      cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h_scores_out, e->d_scores_all, sizeof(float) * n_neurons, cudaMemcpyDeviceToHost, st));
@@ -1452,8 +1501,31 @@ int milan_describe_host(MilanEngine* engine, const uint8_t* h_images, const uint
     CU(cudaMemcpyAsync(steps.data(), e->d_steps_all, sizeof(int) * steps.size(), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   for (int i = 0; i < n_neurons; ++i)
-    h_steps_out[i] = strategy == 0 ? length : steps[(i / chunk) * groups_per_chunk + (i % chunk) / group_size];
-  if (e->profiling) for (auto& x : ev) cudaEventDestroy(x);
+    h_steps_out[i] = strategy == 0 ? length
+                                   : steps[(i / e->host_chunk) * e->host_groups_per_chunk + (i % e->host_chunk) / group_size];
+  if (e->collect_conv_events(st)) return 1;
+  return 0;
+}
+
+int milan_describe_device(MilanEngine* engine, const uint8_t* d_images, const uint8_t* d_masks, int32_t n_neurons,
+                          int32_t k, int32_t strategy, int32_t mi, int32_t length, int32_t beam, int32_t group_size,
+                          float temperature, int64_t* d_tokens_out, float* d_scores_out, void* stream) {
+  CHECK_READY(engine);
+  CHECK_DECODER(engine);
+  MilanEngine* e = engine;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!e->cfg.has_encoder) return fail("engine was created without an encoder");
+  const int n_keys = k * (e->spatial ? kSpatialKeys : 1);
+  if (n_keys > e->cfg.max_keys) return fail("k=%d (%d keys) exceeds max_keys %d", k, n_keys, e->cfg.max_keys);
+  if (group_size <= 0) group_size = 16;
+  if (n_neurons <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(d_images) % 16 != 0 || (static_cast<size_t>(k) * 3 * 224 * 224) % 16 != 0)
+    return fail("milan_describe_device: d_images must be 16-byte aligned");
+  if (e->describe(d_images, d_masks, false, n_neurons, k, strategy, mi, length, beam, group_size, temperature, st)) return 1;
+  CU(cudaMemcpyAsync(d_tokens_out, e->d_tokens_all, sizeof(long long) * static_cast<size_t>(n_neurons) * length,
+                     cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(d_scores_out, e->d_scores_all, sizeof(float) * n_neurons, cudaMemcpyDeviceToDevice, st));
+  if (e->profiling && e->collect_conv_events(st)) return 1;  // (synchronises `st`)
   return 0;
 }
 

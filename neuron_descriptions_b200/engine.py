@@ -201,6 +201,22 @@ class Engine:
                                                     _ptr(tokens), _ptr(scores), _ptr(steps), _stream(self.device)))
         return tokens, scores, steps
 
+    def describe_device(self, images_u8: torch.Tensor, masks_u8: torch.Tensor, strategy: str = 'rerank', mi=False,
+                        length: int = 15, beam: int = 50, group_size: int = 16, temperature: float = 0.2):
+        """DEVICE uint8 tensors (n,k,3,224,224)/(n,k,1,224,224) -> device (tokens (n,length), scores (n)); the
+        chunks are pipelined like `describe_host` (decode of chunk i under the encoder of chunk i+1)."""
+        assert images_u8.dtype == torch.uint8 and masks_u8.dtype == torch.uint8
+        images_u8 = images_u8.to(self.device).contiguous()
+        masks_u8 = masks_u8.to(self.device).contiguous()
+        n, k = images_u8.shape[:2]
+        tokens = self._new(n, length, dtype=torch.long)
+        scores = self._new(n)
+        code = {'greedy': _lib.STRATEGY_GREEDY, 'beam': _lib.STRATEGY_BEAM, 'rerank': _lib.STRATEGY_RERANK}[strategy]
+        _lib.check(self.lib.milan_describe_device(self.handle, _ptr(images_u8), _ptr(masks_u8), n, k, code,
+                                                  int(bool(mi)), length, beam, group_size, float(temperature),
+                                                  _ptr(tokens), _ptr(scores), _stream(self.device)))
+        return tokens, scores
+
     def set_profiling(self, enabled: bool):
         _lib.check(self.lib.milan_set_profiling(self.handle, int(enabled)))
 

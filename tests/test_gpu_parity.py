@@ -266,6 +266,9 @@ def test_describe_host_pipelined_chunks(full_sd):
     for lo in range(0, 11, 4):
         t, s, st = engine.describe_host(images_u8[lo:lo + 4].contiguous(), masks_u8[lo:lo + 4].contiguous(), **kwargs)
         assert torch.equal(tokens[lo:lo + 4], t) and torch.equal(scores[lo:lo + 4], s) and torch.equal(steps[lo:lo + 4], st)
+    # resident inputs: the same pipeline without the copies
+    tokens_d, scores_d = engine.describe_device(images_u8.cuda(), masks_u8.cuda(), **kwargs)
+    assert torch.equal(tokens_d.cpu(), tokens) and torch.equal(scores_d.cpu(), scores)
     tokens_g, scores_g, steps_g = engine.describe_host(images_u8, masks_u8, strategy='greedy', mi=False)
     feats = engine.encode(images_u8.view(-1, 3, 224, 224), masks_u8.view(-1, 1, 224, 224)).view(11, 3, -1)
     for lo in range(0, 11, 4):
