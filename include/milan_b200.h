@@ -141,6 +141,32 @@ int milan_describe_device(MilanEngine* engine, const uint8_t* d_images, const ui
                           int32_t k, int32_t strategy, int32_t mi, int32_t length, int32_t beam, int32_t group_size,
                           float temperature, int64_t* d_tokens_out, float* d_scores_out, void* stream);
 
+/* ---- Stage-1 exemplar statistics (src/exemplars/compute.py:27-246). Stateless: the
+ * caller owns every buffer and runs the described network itself; d_acts is its activation tensor (B, U, P) float32
+ * (B images of the batch, U units, P = H*W positions).
+ *   milan_tally_topk       RunningTopK.add (src/deps/netdissect/runningstats.py:58-94) on the spatial max of each
+ *                          image: d_top_vals (U,k) descending / d_top_ids (U,k) dataset indices, initialised by the
+ *                          caller to -inf / -1; dataset index of image b = base_index + b; k <= 64, B <= 1024
+ *   milan_tally_samples    RunningQuantile.add in its exact regime (runningstats.py:343-386): appends the B*P
+ *                          activations of every unit to d_samples (U, capacity) at column `count`
+ *   milan_tally_hist       beyond that regime: d_hist (U, 65536) uint32 += histogram of the upper 16 bits of the
+ *                          order-preserving float key (deterministic; histograms of several GPUs add)
+ *   milan_quantile_exact   RunningQuantile.quantiles(q) (runningstats.py:557-580) on n <= 8192 kept samples
+ *   milan_quantile_hist    the same estimator read from the histogram (linear inside the selected bin)
+ *   milan_activation_masks ImageVisualizer.pytorch_mask (src/deps/netdissect/imgviz.py:185-198) with the default
+ *                          grid of upsample.upsample_grid (upsample.py:127-157): d_maps (n,H,W) -> d_masks (n,S,S) of
+ *                          0/1 bytes, mask = bilinear(zeros padding, align_corners) > d_levels[i] */
+int milan_tally_topk(const float* d_acts, int32_t B, int32_t U, int32_t P, int64_t base_index, int32_t k,
+                     float* d_pooled_scratch /* (B, U) floats */, float* d_top_vals, int64_t* d_top_ids, void* stream);
+int milan_tally_samples(const float* d_acts, int32_t B, int32_t U, int32_t P, float* d_samples, int64_t capacity,
+                        int64_t count, void* stream);
+int milan_tally_hist(const float* d_acts, int32_t B, int32_t U, int32_t P, uint32_t* d_hist, void* stream);
+int milan_quantile_exact(const float* d_samples, int32_t U, int64_t capacity, int64_t n, float q, float* d_levels,
+                         void* stream);
+int milan_quantile_hist(const uint32_t* d_hist, int32_t U, int64_t n, float q, float* d_levels, void* stream);
+int milan_activation_masks(const float* d_maps, const float* d_levels, int32_t n, int32_t H, int32_t W, int32_t S,
+                           uint8_t* d_masks, void* stream);
+
 /* Counters for bench.py: kernels launched by this library since process start; device ms spent in the encoder
  * convolution kernels inside the last milan_describe_host / milan_encode call when profiling is enabled. */
 int64_t milan_launch_count(void);

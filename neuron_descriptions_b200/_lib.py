@@ -47,6 +47,13 @@ SIGNATURES = {
                                       c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'milan_describe_device': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    'milan_tally_topk': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    'milan_tally_samples': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int64, c_void_p]),
+    'milan_tally_hist': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    'milan_quantile_exact': (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    'milan_quantile_hist': (c_int32, [c_void_p, c_int32, c_int64, c_float, c_void_p, c_void_p]),
+    'milan_activation_masks': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'milan_launch_count': (c_int64, []),
     'milan_set_profiling': (c_int32, [c_void_p, c_int32]),
     'milan_get_profile': (c_int32, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float),

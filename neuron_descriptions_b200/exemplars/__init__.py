@@ -1,0 +1,2 @@
+"""Stage-1 exemplar computation on B200 (mirror of `src/exemplars/__init__.py:15`): `discriminative`, `compute`."""
+from neuron_descriptions_b200.exemplars.compute import ActivationStats, compute, discriminative

@@ -6,6 +6,7 @@ stored. The beam search inside the reference's `Decoder.forward` is `oracle.beam
 (allennlp is not installed; see that file's header) — every other line executed is the reference's own.
 """
 import os
+import pathlib
 import sys
 
 import numpy as np
@@ -117,6 +118,50 @@ def make_encoder_variant_goldens(milan):
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'encoder_variants.npz'), **out)
 
 
+def exemplar_toy_model(seed: int = 0):
+    """The toy CNN of the reference's own stage-1 tests (`tests/exemplars/compute_test.py:149-165`): two 4x4 convs."""
+    import collections
+    gen = torch.Generator().manual_seed(seed)
+    model = torch.nn.Sequential(collections.OrderedDict([
+        ('conv_1', torch.nn.Conv2d(3, 6, 4, padding=2)), ('conv_2', torch.nn.Conv2d(6, 6, 4, padding=2))]))
+    with torch.no_grad():
+        for param in model.parameters():
+            param.copy_(torch.randn(param.shape, generator=gen) * 0.3)
+    return model.eval()
+
+
+def exemplar_toy_images(n: int = 20, size: int = 16, seed: int = 0):
+    return torch.rand(n, 3, size, size, generator=torch.Generator().manual_seed(seed + 5))
+
+
+EXEMPLAR_CASES = (('conv_1', 16, 4), ('conv_2', 24, 3))  # (layer, output_size, k)
+
+
+def make_exemplars_golden():
+    """The reference's `exemplars.compute.discriminative` (`src/exemplars/compute.py:263-349`) on the toy model:
+    20 images x 17x17 (18x18) positions stay below the 8192-sample capacity of the quantile sketch's first level,
+    where the sketch is exact and deterministic."""
+    import tempfile
+    from torch.utils import data
+    compute = ref_import.import_reference_exemplars()
+    model, images = exemplar_toy_model(), exemplar_toy_images()
+    out = {}
+    for layer, output_size, k in EXEMPLAR_CASES:
+        root = pathlib.Path(tempfile.mkdtemp())
+        compute.discriminative(model, data.TensorDataset(images), layer=layer, device='cpu', results_dir=root / 'res',
+                               viz_dir=root / 'viz', display_progress=False, num_workers=0, k=k, quantile=0.99,
+                               image_size=16, output_size=output_size, batch_size=8, save_results=True,
+                               save_viz=False)
+        d = root / 'res' / layer
+        out[f'{layer}_ids'] = np.loadtxt(d / 'ids.csv', delimiter=',').astype(np.int64)
+        out[f'{layer}_activations'] = np.loadtxt(d / 'activations.csv', delimiter=',').astype(np.float32)
+        out[f'{layer}_images'] = np.load(d / 'images.npy')
+        out[f'{layer}_masks'] = np.load(d / 'masks.npy')
+        print(f'exemplars golden [{layer}]: images {out[f"{layer}_images"].shape} masks mean '
+              f'{out[f"{layer}_masks"].mean():.4f} ids[0] {out[f"{layer}_ids"][0].tolist()}')
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'exemplars.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -127,8 +172,11 @@ def main():
         return make_score_golden(milan, lang, vocab)
     if '--only-encoders' in sys.argv:
         return make_encoder_variant_goldens(milan)
+    if '--only-exemplars' in sys.argv:
+        return make_exemplars_golden()
     make_score_golden(milan, lang, vocab)
     make_encoder_variant_goldens(milan)
+    make_exemplars_golden()
 
     # ---- encoder golden: reference PyramidConvEncoder('resnet101') on seeded exemplars.
     sd = synthetic.synthetic_state_dict(seed=0, sharpen=3.0)

@@ -68,6 +68,16 @@ def install_stubs():
         en = _stub('spacy.lang.en', English=_Placeholder)
         spacy.lang = lang
         lang.en = en
+    # the stage-1 path (src/exemplars -> src/deps/netdissect) additionally imports these; nothing of them is executed
+    if 'statsmodels' not in sys.modules:
+        _stub('statsmodels')
+        _stub('statsmodels.stats')
+        _stub('statsmodels.stats.correlation_tools', cov_nearest=None, corr_nearest=None)
+    if 'matplotlib' not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except ImportError:
+            _stub('matplotlib', cm=types.SimpleNamespace(hot=None))
     if 'easydict' not in sys.modules:
         _stub('easydict', EasyDict=_AttrDict)
     if 'allennlp' not in sys.modules:
@@ -95,3 +105,10 @@ def import_reference():
     milan = importlib.import_module('src.milan')
     lang = importlib.import_module('src.utils.lang')
     return milan, lang
+
+
+def import_reference_exemplars():
+    """The reference's stage-1 module (`src/exemplars/compute.py`), imported with the same stubs."""
+    import_reference()
+    import importlib
+    return importlib.import_module('src.exemplars.compute')

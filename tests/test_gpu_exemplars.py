@@ -1,0 +1,89 @@
+"""GPU: stage-1 exemplar computation (`neuron_descriptions_b200/exemplars`) against the golden produced by the
+UNMODIFIED reference `exemplars.compute.discriminative` (`oracle/make_golden.py::make_exemplars_golden`) and
+against the CPU oracle (`oracle/exemplars_oracle.py`) for the histogram regime and the kernels alone."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch.utils import data
+
+from oracle import exemplars_oracle as E
+from oracle.make_golden import EXEMPLAR_CASES, exemplar_toy_images, exemplar_toy_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('layer,output_size,k', EXEMPLAR_CASES)
+def test_discriminative_matches_reference_golden(golden_dir, tmp_path, layer, output_size, k):
+    from neuron_descriptions_b200 import exemplars
+    g = np.load(os.path.join(golden_dir, 'exemplars.npz'))
+    model, images = exemplar_toy_model(), exemplar_toy_images()
+    stats = exemplars.discriminative(model, data.TensorDataset(images), layer=layer, device='cuda:0',
+                                     results_dir=tmp_path, k=k, quantile=0.99, image_size=16,
+                                     output_size=output_size, batch_size=8)
+    assert stats.exact_quantile
+    d = tmp_path / layer
+    assert sorted(p.name for p in d.iterdir()) == ['activations.csv', 'ids.csv', 'images.npy', 'masks.npy']
+    np.testing.assert_array_equal(np.loadtxt(d / 'ids.csv', delimiter=',').astype(np.int64), g[f'{layer}_ids'])
+    np.testing.assert_allclose(np.loadtxt(d / 'activations.csv', delimiter=','), g[f'{layer}_activations'],
+                               rtol=2e-5, atol=2e-6)
+    np.testing.assert_array_equal(np.load(d / 'images.npy'), g[f'{layer}_images'])
+    got, ref = np.load(d / 'masks.npy'), g[f'{layer}_masks']
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    # the model forward runs on the GPU here and on the CPU in the reference: a pixel within an ulp of its level may flip
+    assert int((got != ref).sum()) <= 2, f'{int((got != ref).sum())} mask pixels differ'
+    # the files are a valid exemplar set for the describe path
+    from neuron_descriptions_b200 import milannotations
+    exemplar_set = milannotations.TopImagesDataset(tmp_path, layers=[layer])
+    assert len(exemplar_set) == got.shape[0] and exemplar_set.k == k
+
+
+def test_tally_kernels_vs_oracle():
+    import importlib
+    C = importlib.import_module('neuron_descriptions_b200.exemplars.compute')
+    gen = torch.Generator().manual_seed(3)
+    hiddens = torch.randn(37, 9, 11, 13, generator=gen)
+    hiddens[5, 2] = hiddens[9, 2]  # an exact tie between two images: the earlier index must win
+    tally = C._Tally(5, torch.device('cuda:0'))
+    for lo in range(0, 37, 10):
+        tally.add(hiddens[lo:lo + 10].cuda())
+    stats = tally.result(0.97)
+    pooled, samples = E.pooled_and_samples(hiddens)
+    values, ids = E.topk(pooled.numpy(), 5)
+    np.testing.assert_array_equal(stats.ids.cpu().numpy(), ids)
+    np.testing.assert_array_equal(stats.activations.cpu().numpy(), values)
+    assert stats.exact_quantile and 37 * 11 * 13 <= E.EXACT_CAPACITY
+    np.testing.assert_array_equal(stats.levels.cpu().numpy(), E.quantile_levels(samples.numpy(), np.float32(0.97)))
+
+
+def test_histogram_quantile_beyond_the_exact_regime():
+    import importlib
+    C = importlib.import_module('neuron_descriptions_b200.exemplars.compute')
+    gen = torch.Generator().manual_seed(4)
+    hiddens = torch.randn(64, 7, 20, 20, generator=gen) * 3 + 1  # 25600 samples per unit > 8192
+    tally = C._Tally(3, torch.device('cuda:0'))
+    for lo in range(0, 64, 16):
+        tally.add(hiddens[lo:lo + 16].cuda())
+    stats = tally.result(0.99)
+    assert not stats.exact_quantile
+    samples = hiddens.permute(0, 2, 3, 1).reshape(-1, 7).numpy()
+    n = len(samples)
+    for u in range(7):
+        s = np.sort(samples[:, u])
+        exact = np.interp(0.99, (np.arange(n) + 0.5) / n, s)
+        assert abs(stats.levels[u].item() - exact) <= abs(exact) * 2 ** -7, (stats.levels[u].item(), exact)
+
+
+def test_activation_masks_vs_oracle():
+    import importlib
+    C = importlib.import_module('neuron_descriptions_b200.exemplars.compute')
+    gen = torch.Generator().manual_seed(5)
+    maps = torch.randn(6, 7, 7, generator=gen)
+    levels = torch.tensor([0.0, 0.5, -0.5, 1.0, 0.2, 5.0])
+    for size in (7, 16, 224):
+        got = C.activation_masks(maps.cuda(), levels, size).cpu().numpy()
+        for i in range(len(maps) if size < 100 else 1):
+            ref = (E.upsample_bilinear_zeros(maps[i].numpy(), size) > levels[i].item()).astype(np.uint8)
+            assert int((got[i] != ref).sum()) <= 1
+    assert got[5].sum() == 0

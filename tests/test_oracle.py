@@ -137,3 +137,18 @@ def test_reconstruct_matches_reference_rules():
     assert O.reconstruct([n, 3, n + 2, n + 3, 4], vocab) == 'Dog cat'
     with pytest.raises(ValueError):
         O.reconstruct([n + 9], vocab)
+
+
+@pytest.mark.parametrize('layer,output_size,k', [('conv_1', 16, 4), ('conv_2', 24, 3)])
+def test_exemplars_oracle_matches_reference_golden(golden_dir, layer, output_size, k):
+    """Stage-1 restatement (`oracle/exemplars_oracle.py`) vs the reference's `exemplars.compute.discriminative`."""
+    from oracle import exemplars_oracle as E
+    from oracle.make_golden import exemplar_toy_images, exemplar_toy_model
+    g = _load(golden_dir, 'exemplars.npz')
+    model, images = exemplar_toy_model(), exemplar_toy_images()
+    features = (lambda x: model.conv_1(x)) if layer == 'conv_1' else (lambda x: model(x))
+    out = E.discriminative(features, images, k, 0.99, output_size, batch_size=8)
+    np.testing.assert_array_equal(out['ids'], g[f'{layer}_ids'])
+    np.testing.assert_allclose(out['activations'], g[f'{layer}_activations'], rtol=2e-5, atol=2e-6)  # csv: %.5e
+    np.testing.assert_array_equal(out['images'], g[f'{layer}_images'])
+    np.testing.assert_array_equal(out['masks'], g[f'{layer}_masks'])
