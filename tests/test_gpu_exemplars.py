@@ -87,3 +87,29 @@ def test_activation_masks_vs_oracle():
             ref = (E.upsample_bilinear_zeros(maps[i].numpy(), size) > levels[i].item()).astype(np.uint8)
             assert int((got[i] != ref).sum()) <= 1
     assert got[5].sum() == 0
+
+
+def test_stage1_feeds_stage2(tmp_path):
+    """Exemplars computed on the GPU (224x224, k = 3) are read back as a `TopImagesDataset` and described by the
+    MILAN decoder: the two stages share one on-disk contract (`src/exemplars/compute.py:217-227` ->
+    `src/milannotations/datasets.py:158-197`)."""
+    from neuron_descriptions_b200 import exemplars, milan, milannotations, synthetic
+    from neuron_descriptions_b200.milan import lang
+    model = exemplar_toy_model()
+    images = torch.rand(12, 3, 224, 224, generator=torch.Generator().manual_seed(8))
+    stats = exemplars.discriminative(model, data.TensorDataset(images), layer='conv_2', device='cuda:0',
+                                     results_dir=tmp_path, k=3, quantile=0.99, output_size=224, batch_size=4)
+    assert not stats.exact_quantile  # 12 x 226 x 226 samples per unit: histogram regime
+    exemplar_set = milannotations.TopImagesDataset(tmp_path, layers=['conv_2'])
+    assert len(exemplar_set) == 6 and exemplar_set.k == 3
+    sample = exemplar_set[0]
+    assert sample.images.shape == (3, 3, 224, 224) and sample.masks.shape == (3, 1, 224, 224)
+    assert 0.0 < float(sample.masks.mean()) < 0.05  # ~1 % of the pixels lie above the 0.99 quantile
+    vocab = synthetic.synthetic_vocab(5000)
+    indexer = lang.Indexer(lang.Vocab(vocab), start=True, stop=True, pad=True, unk=True)
+    decoder = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                            lm=milan.LanguageModel(indexer), max_neurons=16)
+    decoder.load_state_dict(synthetic.synthetic_state_dict(seed=0, sharpen=12.0))
+    captions = decoder.predict(exemplar_set, strategy='rerank', beam_size=10, device='cuda:0',
+                               display_progress_as=None)
+    assert len(captions) == 6 and all(isinstance(c, str) and c for c in captions)
