@@ -1,2 +1,3 @@
 """Stage-1 exemplar computation on B200 (mirror of `src/exemplars/__init__.py:15`): `discriminative`, `compute`."""
 from neuron_descriptions_b200.exemplars.compute import ActivationStats, compute, discriminative
+from neuron_descriptions_b200.exemplars import transforms  # noqa: E402,F401

@@ -162,6 +162,30 @@ def make_exemplars_golden():
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'exemplars.npz'), **out)
 
 
+def payload_skeleton(value):
+    """A checkpoint payload with every tensor replaced by ['tensor', shape, dtype] (JSON-serialisable)."""
+    if isinstance(value, dict):
+        return {str(key): payload_skeleton(item) for key, item in value.items()}
+    if torch.is_tensor(value):
+        return ['tensor', list(value.shape), str(value.dtype)]
+    if isinstance(value, (tuple, list)):
+        return [payload_skeleton(item) for item in value]
+    return value
+
+
+def make_checkpoint_skeleton(milan, lang):
+    """Structure of `Decoder.serialize()` (`src/utils/serialize.py:80-118,188-219`, `decoders.py:1072-1109`) as the
+    reference writes it for the shipped architecture: what `milan.pretrained()` has to ingest."""
+    import json
+    vocab = synthetic.synthetic_vocab(40)
+    indexer = lang.Indexer(lang.Vocab(tuple(vocab)), tokenize=None, start=True, stop=True, pad=True, unk=True)
+    decoder = milan.decoders.Decoder(indexer, milan.encoders.PyramidConvEncoder('resnet101', pretrained=False),
+                                     lm=milan.lms.LanguageModel(indexer))
+    with open(os.path.join(GOLDEN_DIR, 'checkpoint_skeleton.json'), 'w') as handle:
+        json.dump(payload_skeleton(decoder.serialize()), handle, indent=0, sort_keys=True)
+    print('checkpoint skeleton:', len(decoder.state_dict()), 'state_dict entries')
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -174,9 +198,12 @@ def main():
         return make_encoder_variant_goldens(milan)
     if '--only-exemplars' in sys.argv:
         return make_exemplars_golden()
+    if '--only-checkpoint' in sys.argv:
+        return make_checkpoint_skeleton(milan, lang)
     make_score_golden(milan, lang, vocab)
     make_encoder_variant_goldens(milan)
     make_exemplars_golden()
+    make_checkpoint_skeleton(milan, lang)
 
     # ---- encoder golden: reference PyramidConvEncoder('resnet101') on seeded exemplars.
     sd = synthetic.synthetic_state_dict(seed=0, sharpen=3.0)

@@ -91,3 +91,63 @@ def test_checkpoint_round_trip(tmp_path):
     assert set(loaded.state_dict()) == set(sd)
     via_hub = milan.pretrained('base', path=path)
     assert via_hub.vocab_size == 34
+
+
+def test_reference_checkpoint_payload_is_ingested(tmp_path):
+    """A payload with exactly the structure the UNMODIFIED reference's `Decoder.serialize()` writes
+    (`tests/golden/checkpoint_skeleton.json`, made by `oracle/make_golden.py::make_checkpoint_skeleton`; tensors
+    materialised from their recorded shapes) loads through `milan.pretrained`, and our own `serialize()` has the
+    same structure, so checkpoints move both ways."""
+    import json
+    from neuron_descriptions_b200 import milan, synthetic
+    skeleton = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'checkpoint_skeleton.json')))
+
+    def materialise(node):
+        if isinstance(node, list) and len(node) == 3 and node[0] == 'tensor':
+            dtype = getattr(torch, node[2].split('.')[-1])
+            return torch.zeros(node[1], dtype=dtype) if dtype != torch.float32 else torch.full(node[1], 0.01)
+        if isinstance(node, dict):
+            return {key: materialise(value) for key, value in node.items()}
+        if isinstance(node, list):
+            return tuple(materialise(value) for value in node)
+        return node
+
+    payload = materialise(skeleton)
+    assert set(payload) == {'properties', 'children', 'state_dict'}
+    path = tmp_path / 'base.pth'
+    torch.save(payload, path)
+    decoder = milan.pretrained('base', path=path)
+    props = payload['properties']
+    assert decoder.length == props['length'] == 15 and decoder.beam_size == props['beam_size'] == 50
+    assert decoder.strategy == props['strategy'] == 'rerank' and decoder.temperature == props['temperature']
+    assert decoder.indexer.vocab.tokens == tuple(synthetic.synthetic_vocab(40))
+    assert decoder.indexer.start_index == 40 and decoder.indexer.stop_index == 41 and decoder.vocab_size == 44
+    assert decoder.lm is not None and decoder.lm.hidden_size == 512 and decoder.encoder.config == 'resnet101'
+    # every tensor the engine ingests is present under the reference's key names (SURVEY.md section 5)
+    state = decoder.state_dict()
+    assert len(state) == len(payload['state_dict']) == 658
+    for key in ('encoder.mean', 'encoder.encoder.model.layer3.22.conv3.weight', 'lstm.weight_ih', 'output.1.bias',
+                'attend.key_to_hidden.weight', 'lm.lstm.weight_hh_l1', 'lm.output.0.weight'):
+        assert key in state, key
+
+    # our serializer writes the same structure (the tokenizer slot is None on both sides)
+    def structure(node):
+        if torch.is_tensor(node):
+            return ['tensor', list(node.shape), str(node.dtype)]
+        if isinstance(node, dict):
+            return {str(key): structure(value) for key, value in node.items()}
+        if isinstance(node, (tuple, list)):
+            return [structure(value) for value in node]
+        return node
+
+    ours = structure(decoder.serialize())
+    assert ours['children'] == skeleton['children']
+    assert ours['state_dict'] == skeleton['state_dict']
+    ref_props, our_props = skeleton['properties'], ours['properties']
+    assert set(our_props) == set(ref_props)
+    for key in ('embedding_size', 'hidden_size', 'attention_hidden_size', 'dropout', 'length', 'strategy',
+                'temperature', 'beam_size'):
+        assert our_props[key] == ref_props[key], key
+    assert our_props['indexer'] == ref_props['indexer']
+    assert our_props['lm']['properties'] == ref_props['lm']['properties']
+    assert our_props['encoder']['properties']['config'] == ref_props['encoder']['properties']['config']

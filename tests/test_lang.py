@@ -67,3 +67,17 @@ def test_oracle_score_matches_reference_golden(golden_dir):
     np.testing.assert_allclose(O.score(tokenized, feats, sd, VOCAB).numpy(), g['scores_mi'], atol=2e-4)
     np.testing.assert_allclose(O.score(tokenized, feats[:1], sd, VOCAB, mi=False).numpy(), g['scores_one'],
                                atol=2e-4)
+
+
+def test_spatialize_vit_mlp_matches_reference_semantics():
+    """`src/exemplars/transforms.py:55-81`: drop CLS, patches become a square map, units become channels."""
+    from neuron_descriptions_b200.exemplars import transforms
+    hiddens = torch.arange(2 * 17 * 3, dtype=torch.float32).view(2, 17, 3)
+    out = transforms.spatialize_vit_mlp(hiddens)
+    assert out.shape == (2, 3, 4, 4)
+    for b in range(2):
+        for unit in range(3):
+            for patch in range(16):
+                assert out[b, unit, patch // 4, patch % 4] == hiddens[b, 1 + patch, unit]
+    with pytest.raises(AssertionError):
+        transforms.spatialize_vit_mlp(torch.zeros(1, 12, 3))
