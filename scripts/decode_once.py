@@ -1,0 +1,11 @@
+import os, sys, torch
+sys.path.insert(0, '/root/repo')
+from neuron_descriptions_b200 import synthetic
+from neuron_descriptions_b200.engine import Engine
+from oracle.make_golden import synthetic_features
+feats = synthetic_features(64, 15, seed=3).cuda()
+sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0, with_encoder=False)
+engine = Engine(sd, vocab_size=5004, device='cuda:0', max_neurons=64)
+for _ in range(3):
+    out = engine.decode_beam(feats, 15, 50, True, 0.2, group_size=16)
+torch.cuda.synchronize()

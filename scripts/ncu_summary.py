@@ -25,10 +25,12 @@ def to_us(value, unit):
     return {'ns': value / 1e3, 'us': value, 'ms': value * 1e3, 's': value * 1e6}.get(unit, value)
 
 
-def launches(path, out):
+def launches(path, out, limit=None):
     with open(path) as handle:
         lines = [line for line in handle if not line.startswith('==')]
     rows = [row for row in csv.DictReader(lines) if row['Metric Name'] == 'gpu__time_duration.sum']
+    if limit:
+        rows = rows[:int(limit)]  # one step's worth of launches
     total, count = collections.OrderedDict(), collections.Counter()
     for row in rows:
         name = re.sub(r'\(.*', '', row['Kernel Name']).replace('void ', '').replace('unnamed>::', '')
@@ -95,4 +97,4 @@ def traffic(path, out_json):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
