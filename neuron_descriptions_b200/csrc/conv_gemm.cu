@@ -33,13 +33,20 @@ struct SmemLayout {
   static constexpr int kABytes = kGemmBlockM * BK * 2;  // one A plane per stage (BK = 64: 16 KiB, SW128; 32: SW64)
   static constexpr int kBBytes = BLOCK_N * BK * 2;
   static constexpr int kPlanes = SPLIT ? 2 : 1;
-  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  // The 64-byte-k-block variant is the 7x7 stem: its whole weight matrix (7 k-blocks x 64 rows, 56 KB as hi + lo)
+  // stays resident in shared memory for the life of the CTA, the stages carry the A windows only. Re-fetching it
+  // for each of the 94 080 tiles of a 960-image step was a third of the kernel's L2 -> SM traffic.
+  static constexpr bool kResidentB = BK == 32;
+  static constexpr int kResidentKb = kResidentB ? 7 : 0;
+  static constexpr int kResidentBytes = kResidentKb * kPlanes * kBBytes;
+  static constexpr int kStageBytes = kPlanes * (kABytes + (kResidentB ? 0 : kBBytes));
   static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kTileBytes : 0;            // one 64-col chunk
   static constexpr int kResBytes = (EPI == EPI_BF16 && HAS_RES) ? 2 * kPlanes * kTileBytes : 0;  // 2-deep ring
-  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kResBytes) / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kResBytes - kResidentBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarrierBytes = 512;
-  static constexpr int kTotalBytes = kStages * kStageBytes + kStagingBytes + kResBytes + kBarrierBytes + 1024;
+  static constexpr int kTotalBytes =
+      kStages * kStageBytes + kStagingBytes + kResBytes + kResidentBytes + kBarrierBytes + 1024;
   static_assert(kStages >= 2, "not enough shared memory for a pipelined main loop");
   static_assert(kTotalBytes <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -62,13 +69,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages * L::kStageBytes;
   uint8_t* res_smem = staging + L::kStagingBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_smem + L::kResBytes);
+  uint8_t* resident_b = res_smem + L::kResBytes;  // [kResidentKb][hi | lo] weight k-blocks (stem variant only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(resident_b + L::kResidentBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + kTmemBufs;
   uint64_t* res_full_bar = tmem_empty_bar + kTmemBufs;
   uint64_t* res_empty_bar = res_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + 2);
+  uint64_t* resident_bar = res_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resident_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +109,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       mbar_init(&res_full_bar[s], 1);
       mbar_init(&res_empty_bar[s], kEpiThreads);
     }
+    mbar_init(resident_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
@@ -121,7 +131,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = L::kPlanes * (p.a_box_bytes + L::kBBytes);
+      const uint32_t tx_bytes = L::kPlanes * (p.a_box_bytes + (L::kResidentB ? 0 : L::kBBytes));
+      if (L::kResidentB) {  // the whole weight matrix once (n_tiles == 1, num_kb <= kResidentKb: checked at launch)
+        mbar_arrive_expect_tx(resident_bar, static_cast<uint32_t>(num_kb) * L::kPlanes * L::kBBytes);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          uint8_t* dst = resident_b + kb * (L::kPlanes * L::kBBytes);
+          tma_load_2d(dst, &p.tmap_b[0], resident_bar, kb * BK, 0);
+          if (SPLIT) tma_load_2d(dst + L::kBBytes, &p.tmap_b[1], resident_bar, kb * BK, 0);
+        }
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
@@ -148,9 +166,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (SPLIT)
                 tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
             }
-            uint8_t* sb = st + L::kPlanes * kABytes;
-            tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
-            if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+            if (!L::kResidentB) {
+              uint8_t* sb = st + L::kPlanes * kABytes;
+              tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+              if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -164,6 +184,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;  // running accumulator-chunk counter: buffer = cc % kTmemBufs, phase = (cc / kTmemBufs) & 1
+      if (L::kResidentB) mbar_wait(resident_bar, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int kb = 0;
         for (int chunk = 0; chunk < num_chunks; ++chunk, ++cc) {
@@ -178,7 +199,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
-            const uint32_t b_hi = a_hi + L::kPlanes * kABytes;
+            const uint32_t b_hi = L::kResidentB ? smem_u32(resident_b + kb * (L::kPlanes * L::kBBytes))
+                                                : a_hi + L::kPlanes * kABytes;
             const uint64_t da_hi = make_smem_desc_k<BK>(a_hi);
             const uint64_t db_hi = make_smem_desc_k<BK>(b_hi);
             const uint64_t da_lo = make_smem_desc_k<BK>(a_hi + kABytes);
@@ -400,6 +422,11 @@ int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const
   }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
   if (total_tiles <= 0) return 0;
+  if (L::kResidentB) {  // resident weights: one N tile, every k-block of it in the resident region
+    int num_kb = 0;
+    for (int t = 0; t < p.num_taps; ++t) num_kb += p.tap_cb[t] > 0 ? p.tap_cb[t] : p.cin / BK;
+    if (p.n_tiles != 1 || num_kb > L::kResidentKb) return static_cast<int>(cudaErrorInvalidValue);
+  }
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   kernel<<<grid, kNumThreads, L::kTotalBytes, stream>>>(p, skip_flag);
   g_launches.fetch_add(1, std::memory_order_relaxed);
