@@ -23,6 +23,8 @@ import torch
 from torch.utils import data
 
 from neuron_descriptions_b200 import _lib
+from neuron_descriptions_b200 import sharding as neuron_sharding
+from neuron_descriptions_b200.exemplars import sharding
 
 EXACT_CAPACITY = 8192  # columns of the reference sketch's first level (2 * r, r = 4096: tally.py:199-200)
 
@@ -54,10 +56,10 @@ from neuron_descriptions_b200.exemplars.transforms import first, identity  # noq
 class _Tally:
     """Running top-k + quantile state on the device (RunningTopK + RunningQuantile of the reference)."""
 
-    def __init__(self, k: int, device):
+    def __init__(self, k: int, device, first_index: int = 0):
         self.k, self.device = k, device
         self.lib = _lib.load()
-        self.count = 0          # images seen
+        self.count = first_index  # dataset index of the next image (a rank's shard starts at `first_index`)
         self.samples_seen = 0   # activations per unit seen
         self.top_vals = self.top_ids = self.samples = self.hist = None
         self.kept = []          # batches kept while still in the exact regime
@@ -82,29 +84,48 @@ class _Tally:
                                                 self.samples_seen, _stream(self.device)), 'milan_tally_samples')
         else:
             if self.hist is None:  # leaving the exact regime: fold what was kept into the histogram
-                self.hist = torch.zeros(U, 65536, dtype=torch.int32, device=self.device)
-                if self.samples_seen:
-                    kept = self.samples[:, :self.samples_seen].t().contiguous().view(self.samples_seen, U, 1)
-                    _check(self.lib.milan_tally_hist(_ptr(kept), self.samples_seen, U, 1, _ptr(self.hist),
-                                                     _stream(self.device)), 'milan_tally_hist')
-                self.samples = None
+                self._to_histogram()
             _check(self.lib.milan_tally_hist(_ptr(acts), B, U, P, _ptr(self.hist), _stream(self.device)),
                    'milan_tally_hist')
         self.count += B
         self.samples_seen += B * P
 
+    def _to_histogram(self):
+        """Leave the exact regime: fold the kept samples into a fresh histogram."""
+        U = self.samples.shape[0]
+        self.hist = torch.zeros(U, 65536, dtype=torch.int32, device=self.device)
+        if self.samples_seen:
+            kept = self.samples[:, :self.samples_seen].t().contiguous().view(self.samples_seen, U, 1)
+            _check(self.lib.milan_tally_hist(_ptr(kept), self.samples_seen, U, 1, _ptr(self.hist),
+                                             _stream(self.device)), 'milan_tally_hist')
+        self.samples = None
+
     def result(self, quantile: float) -> ActivationStats:
+        """Read-out; with torch.distributed initialised the per-rank statistics are merged first (every rank gets
+        the same answer; see `exemplars/sharding.py`)."""
         U = self.top_vals.shape[0]
-        levels = torch.empty(U, device=self.device)
-        exact = self.hist is None
-        if exact:
-            _check(self.lib.milan_quantile_exact(_ptr(self.samples), U, EXACT_CAPACITY, self.samples_seen,
-                                                 float(quantile), _ptr(levels), _stream(self.device)),
-                   'milan_quantile_exact')
+        top_vals, top_ids = sharding.merge_topk(self.top_vals, self.top_ids)
+        total = sharding.total_count(self.samples_seen, self.device)
+        world, _ = sharding.world_and_rank()
+        # every rank must take the same branch: exact iff ALL samples of all ranks fit the sketch's first level
+        if world > 1:
+            flag = torch.tensor([1 if self.hist is None else 0], device=self.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            exact = bool(flag.item()) and total <= EXACT_CAPACITY
         else:
-            _check(self.lib.milan_quantile_hist(_ptr(self.hist), U, self.samples_seen, float(quantile), _ptr(levels),
+            exact = self.hist is None
+        levels = torch.empty(U, device=self.device)
+        if exact:
+            samples, n = sharding.gather_samples(self.samples, self.samples_seen, EXACT_CAPACITY)
+            _check(self.lib.milan_quantile_exact(_ptr(samples), U, EXACT_CAPACITY, n, float(quantile), _ptr(levels),
+                                                 _stream(self.device)), 'milan_quantile_exact')
+        else:
+            if self.hist is None:
+                self._to_histogram()
+            hist = sharding.sum_histograms(self.hist.clone() if world > 1 else self.hist)
+            _check(self.lib.milan_quantile_hist(_ptr(hist), U, total, float(quantile), _ptr(levels),
                                                 _stream(self.device)), 'milan_quantile_hist')
-        return ActivationStats(self.top_vals, self.top_ids, levels, exact)
+        return ActivationStats(top_vals, top_ids, levels, exact)
 
 
 def activation_masks(maps: torch.Tensor, levels: torch.Tensor, size: int) -> torch.Tensor:
@@ -188,9 +209,12 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
         hiddens = hiddens.to(device)
         return hiddens if unit_index is None else hiddens[:, unit_index]
 
-    # ---- pass 1: tally (tally.tally_topk_and_quantile, tally.py:199-222)
-    tally = _Tally(k, device)
-    loader = data.DataLoader(dataset, batch_size=batch_size, shuffle=False)
+    # ---- pass 1: tally (tally.tally_topk_and_quantile, tally.py:199-222); under torch.distributed every rank
+    # tallies a contiguous range of the images and the statistics are merged in `_Tally.result`
+    world, rank = sharding.world_and_rank()
+    lo, hi = neuron_sharding.shard_range(len(dataset), rank, world)
+    tally = _Tally(k, device, first_index=lo)
+    loader = data.DataLoader(data.Subset(dataset, range(lo, hi)), batch_size=batch_size, shuffle=False)
     for batch in loader:
         batch = batch if isinstance(batch, (list, tuple)) else [batch]
         tally.add(select(compute_topk_and_quantile(*batch)))
@@ -202,8 +226,9 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
     # tally.gather_topk, tally.py:92-124): re-run the model on the needed images only
     ids = stats.ids.cpu()
     n_units = ids.shape[0]
-    needed = sorted(set(ids.view(-1).tolist()))
-    position = {image: i for i, image in enumerate(needed)}
+    needed = sorted(image for image in set(ids.view(-1).tolist()) if image >= 0)
+    needed = needed[slice(*neuron_sharding.shard_range(len(needed), rank, world))]  # this rank's share of pass 2
+    owned = set(needed)
     normalizer = renormalizer if renormalizer is not None else _find_normalizer(dataset)
     mean, std = ((normalizer.mean, normalizer.std) if normalizer is not None else ((0., 0., 0.), (1., 1., 1.)))
     masks = torch.zeros(n_units, k, 1, output_size, output_size, dtype=torch.uint8)
@@ -212,8 +237,9 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
     offset = 0
     wanted = {}  # image -> [(unit, rank)]
     for unit in range(n_units):
-        for rank, image in enumerate(ids[unit].tolist()):
-            wanted.setdefault(image, []).append((unit, rank))
+        for slot, image in enumerate(ids[unit].tolist()):
+            if image in owned:
+                wanted.setdefault(image, []).append((unit, slot))
     for batch in data.DataLoader(subset, batch_size=batch_size, shuffle=False):
         batch = batch if isinstance(batch, (list, tuple)) else [batch]
         hiddens = select(compute_activations(*batch)).float()
@@ -221,17 +247,19 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
         pairs, maps, levels = [], [], []
         for local in range(len(hiddens)):
             image = needed[offset + local]
-            for unit, rank in wanted[image]:
-                pairs.append((unit, rank, local))
+            for unit, slot in wanted[image]:
+                pairs.append((unit, slot, local))
                 maps.append(hiddens[local, unit])
                 levels.append(stats.levels[unit])
         got = activation_masks(torch.stack(maps), torch.stack(levels), output_size).cpu()
-        for (unit, rank, local), mask in zip(pairs, got):
-            masks[unit, rank, 0] = mask
-            images[unit, rank] = bytes_[local]
+        for (unit, slot, local), mask in zip(pairs, got):
+            masks[unit, slot, 0] = mask
+            images[unit, slot] = bytes_[local]
         offset += len(hiddens)
-    del position
-    if save_results and results_dir is not None:
+    if world > 1:  # every slot was filled by exactly one rank
+        masks = sharding.max_bytes(masks.to(device)).cpu()
+        images = sharding.max_bytes(images.to(device)).cpu()
+    if save_results and results_dir is not None and rank == 0:
         numpy.save(f'{results_dir}/images.npy', images.numpy())
         numpy.save(f'{results_dir}/masks.npy', masks.numpy())
         for metadata, name, fmt in ((stats.activations, 'activations', '%.5e'), (stats.ids, 'ids', '%i')):

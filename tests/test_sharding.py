@@ -65,3 +65,68 @@ def test_predict_sharded_two_ranks_gloo(tmp_path, n):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count('ok') == 2
+
+
+def test_exemplar_select_topk_ties_and_empty_slots():
+    from neuron_descriptions_b200.exemplars import sharding as es
+    values = torch.tensor([[1.0, 3.0, 3.0, float('-inf'), 2.0, 3.0]])
+    ids = torch.tensor([[7, 9, 4, -1, 1, 12]])
+    v, i = es.select_topk(values, ids, 4)
+    assert i.tolist() == [[4, 9, 12, 1]] and v.tolist() == [[3.0, 3.0, 3.0, 2.0]]
+    v, i = es.select_topk(values[:, :1], torch.tensor([[-1]]), 2)
+    assert i.tolist() == [[-1]] and v.tolist() == [[float('-inf')]]
+
+
+EXEMPLAR_WORKER = textwrap.dedent('''
+    import os, sys, torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ['MILAN_ROOT'])
+    from neuron_descriptions_b200 import sharding as neuron_sharding
+    from neuron_descriptions_b200.exemplars import sharding as es
+
+    world, rank, _ = neuron_sharding.init_distributed()
+    assert world == 2
+    gen = torch.Generator().manual_seed(0)
+    n, units, k, positions = 23, 5, 4, 6
+    pooled = torch.randn(n, units, generator=gen)
+    pooled[3, 1] = pooled[17, 1] = 9.0            # a tie across the two shards: the earlier image must win
+    samples = torch.randn(n * positions, units, generator=gen)
+    lo, hi = neuron_sharding.shard_range(n, rank, world)
+    # what one rank's tally kernel would hold after its shard
+    local_v, local_i = torch.topk(pooled[lo:hi].t(), k, dim=1)
+    values, ids = es.merge_topk(local_v.contiguous(), (local_i + lo).contiguous())
+    ref_v, ref_i = es.select_topk(pooled.t().contiguous(), torch.arange(n).repeat(units, 1), k)
+    assert torch.equal(ids, ref_i) and torch.equal(values, ref_v), (rank, ids, ref_i)
+    assert ids[1, 0].item() == 3 and ids[1, 1].item() == 17
+    # exact-regime samples: concatenation in rank order, counts differ between the ranks
+    cap = 256
+    kept = torch.zeros(units, cap)
+    mine = samples[lo * positions:hi * positions].t()
+    kept[:, :mine.shape[1]] = mine
+    merged, total = es.gather_samples(kept, mine.shape[1], cap)
+    assert total == n * positions and torch.equal(merged[:, :total], samples.t())
+    assert es.total_count(mine.shape[1], 'cpu') == n * positions
+    # histograms add, byte results take the union
+    hist = torch.zeros(units, 16, dtype=torch.int32)
+    hist[:, rank] = rank + 1
+    assert es.sum_histograms(hist)[:, :2].tolist() == [[1, 2]] * units
+    masks = torch.zeros(4, dtype=torch.uint8)
+    masks[rank * 2] = 1
+    assert es.max_bytes(masks).tolist() == [1, 0, 1, 0]
+    neuron_sharding.finalize_distributed()
+    print('rank', rank, 'ok')
+''')
+
+
+def test_exemplar_statistics_merge_two_ranks_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(EXEMPLAR_WORKER)
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MILAN_ROOT=ROOT, CUDA_VISIBLE_DEVICES='')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count('ok') == 2
