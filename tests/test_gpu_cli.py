@@ -81,3 +81,27 @@ def test_predict_streams_chunks_from_disk(tmp_path):
     again = decoder.predict(dataset, features=feats, strategy='rerank', beam_size=8, batch_size=2,
                             display_progress_as=None)
     assert list(again) == list(ref)
+
+
+def test_compute_exemplars_cli(tmp_path):
+    """`scripts/compute_exemplars.py` (stage 1) on an image folder -> files `TopImagesDataset` reads."""
+    from PIL import Image
+    from scripts import compute_exemplars
+    from neuron_descriptions_b200 import milannotations
+    rng = np.random.default_rng(0)
+    for cls in ('a', 'b'):
+        (tmp_path / 'images' / cls).mkdir(parents=True)
+        for i in range(5):
+            Image.fromarray(rng.integers(0, 256, (260, 300, 3), dtype=np.uint8)).save(tmp_path / 'images' / cls / f'{i}.png')
+    compute_exemplars.main(['resnet18', 'toyset', '--dataset-path', str(tmp_path / 'images'), '--results-root',
+                            str(tmp_path / 'exemplars'), '--layer-names', 'layer4', '--units', '4', '--k', '3',
+                            '--batch-size', '4', '--device', 'cuda:0'])
+    root = tmp_path / 'exemplars' / 'resnet18' / 'toyset'
+    assert sorted(p.name for p in (root / 'layer4').iterdir()) == ['activations.csv', 'ids.csv', 'images.npy',
+                                                                    'masks.npy', 'units.npy']
+    dataset = milannotations.TopImagesDataset(root, layers=['layer4'])
+    assert len(dataset) == 4 and dataset.k == 3
+    sample = dataset[1]
+    assert sample.unit == 1 and sample.images.shape == (3, 3, 224, 224) and sample.masks.shape == (3, 1, 224, 224)
+    ids = np.loadtxt(root / 'layer4' / 'ids.csv', delimiter=',')
+    assert ids.shape == (4, 3) and ids.min() >= 0 and ids.max() < 10
