@@ -43,7 +43,10 @@ struct SmemLayout {
   static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kTileBytes : 0;            // one 64-col chunk
   static constexpr int kResBytes = (EPI == EPI_BF16 && HAS_RES) ? 2 * kPlanes * kTileBytes : 0;  // 2-deep ring
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kResBytes - kResidentBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+#ifndef MILAN_MAX_STAGES
+#define MILAN_MAX_STAGES 8  // (-DMILAN_MAX_STAGES=n: pipeline-depth sensitivity experiments)
+#endif
+  static constexpr int kStages = kStagesRaw > MILAN_MAX_STAGES ? MILAN_MAX_STAGES : kStagesRaw;
   static constexpr int kBarrierBytes = 512;
   static constexpr int kTotalBytes =
       kStages * kStageBytes + kStagingBytes + kResBytes + kResidentBytes + kBarrierBytes + 1024;
