@@ -31,6 +31,7 @@ import torch  # noqa: E402
 METRIC = 'neurons described/sec (k=15, beam=50)'
 UNIT = 'neurons/s'
 K_EXEMPLARS, BEAM, LENGTH, GROUP = 15, 50, 15, 16
+MAX_STEPS_PER_CALL = 8
 CONV_FLOP_PER_NEURON = 2.0 * 7.79935744e9 * K_EXEMPLARS  # 104 convs through layer4
 # every conv input / residual / output tensor touched once as (hi, lo) bf16 planes; the four
 # downsample tensors are never materialised (conv3 + downsample run as one GEMM): 157.5 - 11.6 + 2.1 GB per 64 neurons
@@ -207,29 +208,40 @@ def main():
             dist.all_gather_into_tensor(gathered_scores, scores)
         return tokens
 
-    # value: the exemplars of all K steps resident in HBM (alternating the two batches), one API call.
-    dev_all = (torch.cat([dev[i % 2][0] for i in range(steps)]), torch.cat([dev[i % 2][1] for i in range(steps)]))
+    # value / e2e: the exemplars of the K steps (alternating the two batches) go through the pipelined API in calls
+    # of at most MAX_STEPS_PER_CALL steps, so a large --steps does not need K x 193 MB of pinned / device buffers.
+    per_call = min(steps, MAX_STEPS_PER_CALL)
+    call_steps = [min(per_call, steps - lo) for lo in range(0, steps, per_call)]
+    dev_all = (torch.cat([dev[i % 2][0] for i in range(per_call)]), torch.cat([dev[i % 2][1] for i in range(per_call)]))
+    host_all = (torch.cat([host[i % 2][0] for i in range(per_call)]).pin_memory(),
+                torch.cat([host[i % 2][1] for i in range(per_call)]).pin_memory())
+    gathered_all_tokens = torch.empty(world, nb * per_call, LENGTH, dtype=torch.long, device=device) if world > 1 else None
+    gathered_all_scores = torch.empty(world, nb * per_call, dtype=torch.float32, device=device) if world > 1 else None
+
+    def gather(tokens, scores):
+        if world > 1:
+            n = tokens.shape[0]
+            if n == nb * per_call:
+                dist.all_gather_into_tensor(gathered_all_tokens, tokens.to(device, non_blocking=True))
+                dist.all_gather_into_tensor(gathered_all_scores, scores.to(device, non_blocking=True))
+            else:  # the short last call of an uneven split
+                dist.all_gather_into_tensor(gathered_all_tokens[:, :n].contiguous(), tokens.to(device))
+                dist.all_gather_into_tensor(gathered_all_scores[:, :n].contiguous(), scores.to(device))
 
     def resident_all(engine_):
-        tokens, scores = engine_.describe_device(dev_all[0], dev_all[1], strategy='rerank', length=LENGTH, beam=BEAM,
-                                                 group_size=GROUP, temperature=0.2)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered_all_tokens, tokens)
-            dist.all_gather_into_tensor(gathered_all_scores, scores)
+        for n_steps in call_steps:
+            n = nb * n_steps
+            tokens, scores = engine_.describe_device(dev_all[0][:n], dev_all[1][:n], strategy='rerank', length=LENGTH,
+                                                     beam=BEAM, group_size=GROUP, temperature=0.2)
+            gather(tokens, scores)
         return tokens
 
-    # e2e: the exemplars of all K steps in one pinned host buffer (alternating the two batches), one API call.
-    host_all = (torch.cat([host[i % 2][0] for i in range(steps)]).pin_memory(),
-                torch.cat([host[i % 2][1] for i in range(steps)]).pin_memory())
-    gathered_all_tokens = torch.empty(world, nb * steps, LENGTH, dtype=torch.long, device=device) if world > 1 else None
-    gathered_all_scores = torch.empty(world, nb * steps, dtype=torch.float32, device=device) if world > 1 else None
-
     def e2e_all(engine_):
-        tokens, scores, _ = engine_.describe_host(host_all[0], host_all[1], strategy='rerank', length=LENGTH, beam=BEAM,
-                                                  group_size=GROUP, temperature=0.2)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered_all_tokens, tokens.to(device, non_blocking=True))
-            dist.all_gather_into_tensor(gathered_all_scores, scores.to(device, non_blocking=True))
+        for n_steps in call_steps:
+            n = nb * n_steps
+            tokens, scores, _ = engine_.describe_host(host_all[0][:n], host_all[1][:n], strategy='rerank', length=LENGTH,
+                                                      beam=BEAM, group_size=GROUP, temperature=0.2)
+            gather(tokens, scores)
         return tokens
 
     def barrier():
@@ -316,7 +328,7 @@ def main():
             'precision': ('bf16 hi/lo split operands, 3 tcgen05 MMAs per k-block, fp32 TMEM accumulation (fp32-class '
                           'results; parity-tested)' if args.precision == 'split' else 'plain bf16 operands'),
             'l2': 'inputs larger than L2: 193 MB of fresh exemplars + >10 GB of activations per step vs 126 MB L2',
-            'call': f'one milan_describe_device call over the {steps} steps ({nb * steps} resident neurons)',
+            'call': f'milan_describe_device over the {steps} steps ({nb * steps} resident neurons) in {len(call_steps)} call(s)',
         },
         'roofline': {
             'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
@@ -336,8 +348,8 @@ def main():
                                'step_total_profiled_pass': ms_prof / steps},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nb * K_EXEMPLARS * 4 * 224 * 224,
                 'd2h_bytes_per_step': nb * (LENGTH * 8 + 4 + 4), 'ms_per_step': ms_e2e / steps,
-                'call': f'one milan_describe_host call over the {steps} steps ({nb * steps} neurons, pinned host '
-                        'buffers); H2D of chunk i+1 overlaps the compute of chunk i'},
+                'call': f'milan_describe_host over the {steps} steps ({nb * steps} neurons, pinned host buffers) in '
+                        f'{len(call_steps)} call(s); H2D of chunk i+1 overlaps the compute of chunk i'},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'clocks_e2e': clocks_e2e,
