@@ -15,6 +15,7 @@
 #include "ptx.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -57,15 +58,25 @@ struct SmemLayout {
 // byte offset of 16-byte chunk j of row r inside a [128][128 B] tile with the TMA/UMMA 128-byte swizzle
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
 
-template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK, bool WIDE>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p,
                                                                    const int* __restrict__ skip_flag) {
   if (skip_flag != nullptr && *skip_flag != 0) return;  // uniform: whole grid exits before touching any barrier
   using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES, BK>;
   constexpr int kABytes = L::kABytes;
   constexpr int kStages = L::kStages;
-  constexpr int kTmemBufs = 4;                 // accumulator ring
-  constexpr uint32_t kTmemCols = kTmemBufs * BLOCK_N;  // 512 or 256 columns (power of two)
+  // WIDE (split mode, long-K problems without a residual): TWO MMAs per K step instead of three. The hi and lo planes
+  // of B are adjacent in shared memory, so A_hi x [B_hi; B_lo]^T is one N = 2 * BLOCK_N instruction whose result is
+  // [hi*hi | hi*lo] side by side, and A_lo x B_hi^T accumulates into the first half; the epilogue adds the halves.
+  // A 128 x N x 16 MMA costs the same ~60 ns for every N <= 128 (csrc/probe_mma_rate.cu): the main loop pays per
+  // instruction, not per FLOP. Short-K / residual problems keep three MMAs and the deeper accumulator ring: their
+  // epilogue is the critical path and would only see the doubled TMEM reads.
+  static_assert(!WIDE || SPLIT, "the wide form only exists in split mode");
+  constexpr bool wide = WIDE;
+  constexpr int acc_cols = WIDE ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
+  constexpr int kTmemBufs = (512 / acc_cols) < 4 ? (512 / acc_cols) : 4;  // accumulator ring
+  constexpr int tmem_bufs = kTmemBufs;
+  constexpr uint32_t kTmemCols = kTmemBufs * acc_cols;  // 512 or 256 columns (power of two)
   constexpr int kChunks = BLOCK_N / 64;        // 64-column epilogue chunks per tile
 
   extern __shared__ uint8_t smem_raw[];
@@ -161,9 +172,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             uint8_t* st = smem + stage * L::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             if (p.stem_mode) {
-              // filter row `tap`: window of padded row 2*(h0 + tap/2) + (tap & 1): coords (k, ow, parity, pair, n)
-              tma_load_5d(st, &p.tmap_a[0][0], &full_bar[stage], 0, w0, p.tap_dw[tap], ch, n0);
-              if (SPLIT) tma_load_5d(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 0, w0, p.tap_dw[tap], ch, n0);
+              // filter row `tap`: the raw 22-pixel segments of padded rows 2*(h + tap/2) + (tap & 1), h = h0..h0+15,
+              // that the tile's 8 output columns read; coords (element of the row, parity, row pair, n)
+              tma_load_4d(st, &p.tmap_a[0][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
+              if (SPLIT) tma_load_4d(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
             } else {
               tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * BK, cw, ch, n0);
               if (SPLIT)
@@ -184,6 +196,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_16bit(kGemmBlockM, BLOCK_N, p.fp16_operands ? 0u : 1u);
+      const uint32_t idesc_wide = make_idesc_16bit(kGemmBlockM, 2 * BLOCK_N, p.fp16_operands ? 0u : 1u);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t cc = 0;  // running accumulator-chunk counter: buffer = cc % kTmemBufs, phase = (cc / kTmemBufs) & 1
@@ -191,11 +204,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int kb = 0;
         for (int chunk = 0; chunk < num_chunks; ++chunk, ++cc) {
-          const int as = cc % kTmemBufs;
-          const uint32_t aphase = (cc / kTmemBufs) & 1;
+          const int as = cc % tmem_bufs;
+          const uint32_t aphase = (cc / tmem_bufs) & 1;
           mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+          const uint32_t tmem_d = tmem_base + as * acc_cols;
           const int kb_end = (kb + kb_per_chunk < num_kb) ? kb + kb_per_chunk : num_kb;
           const int kb_first = kb;
           for (; kb < kb_end; ++kb) {
@@ -204,17 +217,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
             const uint32_t b_hi = L::kResidentB ? smem_u32(resident_b + kb * (L::kPlanes * L::kBBytes))
                                                 : a_hi + L::kPlanes * kABytes;
-            const uint64_t da_hi = make_smem_desc_k<BK>(a_hi);
+            // BK == 32 is the stem: A is not an im2col tile but the raw input rows, addressed as overlapping windows
+            const uint64_t da_hi = BK == 32 ? make_smem_desc_stem_rows(a_hi) : make_smem_desc_k<BK>(a_hi);
             const uint64_t db_hi = make_smem_desc_k<BK>(b_hi);
-            const uint64_t da_lo = make_smem_desc_k<BK>(a_hi + kABytes);
             const uint64_t db_lo = make_smem_desc_k<BK>(b_hi + L::kBBytes);
+            const uint64_t da_lo =
+                BK == 32 ? make_smem_desc_stem_rows(a_hi + kABytes) : make_smem_desc_k<BK>(a_hi + kABytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
-              umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
-              if (SPLIT) {
+              const uint32_t accumulate = (kb > kb_first || k > 0) ? 1u : 0u;
+              if (wide) {  // db_hi spans the hi rows and, right behind them, the lo rows
+                umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc_wide, accumulate);
                 umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
-                umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+              } else {
+                umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate);
+                if (SPLIT) {
+                  umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                  umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                }
               }
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -278,11 +299,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       // ---- gather the accumulator: this thread owns columns c*64 + group*32 + [0,32) of row `row`
       float v[kChunks][32];
       for (int chunk = 0; chunk < num_chunks; ++chunk, ++cc) {
-        const int as = cc % kTmemBufs;
-        const uint32_t aphase = (cc / kTmemBufs) & 1;
+        const int as = cc % tmem_bufs;
+        const uint32_t aphase = (cc / tmem_bufs) & 1;
         mbar_wait(&tmem_full_bar[as], aphase);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + group * 32;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * acc_cols + group * 32;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
           uint32_t acc[32];
@@ -292,6 +313,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[c][j] = __uint_as_float(acc[j]);
           } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c][j] += __uint_as_float(acc[j]);
+          }
+          if (wide) {  // + the hi*lo half of the buffer
+            tmem_ld_32x32(taddr + BLOCK_N + c * 64, acc);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[c][j] += __uint_as_float(acc[j]);
           }
@@ -409,10 +436,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_all_launches{0};
 
-template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK>
+template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK, bool WIDE>
 int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
   using L = SmemLayout<BLOCK_N, SPLIT, EPI, HAS_RES, BK>;
-  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI, HAS_RES, BK>;
+  auto kernel = conv_gemm_kernel<BLOCK_N, SPLIT, EPI, HAS_RES, BK, WIDE>;
   static bool configured = false;
   static std::mutex mu;
   {
@@ -447,21 +474,39 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
                      cudaStream_t stream, const int* skip_flag) {
   const bool res = p.has_res != 0;
   const int bk = p.block_k == 32 ? 32 : 64;
-#define MILAN_DISPATCH(BN, SP, EP, RS, BKV)                                                  \
-  if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV)       \
-    return launch_impl<BN, SP, EP, RS, BKV>(p, num_sms, stream, skip_flag);
-  MILAN_DISPATCH(128, true, EPI_BF16, false, 64)
-  MILAN_DISPATCH(128, true, EPI_BF16, true, 64)
-  MILAN_DISPATCH(128, false, EPI_BF16, false, 64)
-  MILAN_DISPATCH(128, false, EPI_BF16, true, 64)
-  MILAN_DISPATCH(64, true, EPI_BF16, false, 64)
-  MILAN_DISPATCH(64, false, EPI_BF16, false, 64)
-  MILAN_DISPATCH(64, true, EPI_BF16, true, 64)    // BasicBlock conv2 of layer1 (resnet18/34): 64 outputs + residual
-  MILAN_DISPATCH(64, false, EPI_BF16, true, 64)
-  MILAN_DISPATCH(64, true, EPI_BF16, false, 32)   // stem: 64-byte k-blocks (SWIZZLE_64B)
-  MILAN_DISPATCH(64, false, EPI_BF16, false, 32)
-  MILAN_DISPATCH(128, true, EPI_F32, false, 64)
-  MILAN_DISPATCH(128, false, EPI_F32, false, 64)
+  // Two wide MMAs per K step (kernel comment) when the main loop, not the epilogue, is the long pole.
+  bool wide = false;
+  if (split != 0 && !res) {
+    int num_kb = 0;
+    for (int t = 0; t < p.num_taps; ++t) num_kb += p.tap_cb[t] > 0 ? p.tap_cb[t] : p.cin / bk;
+    static const int min_k = [] {
+      const char* e = getenv("MILAN_WIDE_SPLIT_MIN_K");  // experiment knob; 0 disables the wide form
+      return e != nullptr ? atoi(e) : 256;  // measured: 256 > 512 > 1024 > off (bench.py, same box)
+    }();
+    // fp32-output GEMMs (decoder / LM) store 4 bytes per element from the epilogue: only the K = 4544 LSTM input GEMM is
+    // main-loop-bound (ncu, one decode step: K = 512 GEMMs 53 -> 62 us with the wide form, K = 4544 172 -> 160 us)
+    const int need_k = epilogue == EPI_F32 ? 4 * min_k : min_k;
+    wide = min_k > 0 && (bk == 32 || num_kb * bk >= need_k);
+  }
+#define MILAN_DISPATCH(BN, SP, EP, RS, BKV, WD)                                                          \
+  if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV && wide == WD)     \
+    return launch_impl<BN, SP, EP, RS, BKV, WD>(p, num_sms, stream, skip_flag);
+  MILAN_DISPATCH(128, true, EPI_BF16, false, 64, false)
+  MILAN_DISPATCH(128, true, EPI_BF16, false, 64, true)
+  MILAN_DISPATCH(128, true, EPI_BF16, true, 64, false)
+  MILAN_DISPATCH(128, false, EPI_BF16, false, 64, false)
+  MILAN_DISPATCH(128, false, EPI_BF16, true, 64, false)
+  MILAN_DISPATCH(64, true, EPI_BF16, false, 64, false)
+  MILAN_DISPATCH(64, true, EPI_BF16, false, 64, true)
+  MILAN_DISPATCH(64, false, EPI_BF16, false, 64, false)
+  MILAN_DISPATCH(64, true, EPI_BF16, true, 64, false)    // BasicBlock conv2 of layer1 (resnet18/34): 64 outputs + residual
+  MILAN_DISPATCH(64, false, EPI_BF16, true, 64, false)
+  MILAN_DISPATCH(64, true, EPI_BF16, false, 32, true)    // stem: raw-row A windows, 64-byte k-blocks of B (SWIZZLE_64B)
+  MILAN_DISPATCH(64, true, EPI_BF16, false, 32, false)
+  MILAN_DISPATCH(64, false, EPI_BF16, false, 32, false)
+  MILAN_DISPATCH(128, true, EPI_F32, false, 64, false)
+  MILAN_DISPATCH(128, true, EPI_F32, false, 64, true)
+  MILAN_DISPATCH(128, false, EPI_F32, false, 64, false)
 #undef MILAN_DISPATCH
   return static_cast<int>(cudaErrorInvalidValue);
 }
@@ -506,7 +551,9 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, s,
                   b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  swizzle_bytes == 0    ? CU_TENSOR_MAP_SWIZZLE_NONE
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                        : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -36,7 +36,7 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap tmap_b[2];     // [hi|lo]
   CUtensorMap tmap_out[2];   // [hi|lo] EPI_BF16: output tensor, box (64, box_w, box_h, box_n), TMA store
   CUtensorMap tmap_res[2];   // [hi|lo] EPI_BF16 + residual: same geometry as tmap_out, TMA load
-  int stem_mode;             // 1: A is the 5-D overlapping-window map of the 7x7/2 stem (see build_stem_params)
+  int stem_mode;             // 1: A is the raw-row map of the 7x7/2 stem, windows formed by the MMA descriptor (see build_stem_params)
   int has_res;               // residual add in the epilogue
   int block_k;               // k-block width in elements: 64 (default, 128B swizzle) or 32 (stem, 64B swizzle)
   int kb_per_chunk;          // k-blocks accumulated in TMEM before promotion to fp32 registers (0 = all)

@@ -244,25 +244,26 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
     p->tap_dw[r] = static_cast<int8_t>(r & 1);   // row parity coordinate
     p->tap_dh[r] = static_cast<int8_t>(r >> 1);  // row-pair offset
   }
-  int bw, bh, bn;
-  choose_box(O, O, N, &bw, &bh, &bn);
+  // 8 x 16 output pixels per tile: one 8-row MMA group per image row, so the raw row segments the filter row reads
+  // (8 * 2 + 6 = 22 pixels = 176 B) sit at a constant pitch in shared memory (make_smem_desc_stem_rows).
+  const int bw = 8, bh = 16, bn = 1;
   p->box_w = bw; p->box_h = bh; p->box_n = bn;
   p->tiles_w = (O + bw - 1) / bw; p->tiles_h = (O + bh - 1) / bh; p->tiles_n = (N + bn - 1) / bn;
   p->out_w = O; p->out_h = O; p->out_n = N;
-  p->a_box_bytes = static_cast<uint32_t>(bw) * bh * bn * kStemBlockK * 2;
+  const uint32_t seg_elems = (2 * bw + 6) * 4;  // 88 bf16 = 176 B
+  p->a_box_bytes = seg_elems * 2 * bh;
   const uint64_t P = static_cast<uint64_t>(kStemPadW) * 4 * 2;  // padded row pitch in bytes
   const __nv_bfloat16* imgs[2] = {img_hi, img_lo};
   const __nv_bfloat16* ws[2] = {w_hi, w_lo};
   __nv_bfloat16* outs[2] = {out_hi, out_lo};
   const int np = split ? 2 : 1;
   for (int hl = 0; hl < np; ++hl) {
-    // dims: (k: 32 elems = 8 px x 4 ch, ow, row parity, row pair, n)
-    const uint64_t dims[5] = {kStemBlockK, static_cast<uint64_t>(O), 2, static_cast<uint64_t>(kStemPadH / 2),
+    // dims: (element of a padded row: pixel * 4 + channel, row parity, row pair, n); no swizzle
+    const uint64_t dims[4] = {static_cast<uint64_t>(kStemPadW) * 4, 2, static_cast<uint64_t>(kStemPadH / 2),
                               static_cast<uint64_t>(N)};
-    const uint64_t strides[4] = {16, P, 2 * P, static_cast<uint64_t>(kStemPadH) * P};
-    const uint32_t box[5] = {kStemBlockK, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh),
-                             static_cast<uint32_t>(bn)};
-    int rc = make_tmap_nd(&p->tmap_a[hl][0], imgs[hl], 5, dims, strides, box, kStemBlockK * 2);
+    const uint64_t strides[3] = {P, 2 * P, static_cast<uint64_t>(kStemPadH) * P};
+    const uint32_t box[4] = {seg_elems, 1, static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    int rc = make_tmap_nd(&p->tmap_a[hl][0], imgs[hl], 4, dims, strides, box, 0);
     if (rc) return rc;
     for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];
     rc = make_tmap_2d(&p->tmap_b[hl], ws[hl], kStemKTotal, 64, kStemKTotal * 2, 64, kStemBlockK);

@@ -167,6 +167,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
   return d;
 }
+// The 7x7/2 stem reads its A operand straight from raw NHWC4 input rows: output pixel x of a filter row needs the 8
+// input pixels (64 B) starting at pixel 2x, i.e. byte 16 x of the row. In the un-swizzled K-major layout the 8 rows of
+// a core matrix are 16 B apart and LBO is the distance to the next 16-byte K chunk; with LBO = 16 as well, row m reads
+// bytes [16 m, 16 m + 64): overlapping windows, im2col done by the descriptor (csrc/probe_ts_mma.cu checks it).
+// SBO = 176: one 8-pixel output group per image row, whose raw segment is 8 * 16 + 48 bytes.
+constexpr uint32_t kStemSegBytes = 176;
+__device__ __forceinline__ uint64_t make_smem_desc_stem_rows(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(16 >> 4) << 16;             // leading byte offset
+  d |= static_cast<uint64_t>(kStemSegBytes >> 4) << 32;  // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;                                              // swizzle mode 0
+}
 template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t smem_addr) {
   return BK == 64 ? make_smem_desc_sw128(smem_addr) : make_smem_desc_sw64(smem_addr);

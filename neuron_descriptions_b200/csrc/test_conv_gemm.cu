@@ -185,7 +185,7 @@ static int run_case(const Case& c, int num_sms) {
   return ok ? 0 : 1;
 }
 
-// 7x7 stride-2 stem through the 5-D overlapping-window tensor map vs a direct CPU convolution.
+// 7x7 stride-2 stem (raw input rows + overlapping-window MMA descriptor) vs a direct CPU convolution.
 static int run_stem(int N, int split, int num_sms) {
   std::mt19937 rng(99);
   std::normal_distribution<float> nd(0.f, 1.f);

@@ -64,13 +64,15 @@ def full(path, out):
 
 
 
-def traffic(path, out_json):
+def traffic(path, out_json, kernel='conv_gemm_kernel', limit=100):
     """ncu csv with dram__bytes_{read,write}.sum + gpu__time_duration.sum + tensor pipe % for every conv launch of a
     step -> profiles/conv_traffic.json (mean DRAM bytes per launch, consumed by bench.py's roofline.traffic)."""
     import json
     with open(path) as handle:
         lines = [line for line in handle if not line.startswith('==')]
-    rows = list(csv.DictReader(lines))
+    rows = [row for row in csv.DictReader(lines) if kernel in row['Kernel Name']]
+    keep = list(collections.OrderedDict((row['ID'], None) for row in rows))[:int(limit)]  # the encoder's launches
+    rows = [row for row in rows if row['ID'] in set(keep)]
     per = collections.defaultdict(dict)
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     for row in rows:
@@ -96,5 +98,49 @@ def traffic(path, out_json):
     print(json.dumps(result, indent=1))
 
 
+def layers(path, out):
+    """Same csv as `traffic`: one line per encoder conv launch of the resnet101 step, in execution order
+    (stem, then conv1 / conv2 / conv3 of every bottleneck; the x.0 blocks run conv3 + downsample as one launch)."""
+    with open(path) as handle:
+        lines = [line for line in handle if not line.startswith('==')]
+    per = collections.OrderedDict()
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for row in csv.DictReader(lines):
+        if 'conv_gemm_kernel' not in row['Kernel Name']:
+            continue
+        value = float(row['Metric Value'].replace(',', ''))
+        name = row['Metric Name']
+        if name.startswith('dram__bytes'):
+            value *= scale.get(row['Metric Unit'], 1.0)
+        elif name == 'gpu__time_duration.sum':
+            value = to_us(row['Metric Value'], row['Metric Unit'])
+        per.setdefault(row['ID'], {})[name] = value
+    names = ['stem 7x7/2 3->64']
+    for li, (blocks, planes) in enumerate(((3, 64), (4, 128), (23, 256), (3, 512)), start=1):
+        for b in range(blocks):
+            stride = '/2' if (b == 0 and li > 1) else ''
+            names.append(f'layer{li}.{b}.conv1 1x1 ->{planes}')
+            names.append(f'layer{li}.{b}.conv2 3x3{stride} ->{planes}')
+            names.append(f'layer{li}.{b}.conv3' + ('+downsample' if b == 0 else '') + f' 1x1 ->{planes * 4}'
+                         + ('' if b == 0 else ' +res'))
+    rows = list(per.values())[:len(names)]
+    tensor_key = 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'
+    with open(out, 'w') as handle:
+        handle.write('# ncu --metrics gpu__time_duration.sum,' + tensor_key + ',dram__bytes_read.sum,dram__bytes_write.sum '
+                     '--clock-control none\n# one bench step (64 neurons = 960 images): the encoder conv launches in '
+                     f'execution order ({path})\n')
+        handle.write(f'{"conv":44s} {"us":>9s} {"tensor%":>8s} {"rd MB":>8s} {"wr MB":>8s} {"DRAM GB/s":>10s}\n')
+        tot = collections.Counter()
+        for name, v in zip(names, rows):
+            t = v.get('gpu__time_duration.sum', 0.0)
+            rd, wr = v.get('dram__bytes_read.sum', 0.0), v.get('dram__bytes_write.sum', 0.0)
+            handle.write(f'{name:44s} {t:9.1f} {v.get(tensor_key, 0.0):8.1f} {rd / 1e6:8.0f} {wr / 1e6:8.0f} '
+                         f'{(rd + wr) / max(t, 1e-9) / 1e3:10.0f}\n')
+            tot['t'] += t; tot['rd'] += rd; tot['wr'] += wr; tot['tw'] += t * v.get(tensor_key, 0.0)
+        handle.write(f'{"TOTAL":44s} {tot["t"]:9.1f} {tot["tw"] / max(tot["t"], 1e-9):8.1f} {tot["rd"] / 1e6:8.0f} '
+                     f'{tot["wr"] / 1e6:8.0f} {(tot["rd"] + tot["wr"]) / max(tot["t"], 1e-9) / 1e3:10.0f}\n')
+    print(open(out).read()[-400:])
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])
+    {'launches': launches, 'full': full, 'traffic': traffic, 'layers': layers}[sys.argv[1]](*sys.argv[2:])
