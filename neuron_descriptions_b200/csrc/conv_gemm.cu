@@ -485,7 +485,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     }();
     // fp32-output GEMMs (decoder / LM) store 4 bytes per element from the epilogue: only the K = 4544 LSTM input GEMM is
     // main-loop-bound (ncu, one decode step: K = 512 GEMMs 53 -> 62 us with the wide form, K = 4544 172 -> 160 us)
-    const int need_k = epilogue == EPI_F32 ? 4 * min_k : min_k;
+    const int need_k = epilogue == EPI_F32 ? 8 * min_k : min_k;
     wide = min_k > 0 && (bk == 32 || num_kb * bk >= need_k);
   }
 #define MILAN_DISPATCH(BN, SP, EP, RS, BKV, WD)                                                          \
