@@ -170,7 +170,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           for (int cb = 0; cb < tap_blocks; ++cb, kcoord += BK) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * L::kStageBytes;
+#ifdef MILAN_PROBE_SKIP  // fill-rate experiments: 1 = no B loads, 2 = no A loads, 3 = neither
+            const bool probe_a = (MILAN_PROBE_SKIP & 2) == 0, probe_b = (MILAN_PROBE_SKIP & 1) == 0;
+            mbar_arrive_expect_tx(&full_bar[stage], L::kPlanes * ((probe_a ? p.a_box_bytes : 0u) +
+                                                                   ((probe_b && !L::kResidentB) ? L::kBBytes : 0u)));
+            if (!probe_a) {
+            } else
+#else
+            constexpr bool probe_b = true;
             mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+#endif
             if (p.stem_mode) {
               // filter row `tap`: the raw 22-pixel segments of padded rows 2*(h + tap/2) + (tap & 1), h = h0..h0+15,
               // that the tile's 8 output columns read; coords (element of the row, parity, row pair, n)
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (SPLIT)
                 tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
             }
-            if (!L::kResidentB) {
+            if (!L::kResidentB && probe_b) {
               uint8_t* sb = st + L::kPlanes * kABytes;
               tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
               if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
