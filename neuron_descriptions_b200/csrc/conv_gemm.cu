@@ -142,16 +142,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {  // all 32 lanes, uniform control flow; elect.sync inside the helpers picks the issuing lane
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = L::kPlanes * (p.a_box_bytes + (L::kResidentB ? 0 : L::kBBytes));
       if (L::kResidentB) {  // the whole weight matrix once (n_tiles == 1, num_kb <= kResidentKb: checked at launch)
-        mbar_arrive_expect_tx(resident_bar, static_cast<uint32_t>(num_kb) * L::kPlanes * L::kBBytes);
+        mbar_arrive_expect_tx_elect(resident_bar, static_cast<uint32_t>(num_kb) * L::kPlanes * L::kBBytes);
         for (int kb = 0; kb < num_kb; ++kb) {
           uint8_t* dst = resident_b + kb * (L::kPlanes * L::kBBytes);
-          tma_load_2d(dst, &p.tmap_b[0], resident_bar, kb * BK, 0);
-          if (SPLIT) tma_load_2d(dst + L::kBBytes, &p.tmap_b[1], resident_bar, kb * BK, 0);
+          tma_load_2d_elect(dst, &p.tmap_b[0], resident_bar, kb * BK, 0);
+          if (SPLIT) tma_load_2d_elect(dst + L::kBBytes, &p.tmap_b[1], resident_bar, kb * BK, 0);
         }
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -172,28 +172,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             uint8_t* st = smem + stage * L::kStageBytes;
 #ifdef MILAN_PROBE_SKIP  // fill-rate experiments: 1 = no B loads, 2 = no A loads, 3 = neither
             const bool probe_a = (MILAN_PROBE_SKIP & 2) == 0, probe_b = (MILAN_PROBE_SKIP & 1) == 0;
-            mbar_arrive_expect_tx(&full_bar[stage], L::kPlanes * ((probe_a ? p.a_box_bytes : 0u) +
+            mbar_arrive_expect_tx_elect(&full_bar[stage], L::kPlanes * ((probe_a ? p.a_box_bytes : 0u) +
                                                                    ((probe_b && !L::kResidentB) ? L::kBBytes : 0u)));
             if (!probe_a) {
             } else
 #else
             constexpr bool probe_b = true;
-            mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            mbar_arrive_expect_tx_elect(&full_bar[stage], tx_bytes);
 #endif
             if (p.stem_mode) {
               // filter row `tap`: the raw 22-pixel segments of padded rows 2*(h + tap/2) + (tap & 1), h = h0..h0+15,
               // that the tile's 8 output columns read; coords (element of the row, parity, row pair, n)
-              tma_load_4d(st, &p.tmap_a[0][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
-              if (SPLIT) tma_load_4d(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
+              tma_load_4d_elect(st, &p.tmap_a[0][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
+              if (SPLIT) tma_load_4d_elect(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
             } else {
-              tma_load_4d(st, &p.tmap_a[0][plane], &full_bar[stage], cb * BK, cw, ch, n0);
+              tma_load_4d_elect(st, &p.tmap_a[0][plane], &full_bar[stage], cb * BK, cw, ch, n0);
               if (SPLIT)
-                tma_load_4d(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
+                tma_load_4d_elect(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
             }
             if (!L::kResidentB && probe_b) {
               uint8_t* sb = st + L::kPlanes * kABytes;
-              tma_load_2d(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
-              if (SPLIT) tma_load_2d(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+              tma_load_2d_elect(sb, &p.tmap_b[0], &full_bar[stage], kcoord, n_tile * BLOCK_N);
+              if (SPLIT) tma_load_2d_elect(sb + L::kBBytes, &p.tmap_b[1], &full_bar[stage], kcoord, n_tile * BLOCK_N);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -203,7 +203,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // All 32 lanes run this loop with uniform control flow; elect.sync inside the helpers picks the issuing lane
+    // (see umma_bf16_elect in ptx.cuh: a divergent single-thread region costs ~120 cycles per MMA in operand shuffling).
+    {
       const uint32_t idesc = make_idesc_16bit(kGemmBlockM, BLOCK_N, p.fp16_operands ? 0u : 1u);
       const uint32_t idesc_wide = make_idesc_16bit(kGemmBlockM, 2 * BLOCK_N, p.fp16_operands ? 0u : 1u);
       int stage = 0;
@@ -237,18 +239,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
               const uint32_t accumulate = (kb > kb_first || k > 0) ? 1u : 0u;
               if (wide) {  // db_hi spans the hi rows and, right behind them, the lo rows
-                umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc_wide, accumulate);
-                umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                umma_bf16_elect(tmem_d, da_hi + koff, db_hi + koff, idesc_wide, accumulate);
+                umma_bf16_elect(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
               } else {
-                umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate);
+                umma_bf16_elect(tmem_d, da_hi + koff, db_hi + koff, idesc, accumulate);
                 if (SPLIT) {
-                  umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
-                  umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                  umma_bf16_elect(tmem_d, da_lo + koff, db_hi + koff, idesc, 1u);
+                  umma_bf16_elect(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
                 }
               }
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-            if (kb == kb_end - 1) umma_commit(&tmem_full_bar[as]);
+            umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kb == kb_end - 1) umma_commit_elect(&tmem_full_bar[as]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     __syncwarp();
   } else if (warp == 10) {
     // ------------------------------------------------------------ residual prefetcher
-    if (EPI == EPI_BF16 && HAS_RES && lane == 0) {
+    if (EPI == EPI_BF16 && HAS_RES) {  // all lanes, uniform
       int rb = 0;
       uint32_t rphase = 0;
       const uint32_t tx_bytes = L::kPlanes * p.a_box_bytes;
@@ -272,10 +274,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           if (col0 >= p.cout) break;
           mbar_wait(&res_empty_bar[rb], rphase ^ 1);
           uint8_t* dst = res_smem + rb * (L::kPlanes * kTileBytes);
-          mbar_arrive_expect_tx(&res_full_bar[rb], tx_bytes);
-          tma_load_4d(dst, &p.tmap_res[0], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+          mbar_arrive_expect_tx_elect(&res_full_bar[rb], tx_bytes);
+          tma_load_4d_elect(dst, &p.tmap_res[0], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
           if (SPLIT)
-            tma_load_4d(dst + kTileBytes, &p.tmap_res[1], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h,
+            tma_load_4d_elect(dst + kTileBytes, &p.tmap_res[1], &res_full_bar[rb], col0, tw * p.box_w, th * p.box_h,
                         tn * p.box_n);
           if (++rb == 2) { rb = 0; rphase ^= 1; }
         }
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
     const int group = (warp - 2) >> 2;     // which 32-column half of each 64-column chunk
     const int row = quarter * 32 + lane;
-    const bool leader = (warp == 2 && lane == 0);
+    const bool leader = warp == 2;  // the warp whose elected lane issues the TMA stores (warp-uniform calls)
     uint32_t cc = 0;
     int rb = 0;
     uint32_t rphase = 0;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const bool active = col0 < p.cout;  // uniform across the CTA
           if (active && HAS_RES) mbar_wait(&res_full_bar[rb], rphase);
           // previous TMA store must have finished reading the staging tile before it is overwritten
-          if (leader) tma_store_wait_read<0>();
+          if (leader) tma_store_wait_read_elect<0>();
           named_bar_sync(1, kEpiThreads);
           if (active) {
             const uint8_t* rsrc = res_smem + rb * (L::kPlanes * kTileBytes);
@@ -391,9 +393,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           fence_proxy_async();  // make the generic-proxy smem writes visible to the TMA engine
           named_bar_sync(1, kEpiThreads);
           if (leader && active) {
-            tma_store_4d(&p.tmap_out[0], staging, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
-            if (SPLIT) tma_store_4d(&p.tmap_out[1], staging + kTileBytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
-            tma_store_commit();
+            tma_store_4d_elect(&p.tmap_out[0], staging, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+            if (SPLIT)
+              tma_store_4d_elect(&p.tmap_out[1], staging + kTileBytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+            tma_store_commit_elect();
           }
         }
       } else {  // EPI_F32: direct fp32 stores, 128 B contiguous per thread per 32-column chunk
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         }
       }
     }
-    if (EPI == EPI_BF16 && leader) tma_store_wait_all<0>();  // all stores complete before the CTA exits
+    if (EPI == EPI_BF16 && leader) tma_store_wait_all_elect<0>();  // all stores complete before the CTA exits
   }
 
   tcgen05_fence_before();
@@ -495,7 +498,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     // fp32-output GEMMs (decoder / LM) store 4 bytes per element from the epilogue: only the K = 4544 LSTM input GEMM is
     // main-loop-bound (ncu, one decode step: K = 512 GEMMs 53 -> 62 us with the wide form, K = 4544 172 -> 160 us)
     const int need_k = epilogue == EPI_F32 ? 8 * min_k : min_k;
-    wide = min_k > 0 && (bk == 32 || num_kb * bk >= need_k);
+    wide = min_k > 0 && num_kb * bk >= need_k;  // (the stem, K = 224, stays on three MMAs: 0.370 vs 0.382 ms)
   }
 #define MILAN_DISPATCH(BN, SP, EP, RS, BKV, WD)                                                          \
   if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV && wide == WD)     \

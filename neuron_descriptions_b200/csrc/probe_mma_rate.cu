@@ -23,6 +23,64 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+// Warp-uniform issue: every lane of the warp runs the loop (so ptxas can keep descriptors in uniform registers) and
+// elect.sync inside the asm picks the one lane that issues.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) rate_kernel_uniform(int n, int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_s = smem;
+  uint8_t* b_s = smem + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u + ((i * 2654435761u) & 0x00FF00FFu);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x < 32) {  // whole warp, uniform
+    const uint32_t idesc = make_idesc_16bit(128, n, 1u);
+    const uint64_t da = make_smem_desc_sw128(smem_u32(a_s));
+    const uint64_t db = make_smem_desc_sw128(smem_u32(b_s));
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_elect(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
+    }
+    if (threadIdx.x == 0) {
+      umma_commit(&bars[0]);
+      mbar_wait(&bars[0], 0);
+      cycles[blockIdx.x] = clock64() - t0;
+    }
+    __syncwarp();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // mode 0: SS; 1: TS; 2: SS with A and B un-swizzled "raw window" descriptors (LBO 16) for A
 __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int mode, int ndst, int iters, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
@@ -36,6 +94,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int mode, int ndst,
   fence_proxy_async();
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc(tmem_ptr, 512);
@@ -54,9 +113,13 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int mode, int ndst,
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t tmem_d = tmem_base + (k % ndst) * n;  // ndst independent accumulators, round robin
+        const int nd = ndst >= 100 ? 1 : ndst;
+        const uint32_t tmem_d = tmem_base + (k % nd) * n;  // nd independent accumulators, round robin
         if (mode == 0) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
         else umma_bf16_ts(tmem_d, tmem_a + 8 * k, db + 2 * k, idesc, 1u);
+        // ndst = 100 + c: a tcgen05.commit (to a barrier nobody waits on) after every c-th MMA, as a pipelined main loop
+        // does to free its operand stage
+        if (ndst >= 100 && ((it * 4 + k + 1) % (ndst - 100)) == 0) umma_commit(&bars[1]);
       }
     }
     umma_commit(&bars[0]);
@@ -100,6 +163,32 @@ int main() {
       }
     }
   }
+  cudaFuncSetAttribute(rate_kernel_uniform, cudaFuncAttributeMaxDynamicSharedMemorySize, 52000);
+  for (int n : {64, 128, 256}) {
+    rate_kernel_uniform<<<sms, 128, 52000>>>(n, 50, d);
+    rate_kernel_uniform<<<sms, 128, 52000>>>(n, iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("uniform failed: %s\n", cudaGetErrorString(e)); return 1; }
+    std::vector<long long> h(sms);
+    cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (auto v : h) mx = v > mx ? v : mx;
+    printf("warp-uniform issue (elect.sync)  A from smem  N=%3d : %.1f cycles per MMA (ideal %d)\n", n,
+           static_cast<double>(mx) / (iters * 4), n / 2);
+  }
+  for (int n : {64, 128, 256})
+    for (int every : {4}) {
+      rate_kernel<<<sms, 128, 52000>>>(n, 0, 100 + every, 50, d);
+      rate_kernel<<<sms, 128, 52000>>>(n, 0, 100 + every, iters, d);
+      cudaDeviceSynchronize();
+      std::vector<long long> h(sms);
+      cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (auto v : h) mx = v > mx ? v : mx;
+      printf("A from smem  N=%3d  commit after every %2d MMAs : %.1f cycles per MMA\n", n, every,
+             static_cast<double>(mx) / (iters * 4));
+    }
+  return 0;
   // Sustained throughput under the board's power cap: ~3 s of back-to-back launches per shape, last ~1 s timed.
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
