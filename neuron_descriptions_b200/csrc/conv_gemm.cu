@@ -68,9 +68,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   // WIDE (split mode, long-K problems without a residual): TWO MMAs per K step instead of three. The hi and lo planes
   // of B are adjacent in shared memory, so A_hi x [B_hi; B_lo]^T is one N = 2 * BLOCK_N instruction whose result is
   // [hi*hi | hi*lo] side by side, and A_lo x B_hi^T accumulates into the first half; the epilogue adds the halves.
-  // A 128 x N x 16 MMA costs the same ~60 ns for every N <= 128 (csrc/probe_mma_rate.cu): the main loop pays per
-  // instruction, not per FLOP. Short-K / residual problems keep three MMAs and the deeper accumulator ring: their
-  // epilogue is the critical path and would only see the doubled TMEM reads.
+  // Same FLOPs, but A_hi is fetched from shared memory once instead of twice (20 instead of 24 KB of operand reads per
+  // K step at BLOCK_N = 128) and shared-memory bandwidth - MMA operand reads plus the TMA fill - is what bounds the
+  // long-K convs. Short-K / residual problems keep three MMAs and the deeper accumulator ring:
+  // their epilogue is the critical path and would only see the doubled TMEM reads.
   static_assert(!WIDE || SPLIT, "the wide form only exists in split mode");
   constexpr bool wide = WIDE;
   constexpr int acc_cols = WIDE ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer

@@ -1,6 +1,11 @@
-// Probe (not part of the library): cycles per tcgen05.mma (M = 128, K = 16, bf16) as a function of N and of where
-// the A operand lives (shared memory vs tensor memory), with nothing else touching shared memory. One CTA per SM.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../include probe_mma_rate.cu -o build/probe_mma_rate
+// Probe (not part of the library; `make probes`): cycles per tcgen05.mma (M = 128, K = 16, bf16) as a function of N, of
+// where the A operand lives (shared memory vs tensor memory) and of HOW the instruction is issued, with nothing else
+// touching shared memory. One CTA per SM. Findings on B200:
+//   * issued from a single-thread region (`if (threadIdx.x == 0)`): 112-123 cycles for every N <= 128, SS or TS, one or
+//     four accumulators; N = 256: 166 (SS) / 137 (TS). The floor is ptxas' ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+//     around every uniform-register operand of UTCHMMA in divergent code, not the tensor core.
+//   * issued warp-uniformly (all 32 lanes run the loop, elect.sync picks the lane): 48 / 64 / 128 cycles for
+//     N = 64 / 128 / 256 = the ideal N / 2 from N = 128 up.
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -23,21 +28,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
-// Warp-uniform issue: every lane of the warp runs the loop (so ptxas can keep descriptors in uniform registers) and
-// elect.sync inside the asm picks the one lane that issues.
-__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
+// Warp-uniform issue: every lane of the warp runs the loop (so ptxas keeps descriptors in uniform registers without an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop per operand) and elect.sync inside umma_bf16_elect (ptx.cuh) picks the lane.
 __global__ void __launch_bounds__(128, 1) rate_kernel_uniform(int n, int iters, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,13 +105,9 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int mode, int ndst,
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int nd = ndst >= 100 ? 1 : ndst;
-        const uint32_t tmem_d = tmem_base + (k % nd) * n;  // nd independent accumulators, round robin
+        const uint32_t tmem_d = tmem_base + (k % ndst) * n;  // ndst independent accumulators, round robin
         if (mode == 0) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
         else umma_bf16_ts(tmem_d, tmem_a + 8 * k, db + 2 * k, idesc, 1u);
-        // ndst = 100 + c: a tcgen05.commit (to a barrier nobody waits on) after every c-th MMA, as a pipelined main loop
-        // does to free its operand stage
-        if (ndst >= 100 && ((it * 4 + k + 1) % (ndst - 100)) == 0) umma_commit(&bars[1]);
       }
     }
     umma_commit(&bars[0]);
@@ -176,19 +164,6 @@ int main() {
     printf("warp-uniform issue (elect.sync)  A from smem  N=%3d : %.1f cycles per MMA (ideal %d)\n", n,
            static_cast<double>(mx) / (iters * 4), n / 2);
   }
-  for (int n : {64, 128, 256})
-    for (int every : {4}) {
-      rate_kernel<<<sms, 128, 52000>>>(n, 0, 100 + every, 50, d);
-      rate_kernel<<<sms, 128, 52000>>>(n, 0, 100 + every, iters, d);
-      cudaDeviceSynchronize();
-      std::vector<long long> h(sms);
-      cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
-      long long mx = 0;
-      for (auto v : h) mx = v > mx ? v : mx;
-      printf("A from smem  N=%3d  commit after every %2d MMAs : %.1f cycles per MMA\n", n, every,
-             static_cast<double>(mx) / (iters * 4));
-    }
-  return 0;
   // Sustained throughput under the board's power cap: ~3 s of back-to-back launches per shape, last ~1 s timed.
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
