@@ -2,15 +2,19 @@
 //
 // CTA = 11 warps, persistent over output tiles (static round-robin):
 //   warp 0      : TMA producer  (A boxes per tap / k-block, B weight tiles) -> smem ring, mbarrier full/empty
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer -> fp32 accumulators in TMEM (2 buffers)
+//   warp 1      : TMEM allocator + tcgen05.mma issuer -> fp32 accumulators in TMEM (ring of 2-4 buffers)
 //   warps 2..9  : epilogue, two groups of 4 warps (one warp per TMEM lane quarter and group; group g owns columns
 //                 [32g, 32g+32) of every 64-column chunk): tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 hi/lo
 //                 split -> swizzled smem -> TMA store (EPI_BF16), or fp32 direct stores (EPI_F32)
 //   warp 10     : residual prefetcher: TMA-loads the residual tile of each 64-column chunk into a 2-deep ring
+// The issuing warps (0, 1, 10 and the storing warp 2) run their loops on all 32 lanes with uniform control flow and the
+// `*_elect` helpers of ptx.cuh pick the lane that issues: inside an `if (lane == 0)` region ptxas wraps every
+// uniform-register operand of UTCHMMA / UTMALDG in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~120 cycles per MMA).
 // Two-level accumulation: the tensor core's fp32 accumulation truncates (measured: error grows linearly with the
 // number of chained MMAs, 2.5e-5 abs at K=4544), so the MMA warp starts a fresh TMEM accumulator every
-// `kb_per_chunk` k-blocks and the epilogue warps add the partials in fp32 registers (round-to-nearest). 4 TMEM
-// buffers (512 columns at BLOCK_N=128) let partial drains and the final epilogue overlap the next chunks' MMAs.
+// `kb_per_chunk` k-blocks and the epilogue warps add the partials in fp32 registers (round-to-nearest). The TMEM
+// ring (512 columns: 4 buffers, or 2 double-width ones in the WIDE form) lets partial drains and the final epilogue
+// overlap the next chunks' MMAs.
 #include "conv_gemm.h"
 #include "ptx.cuh"
 

@@ -138,9 +138,11 @@ int build_dual_1x1_params(ConvGemmParams* p, int N, int Ho, int Wo, int Ca, int 
 
 // The 7x7 stride-2 stem as an implicit GEMM without im2col: the input is the zero-padded NHWC4 image
 // [N][232][232][4] (pixel (ih, iw) at (ih + 3, iw + 4); channel 3 = 0) and the k-block of filter row r is the
-// 64-byte window {8 pixels x 4 channels} of padded row 2*oh + r starting at pixel 2*ow, addressed by a 5-D tensor
-// map (k, ow, row parity, row pair, n) whose `ow` stride (16 B) is smaller than the window (overlapping boxes),
-// 64-byte swizzle, block_k = 32. Window pixel 0 carries zero weights. Weights: [64][7*32] (pack_stem_weights).
+// 64-byte window {8 pixels x 4 channels} of padded row 2*oh + r starting at pixel 2*ow. The windows are never
+// materialised: a tile is 8 x 16 output pixels, TMA loads the raw 22-pixel (176 B) segments of the 16 padded rows a
+// filter row touches through a 4-D map (row element, row parity, row pair, n; no swizzle), and the MMA's shared-memory
+// descriptor reads them as overlapping windows (make_smem_desc_stem_rows in ptx.cuh). block_k = 32; window pixel 0
+// carries zero weights. Weights: [64][7*32] (pack_stem_weights), 64-byte swizzle, resident in shared memory.
 // Output: raw conv1 [N][112][112][64] through tmap_out. block_n is 64.
 constexpr int kStemPadH = 232;
 constexpr int kStemPadW = 232;

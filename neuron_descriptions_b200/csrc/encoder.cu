@@ -55,8 +55,8 @@ __device__ __forceinline__ void load_masks4<float>(const float* p, float (&v)[4]
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
 
-// Normalise + repack NCHW images into the zero-padded NHWC4 bf16 layout the stem GEMM reads through its 5-D
-// overlapping-window tensor map: [n][232][232][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
+// Normalise + repack NCHW images into the zero-padded NHWC4 bf16 layout whose raw rows the stem GEMM loads (its MMA
+// descriptor forms the 7-tap windows): [n][232][232][4], pixel (ih, iw) at (ih + 3, iw + 4), channel 3 = 0.
 // One thread per 4 consecutive padded pixels (the x padding of 4 keeps every group fully inside or fully outside
 // the image): one 4-pixel load per channel, two 16-byte stores per plane.
 template <typename T>
