@@ -5,7 +5,9 @@
 //     four accumulators; N = 256: 166 (SS) / 137 (TS). The floor is ptxas' ELECT / R2UR.BROADCAST / BRA.U.ANY loop
 //     around every uniform-register operand of UTCHMMA in divergent code, not the tensor core.
 //   * issued warp-uniformly (all 32 lanes run the loop, elect.sync picks the lane): 48 / 64 / 128 cycles for
-//     N = 64 / 128 / 256 = the ideal N / 2 from N = 128 up.
+//     N = 64 / 128 / 256 from shared memory (N = 64: the 128 B/clk shared-memory read rate), 32 / 64 / 128 with A in
+//     tensor memory = the ideal N / 2. One runtime branch per MMA inside the loop costs ~45 cycles per MMA.
+//   The last section (sustained TFLOP/s) still uses the single-thread form: it shows the floor under the power cap.
 #include "ptx.cuh"
 
 #include <cstdio>
@@ -30,6 +32,21 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // Warp-uniform issue: every lane of the warp runs the loop (so ptxas keeps descriptors in uniform registers without an
 // ELECT / R2UR.BROADCAST / BRA.U.ANY loop per operand) and elect.sync inside umma_bf16_elect (ptx.cuh) picks the lane.
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TS is a template parameter on purpose: one runtime branch per MMA in this loop costs ~45 cycles per MMA.
+template <bool TS>
 __global__ void __launch_bounds__(128, 1) rate_kernel_uniform(int n, int iters, long long* cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -53,10 +70,17 @@ __global__ void __launch_bounds__(128, 1) rate_kernel_uniform(int n, int iters, 
     const uint32_t idesc = make_idesc_16bit(128, n, 1u);
     const uint64_t da = make_smem_desc_sw128(smem_u32(a_s));
     const uint64_t db = make_smem_desc_sw128(smem_u32(b_s));
+    const uint32_t tmem_a = tmem_base + 480;
+    if (TS && threadIdx.x == 0)
+      for (int k = 0; k < 4; ++k) tmem_cp_128x256b(tmem_a + 8 * k, da + 2 * k);
+    __syncwarp();
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_elect(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
+      for (int k = 0; k < 4; ++k) {
+        if (TS) umma_bf16_ts_elect(tmem_base, tmem_a + 8 * k, db + 2 * k, idesc, 1u);
+        else umma_bf16_elect(tmem_base, da + 2 * k, db + 2 * k, idesc, 1u);
+      }
     }
     if (threadIdx.x == 0) {
       umma_commit(&bars[0]);
@@ -151,17 +175,24 @@ int main() {
       }
     }
   }
-  cudaFuncSetAttribute(rate_kernel_uniform, cudaFuncAttributeMaxDynamicSharedMemorySize, 52000);
+  cudaFuncSetAttribute(rate_kernel_uniform<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52000);
+  cudaFuncSetAttribute(rate_kernel_uniform<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52000);
+  for (int ts = 0; ts < 2; ++ts)
   for (int n : {64, 128, 256}) {
-    rate_kernel_uniform<<<sms, 128, 52000>>>(n, 50, d);
-    rate_kernel_uniform<<<sms, 128, 52000>>>(n, iters, d);
+    if (ts) {
+      rate_kernel_uniform<true><<<sms, 128, 52000>>>(n, 50, d);
+      rate_kernel_uniform<true><<<sms, 128, 52000>>>(n, iters, d);
+    } else {
+      rate_kernel_uniform<false><<<sms, 128, 52000>>>(n, 50, d);
+      rate_kernel_uniform<false><<<sms, 128, 52000>>>(n, iters, d);
+    }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("uniform failed: %s\n", cudaGetErrorString(e)); return 1; }
     std::vector<long long> h(sms);
     cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
     long long mx = 0;
     for (auto v : h) mx = v > mx ? v : mx;
-    printf("warp-uniform issue (elect.sync)  A from smem  N=%3d : %.1f cycles per MMA (ideal %d)\n", n,
+    printf("warp-uniform issue (elect.sync)  A from %s  N=%3d : %.1f cycles per MMA (ideal %d)\n", ts ? "tmem" : "smem", n,
            static_cast<double>(mx) / (iters * 4), n / 2);
   }
   // Sustained throughput under the board's power cap: ~3 s of back-to-back launches per shape, last ~1 s timed.
