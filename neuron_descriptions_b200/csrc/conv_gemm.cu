@@ -486,6 +486,10 @@ int launch_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const
 long long conv_gemm_launch_count() { return g_launches.load(); }
 long long total_launch_count() { return g_all_launches.load(); }
 void note_launch(int n) { g_all_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_conv_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_all_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream, const int* skip_flag) {
@@ -505,6 +509,12 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     const int need_k = epilogue == EPI_F32 ? 8 * min_k : min_k;
     wide = min_k > 0 && num_kb * bk >= need_k;  // (the stem, K = 224, stays on three MMAs: 0.370 vs 0.382 ms)
   }
+  static const bool pair_mode = [] {
+    const char* e = getenv("MILAN_PAIR");  // opt-in: cta_group::2 pairs for the long-K bf16 convs (conv_gemm_pair.cu)
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (pair_mode && wide && block_n == 128 && epilogue == EPI_BF16 && bk == 64 && p.has_b_half && !p.stem_mode)
+    return launch_conv_gemm_pair(p, num_sms, stream, skip_flag);
 #define MILAN_DISPATCH(BN, SP, EP, RS, BKV, WD)                                                          \
   if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV && wide == WD)     \
     return launch_impl<BN, SP, EP, RS, BKV, WD>(p, num_sms, stream, skip_flag);

@@ -34,6 +34,8 @@ enum EpilogueKind : int {
 struct alignas(64) ConvGemmParams {
   CUtensorMap tmap_a[2][4];  // [hi|lo][parity plane]
   CUtensorMap tmap_b[2];     // [hi|lo]
+  CUtensorMap tmap_b_half[2];  // [hi|lo] boxes of block_n / 2 rows: what ONE CTA of a cta_group::2 pair loads (conv_gemm_pair.cu)
+  int has_b_half;
   CUtensorMap tmap_out[2];   // [hi|lo] EPI_BF16: output tensor, box (64, box_w, box_h, box_n), TMA store
   CUtensorMap tmap_res[2];   // [hi|lo] EPI_BF16 + residual: same geometry as tmap_out, TMA load
   int stem_mode;             // 1: A is the raw-row map of the 7x7/2 stem, windows formed by the MMA descriptor (see build_stem_params)
@@ -67,6 +69,9 @@ struct alignas(64) ConvGemmParams {
 // beam-search loop to drop the GEMMs of steps after every beam has ended, without a host round trip.
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream, const int* skip_flag = nullptr);
+// CTA-pair variant (conv_gemm_pair.cu): BLOCK_N = 128, split mode, bf16 output, no residual, 64-wide k-blocks.
+int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag);
+void count_conv_launch();
 // Kernel launches performed by this library since process start (for bench.py's gpu_launches).
 long long conv_gemm_launch_count();   // tcgen05 conv/GEMM kernel only
 long long total_launch_count();       // every kernel of the library

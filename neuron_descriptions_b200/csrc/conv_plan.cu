@@ -132,6 +132,10 @@ int build_conv_params(ConvGemmParams* p, const ConvDesc& d, const ConvIO& io, in
   const uint64_t ktot = static_cast<uint64_t>(p->num_taps) * d.Cin;
   for (int hl = 0; hl < nplanes_hi_lo; ++hl) {
     rc = make_tmap_2d(&p->tmap_b[hl], w_planes[hl], ktot, d.Cout, ktot * esz, bn_tile);
+    if (rc == 0 && bn_tile == 128) {
+      rc = make_tmap_2d(&p->tmap_b_half[hl], w_planes[hl], ktot, d.Cout, ktot * esz, bn_tile / 2);
+      p->has_b_half = 1;
+    }
     if (rc) return rc;
   }
   if (!split) {
