@@ -16,8 +16,6 @@
 #include "conv_gemm.h"
 #include "ptx.cuh"
 
-#include <cooperative_groups.h>
-
 #include <mutex>
 
 namespace milan {
