@@ -3,11 +3,15 @@
 TEST INFRASTRUCTURE ONLY (parity oracle). Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
 `--impl reference` legs of `bench.py` may import this module; the product path never does.
 
-PARITY UNPINNED for this file: allennlp is a third-party dependency of the reference (`requirements.txt:7`,
-pinned 2.10.0) that is neither vendored under /root/reference nor installed here, and the reference has no test
-or golden vector for beam search. This restates the published algorithm of
-`allennlp/nn/beam_search.py` @ v2.10.0 (`BeamSearch.search/_search`, `DeterministicSampler`,
-`SequenceLogProbabilityScorer`) with the defaults the reference relies on, anchored on the reference call site
+PINNING: allennlp is a third-party dependency of the reference (`requirements.txt:7`, pinned 2.10.0) that is
+neither vendored under /root/reference nor installed here, and the reference has no test or golden vector for
+beam search, so this file cannot be run against the library itself. It restates the
+published algorithm of `allennlp/nn/beam_search.py` @ v2.10.0 (`BeamSearch.search/_search`,
+`DeterministicSampler`, `SequenceLogProbabilityScorer`) and is pinned by upstream's own published known-answer
+tests (`tests/nn/beam_search_test.py::BeamSearchTest`: the 6-state Markov chain, beam 3 ->
+[[1,2,3,4,5],[2,3,4,5,5],[3,4,5,5,5]] with log .4/.3/.2, greedy, single step, early stopping, per-node beam
+sizes, finished state, bad config, negligible-log-prob and empty-sequence warnings), restated in
+`tests/test_beam_search_upstream.py`. The defaults the reference relies on, anchored on its call site
 `src/milan/decoders.py:467-484`:
 
     BeamSearch(end_index=stop_index, max_steps=length, beam_size=beam_size)
@@ -15,7 +19,7 @@ or golden vector for beam search. This restates the publi
         final scorer = summed log-probabilities, no constraints.
     runner.search(start_predictions (B,), start_state: dict, step(tokens, state) -> (log_probs, state))
 
-Indirect pins available offline (checked in tests/test_oracle.py): beam_size=1 reproduces the reference's greedy
+Further indirect pins on the MILAN decoder itself (tests/test_oracle.py): beam_size=1 reproduces the reference's greedy
 decode token-for-token until `<stop>`; every returned beam score equals the forced-decode log-probability sum of
 its token sequence; rows come back sorted by score.
 """
