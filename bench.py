@@ -328,7 +328,7 @@ def main():
             'precision': ('bf16 hi/lo split operands (3 products per K step, issued as 2 or 3 tcgen05 MMAs), fp32 TMEM '
                           'accumulation (fp32-class results; parity-tested)' if args.precision == 'split'
                           else 'plain bf16 operands'),
-            'conv_cta_pairs': os.environ.get('MILAN_PAIR', '0') not in ('', '0'),  # opt-in cta_group::2 conv kernel
+            'conv_cta_pairs': os.environ.get('MILAN_PAIR', '1') not in ('', '0'),  # cta_group::2 conv kernel (default on)
             'l2': 'inputs larger than L2: 193 MB of fresh exemplars + >10 GB of activations per step vs 126 MB L2',
             'call': f'milan_describe_device over the {steps} steps ({nb * steps} resident neurons) in {len(call_steps)} call(s)',
         },

@@ -510,8 +510,10 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     wide = min_k > 0 && num_kb * bk >= need_k;  // (the stem, K = 224, stays on three MMAs: 0.370 vs 0.382 ms)
   }
   static const bool pair_mode = [] {
-    const char* e = getenv("MILAN_PAIR");  // opt-in: cta_group::2 pairs for the long-K bf16 convs (conv_gemm_pair.cu)
-    return e != nullptr && atoi(e) != 0;
+    // cta_group::2 pairs for the long-K bf16 convs (conv_gemm_pair.cu): default since round 2 (full parity suite green,
+    // same-box bench 1048 -> 1081 neurons/s, profiles/r02a_*); MILAN_PAIR=0 falls back to single-CTA tiles for A/B runs
+    const char* e = getenv("MILAN_PAIR");
+    return e == nullptr || atoi(e) != 0;
   }();
   if (pair_mode && wide && block_n == 128 && epilogue == EPI_BF16 && bk == 64 && p.has_b_half && !p.stem_mode)
     return launch_conv_gemm_pair(p, num_sms, stream, skip_flag);

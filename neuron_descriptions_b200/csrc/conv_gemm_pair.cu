@@ -1,6 +1,6 @@
 // CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM convolution kernel for the long-K bf16 convs:
 // BLOCK_N = 128, split (hi/lo) operands, bf16 hi/lo output through TMA stores, no residual, 64-wide k-blocks.
-// Opt-in (MILAN_PAIR=1, see launch_conv_gemm): DESIGN.md section 8c item 3.
+// Default path for these convs (MILAN_PAIR=0 disables it, see launch_conv_gemm): DESIGN.md section 8c item 3.
 //
 // A cluster of two CTAs (the two SMs of a TPC) computes two vertically adjacent M tiles of the same N tile as ONE
 // 256 x 128 MMA per K step: CTA r loads its own 128 pixels of A (hi + lo) and rows [64 r, 64 r + 64) of the B tile

@@ -107,10 +107,10 @@ def test_compute_exemplars_cli(tmp_path):
     assert ids.shape == (4, 3) and ids.min() >= 0 and ids.max() < 10
 
 
-def test_smoke_with_cta_pair_convs():
-    """The opt-in cta_group::2 conv kernel (MILAN_PAIR=1, read once per process) through the whole engine: smoke()
-    checks features, rerank scores and token ids against the oracle."""
-    env = dict(os.environ, MILAN_PAIR='1', PYTHONPATH=ROOT)
+def test_smoke_without_cta_pair_convs():
+    """The cta_group::2 conv kernel is the default; MILAN_PAIR=0 (read once per process) selects the single-CTA
+    kernel for the same convs. smoke() checks features, rerank scores and token ids against the oracle."""
+    env = dict(os.environ, MILAN_PAIR='0', PYTHONPATH=ROOT)
     out = subprocess.run([sys.executable, os.path.join(ROOT, '__graft_entry__.py'), 'smoke'], env=env,
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
