@@ -45,6 +45,23 @@ int fail(const char* fmt, ...) {
                   __FILE__, __LINE__);                                                                   \
   } while (0)
 
+// Entry points run on the engine's device and leave the caller's current device as they found it (a process may hold
+// tensors on several GPUs; torch tracks its own notion of the current device).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct HostTensor {
   std::vector<float> data;
   std::vector<int64_t> shape;
@@ -1001,6 +1018,7 @@ int MilanEngine::decode_greedy(const float* d_features, int B, int n_keys, int l
                                float* d_pred_out, float* d_attn_out, cudaStream_t st) {
   const int V = cfg.vocab_size, H = cfg.hidden_size, E = cfg.embedding_size, F = cfg.feature_size;
   if (B > Rmax) return fail("decode_greedy: B=%d exceeds capacity %d", B, Rmax);
+  if (length < 1 || length > cfg.max_length) return fail("length %d outside [1, max_length = %d]", length, cfg.max_length);
   if (static_cast<size_t>(B) * n_keys > FRcap) return fail("decode_greedy: too many feature rows");
   if (mi && !cfg.has_lm) return fail("cannot use MI decoding without an LM");
   if (prepare_features(d_features, B, n_keys, st)) return 1;
@@ -1069,7 +1087,7 @@ int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int len
   if (beam > V) return fail("Target vocab size (%d) too small relative to per_node_beam_size (%d).", V, beam);
   if (B > Bmax) return fail("decode_beam: B=%d exceeds max_neurons %d", B, Bmax);
   if (static_cast<size_t>(B) * n_keys > FRcap) return fail("decode_beam: too many feature rows");
-  if (length > cfg.max_length) return fail("length %d exceeds max_length %d", length, cfg.max_length);
+  if (length < 1 || length > cfg.max_length) return fail("length %d outside [1, max_length = %d]", length, cfg.max_length);
   if ((rerank || mi) && !cfg.has_lm) return fail("cannot use MI/rerank decoding without an LM");
   if (rerank && mi) return fail("cannot set `mi=` decoding when reranking");
   if (group_size <= 0) group_size = B;
@@ -1165,7 +1183,6 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   if (e != cudaSuccess || count == 0)
     return fail("no CUDA device available (%s): the milan_b200 engine has no CPU fallback", cudaGetErrorString(e));
   if (device < 0 || device >= count) return fail("device %d out of range (%d devices)", device, count);
-  CU(cudaSetDevice(device));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail("device %s is sm_%d%d; this engine is built for sm_100a only", prop.name, prop.major, prop.minor);
@@ -1204,7 +1221,7 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
 
 void milan_engine_destroy(MilanEngine* engine) {
   if (engine == nullptr) return;
-  cudaSetDevice(engine->device);
+  DeviceGuard device_guard(engine->device);
   cudaDeviceSynchronize();
   for (void* p : engine->allocs) cudaFree(p);
   for (auto& ev : engine->conv_events) {
@@ -1241,7 +1258,8 @@ int milan_engine_finalize(MilanEngine* engine) {
   g_err[0] = 0;
   if (engine == nullptr) return fail("null engine");
   if (engine->finalized) return 0;
-  CU(cudaSetDevice(engine->device));
+  DeviceGuard device_guard(engine->device);
+  CU(device_guard.err);
   if (engine->cfg.has_encoder && engine->finalize_encoder()) return 1;
   // An engine given encoder tensors only (standalone Encoder use, src/milan/encoders.py) has no decoder half.
   engine->has_decoder = !engine->cfg.has_encoder || engine->get("lstm.weight_ih") != nullptr;
@@ -1257,7 +1275,8 @@ int milan_engine_finalize(MilanEngine* engine) {
   g_err[0] = 0;                                                    \
   if ((e) == nullptr) return fail("null engine");                  \
   if (!(e)->finalized) return fail("engine not finalized");        \
-  CU(cudaSetDevice((e)->device));
+  DeviceGuard device_guard_((e)->device);                          \
+  CU(device_guard_.err);
 #define CHECK_DECODER(e) \
   if (!(e)->has_decoder) return fail("engine was created without decoder weights (encoder-only)");
 
@@ -1386,6 +1405,11 @@ int MilanEngine::describe(const uint8_t* images, const uint8_t* masks, bool host
                           int strategy, int mi, int length, int beam, int group_size, float temperature,
                           cudaStream_t st) {
   MilanEngine* e = this;
+  // the result buffers hold max_length ids per neuron and chunks write at done * length: reject what would overrun them
+  if (length < 1 || length > cfg.max_length) return fail("length %d outside [1, max_length = %d]", length, cfg.max_length);
+  if (strategy < 0 || strategy > 2) return fail("unknown strategy %d", strategy);
+  if (strategy != 0 && (beam < 1 || beam > cfg.max_beam || beam > kMaxBeam))
+    return fail("beam size %d unsupported (max %d)", beam, std::min(cfg.max_beam, kMaxBeam));
   const int n_keys = k * (spatial ? kSpatialKeys : 1);  // Decoder.encode: view(batch, -1, feature_size)
   // neurons per chunk: bounded by encoder image capacity and decoder capacity; whole reference groups only
   int chunk = std::min(cfg.max_images / k, cfg.max_neurons);

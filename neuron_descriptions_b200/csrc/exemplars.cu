@@ -16,6 +16,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -123,18 +124,47 @@ __global__ void tally_samples_kernel(const float* __restrict__ acts, int U, int 
   for (int p = threadIdx.x; p < P; p += blockDim.x) dst[p] = src[p];
 }
 
-__global__ void tally_hist_kernel(const float* __restrict__ acts, int U, int P, unsigned* __restrict__ hist) {
-  const int b = blockIdx.x, u = blockIdx.y;
-  const float* src = acts + (static_cast<long long>(b) * U + u) * P;
+// Histogram of the upper 16 key bits per unit. The 65536 bins of a unit (256 KB) do not fit in shared memory, but the
+// activations of one unit live in a narrow band of them: bin = sign | exponent | 7 mantissa bits, so 64 binades around
+// +-1.0 are 8192 bins each. A CTA owns one unit (and a slice of the batch), counts those two windows in shared memory
+// (64 KB) and flushes the non-empty bins once; +-0 and anything outside the windows (|x| < 2^-32 or >= 2^32) go to
+// global memory directly. Lanes of a warp that hit the same bin add once (post-ReLU maps are mostly one value).
+constexpr int kHistWindow = 8192;
+constexpr unsigned kHistPosBase = 0xBF80u - kHistWindow / 2;  // bin of +1.0 = 0xBF80
+constexpr unsigned kHistNegBase = 0x407Fu - kHistWindow / 2;  // bin of -1.0 = 0x407F
+__global__ void __launch_bounds__(256) tally_hist_kernel(const float* __restrict__ acts, int B, int U, int P,
+                                                         int b_per_cta, unsigned* __restrict__ hist) {
+  extern __shared__ unsigned win[];  // [2][kHistWindow]
+  const int u = blockIdx.x;
+  const int b0 = blockIdx.y * b_per_cta;
+  const int b1 = min(B, b0 + b_per_cta);
   unsigned* h = hist + static_cast<long long>(u) * 65536;
-  // lanes of a warp that hit the same bin add once (activations of one unit cluster in a few hundred bins)
-  const int rounds = (P + blockDim.x - 1) / blockDim.x;
-  for (int r = 0; r < rounds; ++r) {
-    const int p = r * blockDim.x + threadIdx.x;
-    const bool live = p < P;
-    const unsigned bin = live ? float_key(src[p]) >> 16 : 0xFFFFFFFFu;
+  for (int i = threadIdx.x; i < 2 * kHistWindow; i += blockDim.x) win[i] = 0;
+  __syncthreads();
+  const long long total = static_cast<long long>(b1 - b0) * P;
+  const long long rounds = (total + blockDim.x - 1) / blockDim.x;
+  for (long long r = 0; r < rounds; ++r) {
+    const long long i = r * blockDim.x + threadIdx.x;
+    const bool live = i < total;
+    unsigned bin = 0xFFFFFFFFu;
+    if (live) {
+      const int b = b0 + static_cast<int>(i / P);
+      const int p = static_cast<int>(i - static_cast<long long>(b - b0) * P);
+      bin = float_key(__ldg(acts + (static_cast<long long>(b) * U + u) * P + p)) >> 16;
+    }
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[bin], static_cast<unsigned>(__popc(peers)));
+    if (live && (threadIdx.x & 31) == __ffs(peers) - 1) {
+      const unsigned n = static_cast<unsigned>(__popc(peers));
+      const unsigned dp = bin - kHistPosBase, dn = bin - kHistNegBase;  // unsigned: out of window -> huge
+      if (dp < static_cast<unsigned>(kHistWindow)) atomicAdd(&win[dp], n);
+      else if (dn < static_cast<unsigned>(kHistWindow)) atomicAdd(&win[kHistWindow + dn], n);
+      else atomicAdd(&h[bin], n);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kHistWindow; i += blockDim.x) {
+    const unsigned n = win[i];
+    if (n != 0) atomicAdd(&h[(i < kHistWindow ? kHistPosBase + i : kHistNegBase + (i - kHistWindow))], n);
   }
 }
 
@@ -258,6 +288,29 @@ int done() {
   return static_cast<int>(cudaGetLastError());
 }
 
+// The stage-1 entry points take bare device pointers: run on the device that owns them (not whatever device is
+// current in the calling thread) and restore the caller's device on the way out.
+struct PointerDeviceGuard {
+  int device = 0, prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit PointerDeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes attr{};
+    err = cudaPointerGetAttributes(&attr, device_ptr);
+    if (err != cudaSuccess) return;
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) { err = cudaErrorInvalidDevicePointer; return; }
+    device = attr.device;
+    err = cudaGetDevice(&prev);
+    if (err != cudaSuccess) return;
+    if (prev == device) prev = -1;
+    else err = cudaSetDevice(device);
+  }
+  ~PointerDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  PointerDeviceGuard(const PointerDeviceGuard&) = delete;
+  PointerDeviceGuard& operator=(const PointerDeviceGuard&) = delete;
+};
+
 }  // namespace
 
 extern "C" {
@@ -266,6 +319,8 @@ int milan_tally_topk(const float* d_acts, int32_t B, int32_t U, int32_t P, int64
                      float* d_pooled_scratch, float* d_top_vals, int64_t* d_top_ids, void* stream) {
   if (B <= 0 || U <= 0) return 0;
   if (k < 1 || k > kMaxTopK || B > kMaxBatch || P < 1) return static_cast<int>(cudaErrorInvalidValue);
+  PointerDeviceGuard guard(d_acts);
+  if (guard.err != cudaSuccess) return static_cast<int>(guard.err);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* pooled = d_pooled_scratch;  // (B, U) spatial maxima
   const long long rows = static_cast<long long>(B) * U;
@@ -283,13 +338,30 @@ int milan_tally_samples(const float* d_acts, int32_t B, int32_t U, int32_t P, fl
                         int64_t count, void* stream) {
   if (B <= 0 || U <= 0) return 0;
   if (count + static_cast<int64_t>(B) * P > capacity) return static_cast<int>(cudaErrorInvalidValue);
+  PointerDeviceGuard guard(d_acts);
+  if (guard.err != cudaSuccess) return static_cast<int>(guard.err);
   tally_samples_kernel<<<dim3(B, U), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_acts, U, P, d_samples, capacity, count);
   return done();
 }
 
 int milan_tally_hist(const float* d_acts, int32_t B, int32_t U, int32_t P, uint32_t* d_hist, void* stream) {
   if (B <= 0 || U <= 0) return 0;
-  tally_hist_kernel<<<dim3(B, U), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_acts, U, P, d_hist);
+  PointerDeviceGuard guard(d_acts);
+  if (guard.err != cudaSuccess) return static_cast<int>(guard.err);
+  constexpr int smem = 2 * kHistWindow * static_cast<int>(sizeof(unsigned));
+  cudaError_t e = cudaFuncSetAttribute(tally_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  // one unit per CTA column; the batch is sliced so that the grid has a few CTAs per SM but every CTA still
+  // amortises its 64 KB window flush over >= 64 K activations where the batch allows
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, guard.device);
+  int slices = (3 * sm_count + U - 1) / U;
+  const long long per_image = P;
+  const int max_slices = static_cast<int>(std::max<long long>(1, static_cast<long long>(B) * per_image / 65536));
+  slices = std::max(1, std::min(std::min(slices, max_slices), B));
+  const int b_per_cta = (B + slices - 1) / slices;
+  slices = (B + b_per_cta - 1) / b_per_cta;
+  tally_hist_kernel<<<dim3(U, slices), 256, smem, static_cast<cudaStream_t>(stream)>>>(d_acts, B, U, P, b_per_cta, d_hist);
   return done();
 }
 
@@ -297,6 +369,8 @@ int milan_quantile_exact(const float* d_samples, int32_t U, int64_t capacity, in
                          void* stream) {
   if (U <= 0) return 0;
   if (n < 1 || n > 8192 || n > capacity) return static_cast<int>(cudaErrorInvalidValue);
+  PointerDeviceGuard guard(d_samples);
+  if (guard.err != cudaSuccess) return static_cast<int>(guard.err);
   int m = 1;
   while (m < n) m <<= 1;
   quantile_exact_kernel<<<U, 1024, static_cast<size_t>(m) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
@@ -307,6 +381,8 @@ int milan_quantile_exact(const float* d_samples, int32_t U, int64_t capacity, in
 int milan_quantile_hist(const uint32_t* d_hist, int32_t U, int64_t n, float q, float* d_levels, void* stream) {
   if (U <= 0) return 0;
   if (n < 1) return static_cast<int>(cudaErrorInvalidValue);
+  PointerDeviceGuard guard(d_hist);
+  if (guard.err != cudaSuccess) return static_cast<int>(guard.err);
   quantile_hist_kernel<<<U, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_hist, n, q, d_levels);
   return done();
 }
@@ -315,6 +391,8 @@ int milan_activation_masks(const float* d_maps, const float* d_levels, int32_t n
                            uint8_t* d_masks, void* stream) {
   if (n <= 0) return 0;
   if (H < 1 || W < 1 || S < 1) return static_cast<int>(cudaErrorInvalidValue);
+  PointerDeviceGuard guard(d_maps);
+  if (guard.err != cudaSuccess) return static_cast<int>(guard.err);
   // upsample_grid with scale_offset=None: scale = S / size, offset = 0.5 * scale - 0.5 (Python floats), then
   // (arange - offset) * (2 / (scale * max(1, size - 1))) - 1 on float32 tensors
   const double sy = static_cast<double>(S) / H, sx = static_cast<double>(S) / W;

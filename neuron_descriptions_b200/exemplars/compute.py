@@ -70,9 +70,7 @@ class _Tally:
         P = hiddens[0, 0].numel()
         acts = hiddens.view(B, U, P)
         if self.top_vals is None:
-            self.top_vals = torch.full((U, self.k), float('-inf'), device=self.device)
-            self.top_ids = torch.full((U, self.k), -1, dtype=torch.long, device=self.device)
-            self.samples = torch.empty(U, EXACT_CAPACITY, device=self.device)
+            self._init_state(U)
         for lo in range(0, B, 1024):
             part = acts[lo:lo + 1024]
             pooled = torch.empty(len(part), U, device=self.device)
@@ -90,6 +88,11 @@ class _Tally:
         self.count += B
         self.samples_seen += B * P
 
+    def _init_state(self, units: int):
+        self.top_vals = torch.full((units, self.k), float('-inf'), device=self.device)
+        self.top_ids = torch.full((units, self.k), -1, dtype=torch.long, device=self.device)
+        self.samples = torch.empty(units, EXACT_CAPACITY, device=self.device)
+
     def _to_histogram(self):
         """Leave the exact regime: fold the kept samples into a fresh histogram."""
         U = self.samples.shape[0]
@@ -103,10 +106,16 @@ class _Tally:
     def result(self, quantile: float) -> ActivationStats:
         """Read-out; with torch.distributed initialised the per-rank statistics are merged first (every rank gets
         the same answer; see `exemplars/sharding.py`)."""
-        U = self.top_vals.shape[0]
+        world, _ = sharding.world_and_rank()
+        # a rank whose image shard was empty never ran add(): it learns the unit count from its peers and joins the
+        # collectives below with empty statistics instead of leaving them blocked
+        U = sharding.max_over_ranks(0 if self.top_vals is None else self.top_vals.shape[0], self.device)
+        if U == 0:
+            raise ValueError('no activations were tallied on any rank')
+        if self.top_vals is None:
+            self._init_state(U)
         top_vals, top_ids = sharding.merge_topk(self.top_vals, self.top_ids)
         total = sharding.total_count(self.samples_seen, self.device)
-        world, _ = sharding.world_and_rank()
         # every rank must take the same branch: exact iff ALL samples of all ranks fit the sketch's first level
         if world > 1:
             flag = torch.tensor([1 if self.hist is None else 0], device=self.device)

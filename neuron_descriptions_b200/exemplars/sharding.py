@@ -80,6 +80,15 @@ def total_count(count: int, device) -> int:
     return int(t.item())
 
 
+def max_over_ranks(value: int, device) -> int:
+    world, _ = world_and_rank()
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.long, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def sum_histograms(hist: torch.Tensor) -> torch.Tensor:
     world, _ = world_and_rank()
     if world > 1:

@@ -438,9 +438,11 @@ class Decoder:
                     else:
                         samples = [dataset[j] for j in range(lo, hi)]
                         images = torch.stack([torch.as_tensor(s[image_index]) for s in samples])
-                        masks = torch.stack([torch.as_tensor(s[mask_index]) for s in samples])
                         images = images.to(engine.device, non_blocking=True)
-                        masks = masks.to(engine.device, non_blocking=True) if mask else None
+                        masks = None
+                        if mask:  # the mask field is only read when asked for (decoders.py:853-858)
+                            masks = torch.stack([torch.as_tensor(s[mask_index]) for s in samples])
+                            masks = masks.to(engine.device, non_blocking=True)
                     if masks is None:
                         output = self(images, encode=True, group_size=group, **kwargs)
                     else:
@@ -541,10 +543,11 @@ class Decoder:
         }
 
     def serialize(self) -> Mapping[str, Any]:
-        """Reference payload layout (`src/utils/serialize.py:80-118,188-203`), tokenizer omitted."""
+        """Reference payload layout (`src/utils/serialize.py:80-118,188-203`). A tokenizer that came in with a
+        reference checkpoint is written back as the opaque payload it arrived as; callables are not serialized."""
         def indexer_payload(indexer):
             props = {'vocab': {'properties': {'tokens': tuple(indexer.vocab.tokens)}, 'children': {}},
-                     'tokenize': None, 'start': indexer.start, 'stop': indexer.stop, 'pad': indexer.pad,
+                     'tokenize': indexer.tokenize_payload, 'start': indexer.start, 'stop': indexer.stop, 'pad': indexer.pad,
                      'unk': indexer.unk, 'length': indexer.length}
             return {'properties': props, 'children': {}}
 

@@ -24,7 +24,7 @@ class Encoder:
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
 
-    def map(self, dataset, mask: bool = True, image_index: int = 2, mask_index: int = 3, batch_size: int = 16,
+    def map(self, dataset, mask: bool = True, image_index: int = -3, mask_index: int = -2, batch_size: int = 64,
             device=None, display_progress_as: Optional[str] = None, **_: Any):
         """`Encoder.map`, `src/milan/encoders.py:61-148`: featurise a whole dataset -> TensorDataset."""
         from torch.utils import data
@@ -33,8 +33,16 @@ class Encoder:
         features = []
         for lo in range(0, len(dataset), batch_size):
             samples = [dataset[i] for i in range(lo, min(lo + batch_size, len(dataset)))]
-            images = torch.stack([torch.as_tensor(s[image_index]) for s in samples])
-            masks = torch.stack([torch.as_tensor(s[mask_index]) for s in samples]) if mask else None
+            # defaults (-3, -2) address AnnotatedTopImages (..., images, masks, annotations) like the reference's;
+            # a plain TopImages sample needs image_index=2, mask_index=3 there too (encoders.py:63-64, :127-139)
+            if not isinstance(samples[0][image_index], torch.Tensor):
+                raise ValueError(f'non-tensor images: {type(samples[0][image_index]).__name__}')
+            images = torch.stack([s[image_index] for s in samples])
+            masks = None
+            if mask:
+                if not isinstance(samples[0][mask_index], torch.Tensor):
+                    raise ValueError(f'non-tensor masks: {type(samples[0][mask_index]).__name__}')
+                masks = torch.stack([s[mask_index] for s in samples])
             shape = images.shape
             flat_images = images.view(-1, *shape[-3:])
             flat_masks = masks.view(-1, *masks.shape[-3:]) if masks is not None else None

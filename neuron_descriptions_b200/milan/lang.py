@@ -65,6 +65,9 @@ class Indexer:
     pad: bool = False
     unk: bool = False
     length: Optional[int] = None
+    # A reference checkpoint's serialized tokenizer ({'properties': {'nlp': (spaCy config, bytes), ...}, 'children':
+    # {}}, src/utils/serialize.py:104-107): opaque here (no spaCy), carried so that `Decoder.save` round-trips it.
+    tokenize_payload: Optional[Any] = dataclasses.field(default=None, compare=False, repr=False)
 
     @functools.cached_property
     def start_index(self) -> int:
@@ -166,59 +169,66 @@ class Indexer:
 
     def unindex(self, indexed, specials: bool = True, start: bool = True, stop: bool = True, pad: bool = True,
                 unk: bool = True):
-        """`src/utils/lang.py:573-612`."""
+        """ids -> token strings (`Indexer.unindex`, `src/utils/lang.py:573-612`).
+
+        Vocabulary ids map to their token; a special id maps to its token when `specials` and its own flag are set
+        and is dropped otherwise; anything else raises ValueError. As in the reference all four special ids are
+        recognised whether or not the indexer itself emits them.
+        """
         if not indexed:
             return ()
-        singleton = isinstance(indexed[0], int)
-        unindexed = []
-        for indices in [indexed] if singleton else indexed:
+        special_text = {index: (token if specials and wanted else None)
+                        for (index, token), wanted in zip(self.specials.items(), (start, stop, pad, unk))}
+        n_vocab = len(self.vocab)
+
+        def decode(indices):
             tokens = []
             for index in indices:
-                if index < len(self.vocab):
+                if index < n_vocab:
                     tokens.append(self.vocab[index])
-                    continue
-                for (special, token), keep in zip(self.specials.items(), (start, stop, pad, unk)):
-                    if index == special:
-                        if specials and keep:
-                            tokens.append(token)
-                        break
+                elif index in special_text:
+                    if special_text[index] is not None:
+                        tokens.append(special_text[index])
                 else:
                     raise ValueError(f'unknown index: {index}')
-            unindexed.append(tuple(tokens))
-        return unindexed[0] if singleton else tuple(unindexed)
+            return tuple(tokens)
+
+        if isinstance(indexed[0], int):
+            return decode(indexed)
+        return tuple(decode(indices) for indices in indexed)
+
+    @staticmethod
+    def _detokenize(tokens, dropped) -> str:
+        """Words -> caption text with the reference's surface rules (`src/utils/lang.py:704-728`): cut at the
+        first `<stop>`, drop special tokens, no space before . , ; : and none around -, sentences capitalised."""
+        tokens = list(tokens)
+        if STOP_TOKEN in tokens:
+            del tokens[tokens.index(STOP_TOKEN):]
+        text = ' '.join(token for token in tokens if token not in dropped)
+        for mark in '.,;:':
+            text = text.replace(' ' + mark, mark)
+        text = text.replace(' -', '-').replace('- ', '-')
+        sentences = (sentence.strip().capitalize() for sentence in text.split('.'))
+        return '. '.join(sentences).strip()
 
     def reconstruct(self, inputs: Union[Sequence[int], Sequence[Sequence[int]], Sequence[str],
                                         Sequence[Sequence[str]]]):
-        """`src/utils/lang.py:678-730`."""
+        """ids or tokens -> caption strings (`Indexer.reconstruct`, `src/utils/lang.py:678-730`); one sequence in,
+        one string out, several in, a tuple out."""
         if not inputs:
             raise ValueError('must provide at least one seq')
-        for index, item in enumerate(inputs):
+        for position, item in enumerate(inputs):
             if not isinstance(item, (int, str)) and not item:
-                raise ValueError(f'input seq {index} is empty')
-        if isinstance(inputs[0], str):
-            tokenized = [inputs]
-        elif isinstance(inputs[0], int):
-            tokenized = [self.unindex(inputs)]
-        elif isinstance(inputs[0][0], str):
-            tokenized = inputs
-        else:
-            assert isinstance(inputs[0][0], int), 'unknown input type'
-            tokenized = self.unindex(inputs)
-        special_tokens = set(self.specials.values())
-        texts = []
-        for tokens in tokenized:
-            tokens = list(tokens)
-            if STOP_TOKEN in tokens:
-                tokens = tokens[:tokens.index(STOP_TOKEN)]
-            text = ' '.join(token for token in tokens if token not in special_tokens)
-            for token in ('.', ',', ';', ':'):
-                text = text.replace(' ' + token, token)
-            for token in ('-',):
-                text = text.replace(' %s' % token, token)
-                text = text.replace('%s ' % token, token)
-            text = '. '.join(sentence.strip().capitalize() for sentence in text.split('.')).strip()
-            texts.append(text)
-        return texts[0] if isinstance(inputs[0], (str, int)) else tuple(texts)
+                raise ValueError(f'input seq {position} is empty')
+        single = isinstance(inputs[0], (int, str))
+        batch = [inputs] if single else inputs
+        probe = batch[0][0]
+        assert isinstance(probe, (int, str)), 'unknown input type'
+        if isinstance(probe, int):
+            batch = self.unindex(batch)
+        dropped = frozenset(self.specials.values())
+        texts = tuple(self._detokenize(tokens, dropped) for tokens in batch)
+        return texts[0] if single else texts
 
     def properties(self):
         return {'vocab': self.vocab, 'tokenize': self.tokenize, 'start': self.start, 'stop': self.stop,
@@ -252,4 +262,5 @@ def indexer_from_payload(payload: Mapping[str, Any]) -> Indexer:
         vocab = Vocab(tuple(vocab['properties']['tokens']))
     return Indexer(vocab=vocab, tokenize=None, start=bool(props.get('start', False)),
                    stop=bool(props.get('stop', False)), pad=bool(props.get('pad', False)),
-                   unk=bool(props.get('unk', False)), length=props.get('length'))
+                   unk=bool(props.get('unk', False)), length=props.get('length'),
+                   tokenize_payload=props.get('tokenize'))

@@ -16,56 +16,65 @@ class TopImages(NamedTuple):
     masks: torch.Tensor
 
 
+class _LayerExemplars(NamedTuple):
+    """One layer directory as written by stage 1 (`src/exemplars/compute.py:217-227`), memory-mapped."""
+    images: numpy.ndarray  # (units, k, 3, H, W) uint8
+    masks: numpy.ndarray   # (units, k, 1, H, W) uint8
+    units: torch.Tensor    # (units,) unit numbers
+
+    @classmethod
+    def open(cls, directory: pathlib.Path, layer: str) -> '_LayerExemplars':
+        arrays = {}
+        for kind in ('images', 'masks'):
+            file = directory / f'{kind}.npy'
+            if not file.exists():
+                raise FileNotFoundError(f'{layer} is missing {file.name}')
+            arrays[kind] = numpy.load(file, mmap_mode='r')  # stays on disk: 12 MB per unit as fp32 otherwise
+        for kind, array in arrays.items():
+            if array.ndim != 5:
+                raise ValueError(f'expected 5D {kind}, got {array.ndim}D in layer {layer}')
+        (n_img, k_img, _, *hw_img), (n_msk, k_msk, _, *hw_msk) = arrays['images'].shape, arrays['masks'].shape
+        if (n_img, k_img) != (n_msk, k_msk):
+            raise ValueError(f'layer {layer} masks/images have different # unit/images: '
+                             f'{(n_img, k_img)} vs. {(n_msk, k_msk)}')
+        if hw_img != hw_msk:
+            raise ValueError(f'layer {layer} masks/images have different height/width '
+                             f'{tuple(hw_img)} vs. {tuple(hw_msk)}')
+        units = torch.arange(n_img)  # units.npy is optional: stage 1 writes it only for a unit subset
+        if (directory / 'units.npy').exists():
+            units = torch.from_numpy(numpy.load(directory / 'units.npy'))
+            if units.dim() != 1:
+                raise ValueError(f'expected 1D units, got {units.dim()}D')
+        return cls(arrays['images'], arrays['masks'], units)
+
+
 class TopImagesDataset(torch.utils.data.Dataset):
-    """Top-activating images for individual units."""
+    """Top-activating images for individual units (`src/milannotations/datasets.py:93-292`).
+
+    Same constructor, sample type, errors and value distribution as the reference (images = byte / 255 in fp32,
+    masks 0.0 / 1.0), but the exemplar files stay memory-mapped uint8 and samples are converted on access; the
+    engine reads them as uint8 through `batch_u8`.
+    """
 
     def __init__(self, root, name: Optional[str] = None, layers: Optional[Iterable] = None, device=None,
                  transform_images=None, transform_masks=None, display_progress: bool = True):
-        del display_progress
-        root = pathlib.Path(root)
-        if not root.is_dir():
-            raise FileNotFoundError(f'root directory not found: {root}')
-        if layers is None:
-            layers = [f.name for f in root.iterdir() if f.is_dir()]
-        if not layers:
+        del display_progress  # nothing is read eagerly, so there is nothing to show progress for
+        self.root = pathlib.Path(root)
+        if not self.root.is_dir():
+            raise FileNotFoundError(f'root directory not found: {self.root}')
+        found = [entry.name for entry in self.root.iterdir() if entry.is_dir()] if layers is None else list(layers)
+        if not found:
             raise ValueError('no layers given and root has no subdirectories')
-        if name is None:
-            name = f'{root.parent.name}/{root.name}'
-        self.root = root
-        self.name = name
-        self.layers = layers = tuple(sorted(str(layer) for layer in layers))
+        self.layers = tuple(sorted(map(str, found)))
+        self.name = name if name is not None else f'{self.root.parent.name}/{self.root.name}'
         self.device = device
-        self.transform_images = transform_images
-        self.transform_masks = transform_masks
-        self.images_by_layer, self.masks_by_layer, self.units_by_layer = {}, {}, {}
-        for layer in layers:
-            images_file = root / str(layer) / 'images.npy'
-            masks_file = root / str(layer) / 'masks.npy'
-            for file in (images_file, masks_file):
-                if not file.exists():
-                    raise FileNotFoundError(f'{layer} is missing {file.name}')
-            images = numpy.load(images_file, mmap_mode='r')
-            masks = numpy.load(masks_file, mmap_mode='r')
-            for kind, array in (('images', images), ('masks', masks)):
-                if array.ndim != 5:
-                    raise ValueError(f'expected 5D {kind}, got {array.ndim}D in layer {layer}')
-            if images.shape[:2] != masks.shape[:2]:
-                raise ValueError(f'layer {layer} masks/images have different # unit/images: '
-                                 f'{images.shape[:2]} vs. {masks.shape[:2]}')
-            if images.shape[3:] != masks.shape[3:]:
-                raise ValueError(f'layer {layer} masks/images have different height/width '
-                                 f'{images.shape[3:]} vs. {masks.shape[3:]}')
-            units_file = root / str(layer) / 'units.npy'
-            if units_file.exists():
-                units = torch.from_numpy(numpy.load(units_file))
-                if units.dim() != 1:
-                    raise ValueError(f'expected 1D units, got {units.dim()}D')
-            else:
-                units = torch.arange(len(images))
-            self.images_by_layer[layer] = images
-            self.masks_by_layer[layer] = masks
-            self.units_by_layer[layer] = units
-        self._index = [(layer, i) for layer in layers for i in range(len(self.images_by_layer[layer]))]
+        self.transform_images, self.transform_masks = transform_images, transform_masks
+        opened = {layer: _LayerExemplars.open(self.root / layer, layer) for layer in self.layers}
+        self.images_by_layer = {layer: files.images for layer, files in opened.items()}
+        self.masks_by_layer = {layer: files.masks for layer, files in opened.items()}
+        self.units_by_layer = {layer: files.units for layer, files in opened.items()}
+        # dataset order = layers sorted by name, units in file order (what the CSV of stage 2 follows)
+        self._index = [(layer, row) for layer in self.layers for row in range(len(opened[layer].images))]
 
     def _convert(self, layer: str, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
         images = torch.from_numpy(numpy.array(self.images_by_layer[layer][i])).float().mul(_BYTE_TO_PT)
@@ -122,13 +131,14 @@ class TopImagesDataset(torch.utils.data.Dataset):
                 torch.empty((n, *mk_shape), dtype=torch.uint8, pin_memory=pin))
 
     def lookup(self, layer, unit: int) -> TopImages:
-        layer = str(layer)
-        if layer not in self.images_by_layer:
+        """Row `unit` of `layer` (`datasets.py:238-259`; like the reference, `unit` is the row, not a unit number)."""
+        stored = self.images_by_layer.get(str(layer))
+        if stored is None:
             raise KeyError(f'layer "{layer}" does not exist')
-        if unit >= len(self.images_by_layer[layer]):
+        if not unit < len(stored):
             raise KeyError(f'layer "{layer}" has no unit {unit}')
-        images, masks = self._convert(layer, unit)
-        return TopImages(layer=layer, unit=unit, images=images, masks=masks)
+        images, masks = self._convert(str(layer), unit)
+        return TopImages(str(layer), unit, images, masks)
 
     def unit(self, index: int):
         layer, i = self._index[index]

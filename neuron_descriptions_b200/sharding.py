@@ -53,8 +53,13 @@ def gather_token_rows(local: torch.Tensor, n_total: int, world: int, pad_value: 
 
 
 class _Slice(torch.utils.data.Dataset):
+    """Rows [lo, hi) of `base`, keeping the attributes `Decoder.predict` inspects (k, transforms)."""
+
     def __init__(self, base, lo, hi):
         self.base, self.lo, self.hi = base, lo, hi
+        for name in ('k', 'transform_images', 'transform_masks'):
+            if hasattr(base, name):
+                setattr(self, name, getattr(base, name))
 
     def __len__(self):
         return self.hi - self.lo
@@ -87,8 +92,11 @@ def predict_sharded(decoder, dataset, world: int = 1, rank: int = 0, batch_size:
     kwargs.setdefault('display_progress_as', None)
     captions_local: List[str] = list(decoder.predict(shard, batch_size=batch_size, **kwargs)) if hi > lo else []
     # captions -> token ids would need the tokenizer; gather the ids the engine produced instead
-    ids = getattr(decoder, 'last_predict_tokens', None)
-    if ids is not None and len(ids) == hi - lo:
+    if hi > lo:
+        ids = getattr(decoder, 'last_predict_tokens', None)
+        if ids is None or len(ids) != hi - lo or len(captions_local) != hi - lo:
+            raise RuntimeError(f'rank {rank}: predict() returned {len(captions_local)} captions and '
+                               f'{None if ids is None else len(ids)} token rows for a shard of {hi - lo} neurons')
         tokens[:, :ids.shape[1]] = ids.cpu()
     device = decoder.engine.device if torch.cuda.is_available() else torch.device('cpu')
     gathered = gather_token_rows(tokens.to(device), n, world, stop)

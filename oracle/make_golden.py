@@ -186,6 +186,43 @@ def make_checkpoint_skeleton(milan, lang):
     print('checkpoint skeleton:', len(decoder.state_dict()), 'state_dict entries')
 
 
+LANG_TOKENS = ('.', ',', ';', ':', '-', 'dog', 'cat', 'a', 'top', 'x.y', 'end-', 'The', 'of')
+LANG_FLAGS = ((True, True, True, True), (False, True, True, True), (True, True, False, False),
+              (False, False, False, False))
+LANG_UNINDEX_KWARGS = ({}, {'specials': False}, {'start': False, 'unk': False}, {'stop': False, 'pad': False})
+
+
+def lang_cases(n_specials: int, seed: int):
+    """Seeded random id sequences over a vocabulary of LANG_TOKENS + `n_specials` special ids."""
+    import random
+    rng = random.Random(seed)
+    n = len(LANG_TOKENS) + n_specials
+    return [[[rng.randrange(n) for _ in range(rng.randint(1, 12))] for _ in range(rng.randint(1, 4))]
+            for _ in range(40)]
+
+
+def make_lang_golden(lang):
+    """`Indexer.unindex` / `Indexer.reconstruct` of the unmodified reference (`src/utils/lang.py:573-730`) on
+    seeded random sequences, for every combination of enabled specials the positional flag matching cares about."""
+    import json
+    out = []
+    for fi, (start, stop, pad, unk) in enumerate(LANG_FLAGS):
+        indexer = lang.Indexer(lang.Vocab(LANG_TOKENS), tokenize=None, start=start, stop=stop, pad=pad, unk=unk)
+        for batch in lang_cases(len(indexer.specials), seed=fi):
+            out.append({
+                'flags': fi,
+                'ids': batch,
+                'unindex': [[list(seq) for seq in indexer.unindex(batch, **kw)] for kw in LANG_UNINDEX_KWARGS],
+                'unindex_single': list(indexer.unindex(batch[0])),
+                'reconstruct': list(indexer.reconstruct(batch)),
+                'reconstruct_single': indexer.reconstruct(batch[0]),
+                'reconstruct_tokens': list(indexer.reconstruct(indexer.unindex(batch))),
+            })
+    with open(os.path.join(GOLDEN_DIR, 'lang_reconstruct.json'), 'w') as handle:
+        json.dump(out, handle, separators=(',', ':'))
+    print(f'lang golden: {len(out)} batches')
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
@@ -200,6 +237,8 @@ def main():
         return make_exemplars_golden()
     if '--only-checkpoint' in sys.argv:
         return make_checkpoint_skeleton(milan, lang)
+    if '--only-lang' in sys.argv:
+        return make_lang_golden(lang)
     make_score_golden(milan, lang, vocab)
     make_encoder_variant_goldens(milan)
     make_exemplars_golden()
@@ -223,6 +262,8 @@ def main():
                         meta=np.array([ENC_NEURONS, K, 0], dtype=np.int64))
     print('encoder golden: features', tuple(features.shape), 'abs mean', features.abs().mean().item(),
           'max', features.abs().max().item())
+
+    make_lang_golden(lang)
 
     # ---- decoder goldens, three logit regimes, from seeded features.
     feats = synthetic_features(DEC_NEURONS, K, seed=0)

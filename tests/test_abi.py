@@ -151,3 +151,47 @@ def test_reference_checkpoint_payload_is_ingested(tmp_path):
     assert our_props['indexer'] == ref_props['indexer']
     assert our_props['lm']['properties'] == ref_props['lm']['properties']
     assert our_props['encoder']['properties']['config'] == ref_props['encoder']['properties']['config']
+
+
+def test_checkpoint_with_spacy_tokenizer_child_is_ingested(tmp_path):
+    """Real MILAN checkpoints (`milan-base.pth`) carry a serialized spaCy tokenizer inside both indexers:
+    `Tokenizer.serialize()` = {'properties': {'nlp': (config_dict, bytes), lemmatize, ...}, 'children': {}}
+    (`src/utils/lang.py:14-71`, `src/utils/serialize.py:104-107`; the reference rebuilds the pipeline from the
+    tuple at `serialize.py:147-153`). Decoding never tokenises, so the payload must load without spaCy, decode
+    ids to text, and survive a save / load round trip untouched."""
+    import json
+    from neuron_descriptions_b200 import milan
+    skeleton = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'checkpoint_skeleton.json')))
+
+    def materialise(node):
+        if isinstance(node, list) and len(node) == 3 and node[0] == 'tensor':
+            return torch.full(node[1], 0.01, dtype=getattr(torch, node[2].split('.')[-1]))
+        if isinstance(node, dict):
+            return {key: materialise(value) for key, value in node.items()}
+        if isinstance(node, list):
+            return tuple(materialise(value) for value in node)
+        return node
+
+    payload = materialise(skeleton)
+    nlp = ({'nlp': {'lang': 'en', 'pipeline': ['tok2vec', 'tagger', 'lemmatizer']}, 'components': {}},
+           b'\x83\xa6config\xc0 not a real spaCy byte string, only its type matters here')
+    tokenizer = {'properties': {'nlp': nlp, 'lemmatize': True, 'lowercase': True, 'ignore_stop': True,
+                                'ignore_punct': True}, 'children': {}}
+    payload['properties']['indexer']['properties']['tokenize'] = tokenizer
+    payload['properties']['lm']['properties']['indexer']['properties']['tokenize'] = tokenizer
+    path = tmp_path / 'base.pth'
+    torch.save(payload, path)
+    decoder = milan.pretrained('base', path=path)
+    assert decoder.indexer.tokenize is None and decoder.indexer.tokenize_payload == tokenizer
+    stop = decoder.indexer.stop_index
+    assert decoder.indexer.reconstruct([[5, 0, 6, stop, 7], [stop]]) == ('The. Of', '')  # vocab: . , - ; : the of and
+    with pytest.raises(NotImplementedError, match='no tokenizer'):
+        decoder.indexer('a caption')  # scoring text needs a tokenizer: pass tokenize= explicitly
+
+    again = tmp_path / 'again.pth'
+    decoder.save(again)
+    reloaded = torch.load(again, map_location='cpu', weights_only=False)
+    for indexer in (reloaded['properties']['indexer'], reloaded['properties']['lm']['properties']['indexer']):
+        config, data = indexer['properties']['tokenize']['properties']['nlp']
+        assert isinstance(config, dict) and isinstance(data, bytes) and (config, data) == nlp
+    assert milan.pretrained('base', path=again).indexer.tokenize_payload == tokenizer

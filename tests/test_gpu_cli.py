@@ -77,7 +77,10 @@ def test_predict_streams_chunks_from_disk(tmp_path):
     assert list(captions) == list(ref)
     assert decoder.last_predict_tokens.shape == (5, 15)
     # the same through precomputed features (Encoder.map + predict(features=...), src/milan/encoders.py:61-148)
-    feats = decoder.encoder.map(dataset, batch_size=2, device='cuda:0', display_progress_as=None)
+    feats = decoder.encoder.map(dataset, image_index=2, mask_index=3, batch_size=2, device='cuda:0',
+                               display_progress_as=None)
+    with pytest.raises(ValueError, match='non-tensor images'):  # reference defaults (-3, -2) hit `unit` here
+        decoder.encoder.map(dataset, batch_size=2, display_progress_as=None)
     again = decoder.predict(dataset, features=feats, strategy='rerank', beam_size=8, batch_size=2,
                             display_progress_as=None)
     assert list(again) == list(ref)

@@ -81,3 +81,30 @@ def test_spatialize_vit_mlp_matches_reference_semantics():
                 assert out[b, unit, patch // 4, patch % 4] == hiddens[b, 1 + patch, unit]
     with pytest.raises(AssertionError):
         transforms.spatialize_vit_mlp(torch.zeros(1, 12, 3))
+
+
+def test_unindex_and_reconstruct_match_reference_golden(golden_dir):
+    """`Indexer.unindex` / `reconstruct` vs the unmodified reference on seeded random id sequences
+    (`oracle/make_golden.py::make_lang_golden`), for every special-token configuration."""
+    import json
+    from oracle.make_golden import LANG_FLAGS, LANG_TOKENS, LANG_UNINDEX_KWARGS
+    with open(os.path.join(golden_dir, 'lang_reconstruct.json')) as handle:
+        cases = json.load(handle)
+    assert len(cases) == 40 * len(LANG_FLAGS)
+    indexers = [lang.Indexer(lang.Vocab(LANG_TOKENS), tokenize=None, start=a, stop=b, pad=c, unk=d)
+                for a, b, c, d in LANG_FLAGS]
+    for case in cases:
+        indexer, batch = indexers[case['flags']], case['ids']
+        for kwargs, want in zip(LANG_UNINDEX_KWARGS, case['unindex']):
+            assert [list(seq) for seq in indexer.unindex(batch, **kwargs)] == want
+        assert list(indexer.unindex(batch[0])) == case['unindex_single']
+        assert list(indexer.reconstruct(batch)) == case['reconstruct']
+        assert indexer.reconstruct(batch[0]) == case['reconstruct_single']
+        assert list(indexer.reconstruct(indexer.unindex(batch))) == case['reconstruct_tokens']
+        assert O.reconstruct(batch[0], LANG_TOKENS) == case['reconstruct_single'] or case['flags'] != 0
+    with pytest.raises(ValueError, match='unknown index'):
+        indexers[0].unindex([len(LANG_TOKENS) + 4])
+    with pytest.raises(ValueError, match='at least one'):
+        indexers[0].reconstruct([])
+    with pytest.raises(ValueError, match='is empty'):
+        indexers[0].reconstruct([[1], []])
