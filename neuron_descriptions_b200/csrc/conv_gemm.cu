@@ -59,6 +59,8 @@ struct SmemLayout {
   static_assert(kTotalBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
+__device__ __forceinline__ float fused_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }  // as decoder.cu's
+
 // byte offset of 16-byte chunk j of row r inside a [128][128 B] tile with the TMA/UMMA 128-byte swizzle
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
 
@@ -404,6 +406,147 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             tma_store_commit_elect();
           }
         }
+      } else if (EPI == EPI_LSTM) {
+        // LSTM cell on the gate pre-activations this thread holds: columns 4u + g, g = (i, f, g, o) of unit u.
+        const FusedEpilogue& fe = p.fe;
+        const long long r = static_cast<long long>(tw) * p.box_w + row;  // flat GEMM: one output row per A row
+        if (r < p.out_w) {
+          const long long src = fe.src_row != nullptr ? fe.src_row[r] : r;
+          const float* add_row = nullptr;
+          if (fe.add_table != nullptr)
+            add_row = fe.add_table +
+                      (fe.add_index != nullptr ? fe.add_index[r * fe.add_stride] : fe.add_const) * fe.add_pitch;
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            const int col0 = n_tile * BLOCK_N + c * 64 + group * 32;
+            if (col0 < p.cout) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[c][4 * j + 0] += b.x; v[c][4 * j + 1] += b.y; v[c][4 * j + 2] += b.z; v[c][4 * j + 3] += b.w;
+              }
+              if (add_row != nullptr) {
+                const float4* a4 = reinterpret_cast<const float4*>(add_row + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(a4 + j);
+                  v[c][4 * j + 0] += b.x; v[c][4 * j + 1] += b.y; v[c][4 * j + 2] += b.z; v[c][4 * j + 3] += b.w;
+                }
+              }
+              const int u0 = col0 >> 2;  // first of this chunk's 8 hidden units
+              const float4* cp = reinterpret_cast<const float4*>(fe.c_in + src * fe.hidden + u0);
+              const float4 c_a = cp[0], c_b = cp[1];
+              const float c_prev[8] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w};
+              float c_new[8], h_new[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float gi = v[c][4 * j], gf = v[c][4 * j + 1], gg = v[c][4 * j + 2], go = v[c][4 * j + 3];
+                c_new[j] = fused_sigmoid(gf) * c_prev[j] + fused_sigmoid(gi) * tanhf(gg);
+                h_new[j] = fused_sigmoid(go) * tanhf(c_new[j]);
+              }
+              float4* co = reinterpret_cast<float4*>(fe.c_out + r * fe.hidden + u0);
+              co[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+              co[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+              if (fe.h_f32 != nullptr) {
+                float4* ho = reinterpret_cast<float4*>(fe.h_f32 + r * fe.hidden + u0);
+                ho[0] = make_float4(h_new[0], h_new[1], h_new[2], h_new[3]);
+                ho[1] = make_float4(h_new[4], h_new[5], h_new[6], h_new[7]);
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split_fp16x2(h_new[2 * j], h_new[2 * j + 1], hi[j], lo[j]);
+              *reinterpret_cast<uint4*>(fe.h_hi + r * fe.h_pitch + u0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (SPLIT) *reinterpret_cast<uint4*>(fe.h_lo + r * fe.h_pitch + u0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      } else if (EPI == EPI_HEAD) {
+        const FusedEpilogue& fe = p.fe;
+        const long long r = static_cast<long long>(tw) * p.box_w + row;
+        const bool valid = r < p.out_w;
+        const int tile_col0 = n_tile * BLOCK_N + group * 32;  // chunk c adds 64 c
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {  // + bias (padded to whole tiles)
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + tile_col0 + c * 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[c][4 * j + 0] += b.x; v[c][4 * j + 1] += b.y; v[c][4 * j + 2] += b.z; v[c][4 * j + 3] += b.w;
+          }
+        }
+        if (n_tile < fe.vocab_tiles) {
+          // vocabulary logits: optional store, softmax partial of this thread's 64 columns, optional target gather
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            const int col0 = tile_col0 + c * 64;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j >= fe.vocab) v[c][j] = -INFINITY;
+              mx = fmaxf(mx, v[c][j]);
+            }
+          }
+          float sum = 0.f;
+          if (mx > -INFINITY) {
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sum += expf(v[c][j] - mx);
+          }
+          if (valid) {
+            fe.partials[r * (2 * fe.vocab_tiles) + n_tile * 2 + group] = make_float2(mx, sum);
+            if (fe.logits != nullptr) {
+#pragma unroll
+              for (int c = 0; c < kChunks; ++c) {
+                const int col0 = tile_col0 + c * 64;
+                float* o = fe.logits + r * fe.ld_logits + col0;
+                if (col0 + 32 <= fe.vocab) {
+                  float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    o4[j] = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (col0 + j < fe.vocab) o[j] = v[c][j];
+                }
+              }
+            }
+            if (fe.target != nullptr) {
+              const int rel = static_cast<int>(fe.target[r * fe.target_stride]) - tile_col0;  // column within this thread's view
+              if (rel >= 0 && rel < 96 && (rel & 32) == 0) {  // [0, 32) -> chunk 0, [64, 96) -> chunk 1
+                float t = 0.f;
+#pragma unroll
+                for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (rel == c * 64 + j) t = v[c][j];
+                fe.tgt_logit[r] = t;
+              }
+            }
+          }
+        } else if (valid) {
+          const bool is_q = n_tile < fe.vocab_tiles + fe.q_tiles;
+          const int base = is_q ? (n_tile - fe.vocab_tiles) * BLOCK_N + group * 32
+                                : (n_tile - fe.vocab_tiles - fe.q_tiles) * BLOCK_N + group * 32;
+          const int limit = is_q ? fe.q_cols : fe.gate_cols;
+          float* dst = is_q ? fe.q_out + r * fe.q_pitch : fe.g_out + r * fe.g_pitch;
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            const int col0 = base + c * 64;
+            if (col0 + 32 <= limit) {  // sections are multiples of 32 columns wide
+              if (!is_q) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[c][j] = fused_sigmoid(v[c][j]);
+              }
+              float4* o4 = reinterpret_cast<float4*>(dst + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                o4[j] = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+            }
+          }
+        }
       } else {  // EPI_F32: direct fp32 stores, 128 B contiguous per thread per 32-column chunk
         const int w = tw * p.box_w + dw, h = th * p.box_h + dh, n = tn * p.box_n + dn;
         const bool valid = row_in_box && w < p.out_w && h < p.out_h && n < p.out_n;
@@ -506,7 +649,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     }();
     // fp32-output GEMMs (decoder / LM) store 4 bytes per element from the epilogue: only the K = 4544 LSTM input GEMM is
     // main-loop-bound (ncu, one decode step: K = 512 GEMMs 53 -> 62 us with the wide form, K = 4544 172 -> 160 us)
-    const int need_k = epilogue == EPI_F32 ? 8 * min_k : min_k;
+    const int need_k = epilogue != EPI_BF16 ? 8 * min_k : min_k;
     wide = min_k > 0 && num_kb * bk >= need_k;  // (the stem, K = 224, stays on three MMAs: 0.370 vs 0.382 ms)
   }
   static const bool pair_mode = [] {
@@ -536,6 +679,9 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
   MILAN_DISPATCH(128, true, EPI_F32, false, 64, false)
   MILAN_DISPATCH(128, true, EPI_F32, false, 64, true)
   MILAN_DISPATCH(128, false, EPI_F32, false, 64, false)
+  MILAN_DISPATCH(128, true, EPI_LSTM, false, 64, false)
+  MILAN_DISPATCH(128, true, EPI_LSTM, false, 64, true)
+  MILAN_DISPATCH(128, true, EPI_HEAD, false, 64, false)
 #undef MILAN_DISPATCH
   return static_cast<int>(cudaErrorInvalidValue);
 }

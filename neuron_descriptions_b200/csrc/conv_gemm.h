@@ -29,6 +29,50 @@ constexpr int kGemmBlockK = 64;
 enum EpilogueKind : int {
   EPI_BF16 = 0,  // out_hi(/out_lo) bf16 NHWC, + bias, + residual, optional ReLU
   EPI_F32 = 1,   // out_f32 row-major [pixel][ldc], + bias
+  EPI_LSTM = 2,  // LSTM cell in the epilogue: the GEMM's columns are gate pre-activations (FusedEpilogue)
+  EPI_HEAD = 3,  // everything that reads h': vocabulary logits + softmax partials | attention query | feature gate
+};
+
+// Arguments of the fused decoder epilogues (flat GEMMs only: one output row per A row).
+//
+// EPI_LSTM (Decoder.step's LSTMCell, src/milan/decoders.py:619; LanguageModel's nn.LSTM, src/milan/lms.py:50-54):
+//   the weight rows are interleaved so that column 4u + g is gate g (i, f, g, o) of hidden unit u; an epilogue
+//   thread therefore owns all four gates of 8 units per 32-column chunk and finishes the cell in registers:
+//   c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c'). The pre-activation never reaches memory.
+// EPI_HEAD (the three linears applied to h': output.1, attend.query_to_hidden, feature_gate.0,
+//   decoders.py:612-621; LM: output.0, lms.py:55-56): column tiles [0, vocab_tiles) are vocabulary logits, the
+//   next q_tiles are the attention query, the rest the feature gate. Each thread reduces its 64 logits of a row to
+//   a (max, sum exp(x - max)) partial; log-softmax is finished by the consumer from 2 * vocab_tiles partials per row.
+struct FusedEpilogue {
+  // ---- EPI_LSTM
+  int hidden;                // H (N = 4H)
+  const float* c_in;         // [rows][H]; row src_row[r] when src_row != nullptr
+  float* c_out;              // [rows][H] (may alias c_in only when src_row == nullptr)
+  const int* src_row;        // beam backpointers: the parent row whose cell state this row continues
+  __nv_bfloat16* h_hi;       // h' as fp16 (hi, lo) planes, row pitch h_pitch elements
+  __nv_bfloat16* h_lo;
+  long long h_pitch;
+  float* h_f32;              // optional [rows][H]
+  const float* add_table;    // optional: pre-activation += add_table[index(r)][col]  (an embedding folded through
+  long long add_pitch;       //           W_ih: the LM's first layer), index(r) = add_index[r * add_stride] or add_const
+  const long long* add_index;
+  long long add_stride;
+  long long add_const;
+  // ---- EPI_HEAD
+  int vocab_tiles, q_tiles;  // column tiles of 128; gate tiles = n_tiles - vocab_tiles - q_tiles
+  int vocab;                 // valid vocabulary columns
+  float* logits;             // [rows][ld_logits] or nullptr (not stored)
+  long long ld_logits;
+  float2* partials;          // [rows][2 * vocab_tiles]: (max, sum exp(x - max)) of each thread's 64 columns
+  float* q_out;              // [rows][q_pitch]
+  long long q_pitch;
+  int q_cols;                // valid query columns (A)
+  float* g_out;              // [rows][g_pitch] = sigmoid(gate pre-activation)
+  long long g_pitch;
+  int gate_cols;             // valid gate columns (F)
+  const long long* target;   // optional: tgt_logit[r] = logit[r][target[r * target_stride]] (LM scoring)
+  long long target_stride;
+  float* tgt_logit;
 };
 
 struct alignas(64) ConvGemmParams {
@@ -61,6 +105,7 @@ struct alignas(64) ConvGemmParams {
   float* out_f32;
   long long ldc;             // row pitch (elements) of the output / residual
   int relu;
+  FusedEpilogue fe;          // EPI_LSTM / EPI_HEAD only
 };
 
 // block_n: 64 or 128. split: hi/lo planes (1) or hi only (0). Returns cudaError_t as int.
@@ -165,5 +210,11 @@ int build_gemm_params(ConvGemmParams* p, long long M, int K, int N, const __nv_b
                       const __nv_bfloat16* a_lo, long long a_pitch, const __nv_bfloat16* w_hi,
                       const __nv_bfloat16* w_lo, const float* bias, float* out, long long ldc, int split,
                       int fp16_operands = 0);
+// Same with the A rows given as TWO matrices side by side, A = [A0 | A1] (K = K0 + K1, both multiples of 64): the
+// second LSTM layer of the LM reads [h of layer 0 | its own h] without either being copied next to the other.
+int build_gemm2_params(ConvGemmParams* p, long long M, int K0, int K1, int N, const __nv_bfloat16* a0_hi,
+                       const __nv_bfloat16* a0_lo, long long a0_pitch, const __nv_bfloat16* a1_hi,
+                       const __nv_bfloat16* a1_lo, long long a1_pitch, const __nv_bfloat16* w_hi,
+                       const __nv_bfloat16* w_lo, const float* bias, int split, int fp16_operands = 0);
 
 }  // namespace milan

@@ -324,4 +324,34 @@ int build_gemm_params(ConvGemmParams* p, long long M, int K, int N, const __nv_b
   return 0;
 }
 
+int build_gemm2_params(ConvGemmParams* p, long long M, int K0, int K1, int N, const __nv_bfloat16* a0_hi,
+                       const __nv_bfloat16* a0_lo, long long a0_pitch, const __nv_bfloat16* a1_hi,
+                       const __nv_bfloat16* a1_lo, long long a1_pitch, const __nv_bfloat16* w_hi,
+                       const __nv_bfloat16* w_lo, const float* bias, int split, int fp16_operands) {
+  if (K1 % kGemmBlockK != 0) return -2;
+  int rc = build_gemm_params(p, M, K0, N, a0_hi, a0_lo, a0_pitch, w_hi, w_lo, bias, nullptr, N, split, fp16_operands);
+  if (rc) return rc;
+  // two "taps" of different depth, each with its own tensor map (the mechanism of build_dual_1x1_params)
+  p->num_taps = 2;
+  p->tap_plane[0] = 0; p->tap_plane[1] = 1;
+  p->tap_cb[0] = static_cast<int16_t>(K0 / kGemmBlockK);
+  p->tap_cb[1] = static_cast<int16_t>(K1 / kGemmBlockK);
+  const __nv_bfloat16* a1_planes[2] = {a1_hi, a1_lo};
+  const __nv_bfloat16* w_planes[2] = {w_hi, w_lo};
+  const int np = split ? 2 : 1;
+  const uint64_t ktot = static_cast<uint64_t>(K0) + K1;
+  for (int hl = 0; hl < np; ++hl) {
+    const uint64_t pitch = static_cast<uint64_t>(a1_pitch) * 2;
+    rc = make_tmap_4d(&p->tmap_a[hl][1], a1_planes[hl], K1, M, 1, 1, pitch, pitch * M, pitch * M, kGemmBlockM, 1, 1);
+    if (rc) return rc;
+    rc = make_tmap_2d(&p->tmap_b[hl], w_planes[hl], ktot, N, ktot * 2, 128);
+    if (rc) return rc;
+  }
+  if (!split) {
+    p->tmap_b[1] = p->tmap_b[0];
+    p->tmap_a[1][1] = p->tmap_a[0][1];
+  }
+  return 0;
+}
+
 }  // namespace milan

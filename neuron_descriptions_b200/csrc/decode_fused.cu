@@ -1,0 +1,560 @@
+// Fused non-GEMM kernels of the beam step and the LM rerank (see decode_fused.h). fp32 throughout; operands that
+// feed a tensor-core GEMM are emitted as IEEE fp16 (hi, lo) pairs like decoder.cu does.
+#include "decode_fused.h"
+
+#include "conv_gemm.h"  // note_launch
+#include "decoder.h"    // kMaxBeam
+#include "ptx.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace milan {
+
+namespace {
+
+__device__ __forceinline__ void store_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, float v0,
+                                             float v1) {
+  uint32_t h, l;
+  split_fp16x2(v0, v1, h, l);
+  *reinterpret_cast<uint32_t*>(hi + off) = h;
+  if (lo != nullptr) *reinterpret_cast<uint32_t*>(lo + off) = l;
+}
+
+// tanh through one ex2 and one rcp: |error| < 2e-7 absolute on the clamped range (tanh(15) rounds to 1.0f). The
+// attention scores sum 512 of these against |w_o| ~ 0.04: far below the 1e-5 the split-fp16 GEMMs leave.
+__device__ __forceinline__ float tanh_fast(float x) {
+  x = fminf(fmaxf(x, -15.0f), 15.0f);
+  const float t = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, t + 1.0f);
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct ValIdx {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(const ValIdx& a, const ValIdx& b) {  // a strictly preferred over b
+  return a.v > b.v || (a.v == b.v && a.i < b.i);
+}
+__device__ __forceinline__ ValIdx warp_argmax(ValIdx x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ValIdx y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    if (better(y, x)) x = y;
+  }
+  return x;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned float_key(float x) {  // order-preserving float -> uint
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ------------------------------------------------------------------ attention + gating + operand assembly
+// Cluster of kAttendCluster CTAs per feature set (neuron). Phase A: the neuron's rows are dealt round-robin to the
+// CTAs; each computes its rows' attention weights (one warp per key), writes the token embedding and copies the
+// parent's h' into the operand row. Cluster barrier. Phase B: each CTA owns a column slice of the features, reads it
+// ONCE into registers and produces that slice of `attenuated * gate` for every row of the neuron.
+__global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
+    attend_fused_kernel(const AttendFusedArgs a) {
+  if (a.skip != nullptr && *a.skip) return;  // uniform over the grid
+  extern __shared__ float sm[];
+  float* q_s = sm;                         // [A]
+  float* sc_s = q_s + a.A;                 // [kFusedMaxKeys]
+  float* w_s = sc_s + kFusedMaxKeys;       // [rpf][n_keys]
+  int* src_s = reinterpret_cast<int*>(w_s + a.rows_per_feature * a.n_keys);  // [rpf]
+  const int fidx = blockIdx.x / kAttendCluster;
+  const int crank = blockIdx.x % kAttendCluster;
+  const int rpf = a.rows_per_feature;
+  const long long row0 = static_cast<long long>(fidx) * rpf;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int rl = crank; rl < rpf; rl += kAttendCluster) {
+    const long long r = row0 + rl;
+    const long long src = a.src_row != nullptr ? a.src_row[r] : r;
+    const float* qrow = a.q + src * a.q_pitch;
+    for (int i = threadIdx.x; i < a.A; i += blockDim.x) q_s[i] = qrow[i];
+    __syncthreads();
+    for (int k = warp; k < a.n_keys; k += 8) {
+      const float* khr = a.kh + (static_cast<long long>(fidx) * a.n_keys + k) * a.A;
+      float s = 0.f;
+      for (int i = lane; i < a.A; i += 32) s += __ldg(a.w_o + i) * tanh_fast(q_s[i] + __ldg(khr + i));
+      s = warp_sum(s);
+      if (lane == 0) sc_s[k] = s + a.b_o;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int k = 0; k < a.n_keys; ++k) mx = fmaxf(mx, sc_s[k]);
+    float den = 0.f;
+    for (int k = 0; k < a.n_keys; ++k) den += expf(sc_s[k] - mx);
+    if (threadIdx.x < a.n_keys) {
+      const float w = expf(sc_s[threadIdx.x] - mx) / den;
+      a.attn_ws[r * a.n_keys + threadIdx.x] = w;
+      if (a.attn_out != nullptr) a.attn_out[r * a.attn_pitch + threadIdx.x] = w;
+    }
+    const long long xoff = r * a.x_pitch;
+    const float* erow = a.embedding + a.tokens[r] * a.E;
+    for (int e2 = threadIdx.x; e2 < a.E / 2; e2 += blockDim.x) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(erow + 2 * e2));
+      store_split2(a.x_hi, a.x_lo, xoff + 2 * e2, v.x, v.y);
+    }
+    if (a.h_src_hi != nullptr) {  // the recurrent state follows the backpointer
+      const long long dst = xoff + a.E + a.F, from = src * a.h_src_pitch;
+      for (int j = threadIdx.x; j < a.H / 8; j += blockDim.x) {
+        *reinterpret_cast<uint4*>(a.x_hi + dst + 8 * j) = *reinterpret_cast<const uint4*>(a.h_src_hi + from + 8 * j);
+        if (a.x_lo != nullptr)
+          *reinterpret_cast<uint4*>(a.x_lo + dst + 8 * j) = *reinterpret_cast<const uint4*>(a.h_src_lo + from + 8 * j);
+      }
+    }
+    __syncthreads();  // q_s / sc_s are reused by the next row
+  }
+  __threadfence();
+  cluster_sync_all();
+
+  // phase B. attn_ws was written by other CTAs of this cluster during this kernel: plain (coherent) loads only.
+  const volatile float* ws = a.attn_ws + row0 * a.n_keys;
+  for (int i = threadIdx.x; i < rpf * a.n_keys; i += blockDim.x) w_s[i] = ws[i];
+  for (int i = threadIdx.x; i < rpf; i += blockDim.x)
+    src_s[i] = a.src_row != nullptr ? a.src_row[row0 + i] : static_cast<int>(row0 + i);
+  __syncthreads();
+  const int F2 = a.F / 2;
+  const int per = (F2 + kAttendCluster - 1) / kAttendCluster;
+  const int j_end = min(F2, (crank + 1) * per);
+  const float* fb = a.features + static_cast<long long>(fidx) * a.n_keys * a.F;
+  for (int j2 = crank * per + threadIdx.x; j2 < j_end; j2 += blockDim.x) {
+    float2 f[kFusedMaxKeys];
+#pragma unroll
+    for (int k = 0; k < kFusedMaxKeys; ++k)
+      f[k] = k < a.n_keys ? __ldg(reinterpret_cast<const float2*>(fb + static_cast<long long>(k) * a.F + 2 * j2))
+                          : make_float2(0.f, 0.f);
+    for (int rl = 0; rl < rpf; ++rl) {
+      const float* w = w_s + rl * a.n_keys;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kFusedMaxKeys; ++k) {
+        if (k < a.n_keys) {
+          s0 += w[k] * f[k].x;
+          s1 += w[k] * f[k].y;
+        }
+      }
+      const float2 g = *reinterpret_cast<const float2*>(a.gate + static_cast<long long>(src_s[rl]) * a.gate_pitch + 2 * j2);
+      store_split2(a.x_hi, a.x_lo, (row0 + rl) * a.x_pitch + a.E + 2 * j2, s0 * g.x, s1 * g.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ per-neuron top-k + beam merge
+// Exact top-`beam` of one row by MSB radix select (the fallback of decoder.cu's row_kernel, run here by the first 256
+// threads of the CTA on a row staged in shared memory): only reached when more than kSelectCandCap values pass the
+// prefilter, e.g. masses of tied logits.
+__device__ void exact_topk_256(const float* pred_s, int V, int beam, float lp, float* cv, int* cc, unsigned* hist,
+                               unsigned* warp_tot, unsigned* sel, int* counts, float* cval, int* cidx, int* eqidx) {
+  const int tid = threadIdx.x;  // < 256
+  const int lane = tid & 31, warp = tid >> 5;
+  unsigned prefix = 0, need = static_cast<unsigned>(beam);
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    named_bar_sync(1, 256);
+    for (int v = tid; v < V; v += 256) {
+      const unsigned k = float_key(pred_s[v]);
+      if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    named_bar_sync(1, 256);
+    const unsigned own = hist[tid];
+    unsigned suf = own;  // inclusive suffix sum over digits (thread t <-> digit t)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    if (lane == 0) warp_tot[warp] = suf;
+    named_bar_sync(1, 256);
+    for (int w = warp + 1; w < 8; ++w) suf += warp_tot[w];
+    const unsigned excl = suf - own;
+    if (excl < need && suf >= need) {
+      sel[0] = tid;
+      sel[1] = need - excl;
+    }
+    named_bar_sync(1, 256);
+    prefix = (prefix << 8) | sel[0];
+    need = sel[1];
+    named_bar_sync(1, 256);
+  }
+  if (tid == 0) { counts[0] = 0; counts[1] = 0; }
+  named_bar_sync(1, 256);
+  for (int v = tid; v < V; v += 256) {
+    const float x = pred_s[v];
+    const unsigned k = float_key(x);
+    if (k > prefix) {
+      const int pos = atomicAdd(&counts[0], 1);
+      cval[pos] = x;
+      cidx[pos] = v;
+    } else if (k == prefix) {
+      const int pos = atomicAdd(&counts[1], 1);
+      if (pos < kMaxBeam) eqidx[pos] = v;
+    }
+  }
+  named_bar_sync(1, 256);
+  if (tid == 0) {
+    const int base = counts[0];
+    const int take = static_cast<int>(need);
+    if (counts[1] <= kMaxBeam) {
+      for (int i = 1; i < counts[1]; ++i) {  // by index (almost always a single element)
+        const int x = eqidx[i];
+        int j = i - 1;
+        while (j >= 0 && eqidx[j] > x) { eqidx[j + 1] = eqidx[j]; --j; }
+        eqidx[j + 1] = x;
+      }
+      for (int i = 0; i < take; ++i) { cidx[base + i] = eqidx[i]; cval[base + i] = pred_s[eqidx[i]]; }
+    } else {  // many exact ties: lowest indices by a linear scan
+      int got = 0;
+      for (int v = 0; v < V && got < take; ++v)
+        if (float_key(pred_s[v]) == prefix) { cidx[base + got] = v; cval[base + got] = pred_s[v]; ++got; }
+    }
+  }
+  named_bar_sync(1, 256);
+  for (int i = tid; i < beam; i += 256) {
+    const ValIdx me{cval[i], cidx[i]};
+    int rank = 0;
+    for (int j = 0; j < beam; ++j) rank += better(ValIdx{cval[j], cidx[j]}, me) ? 1 : 0;
+    cv[rank] = me.v + lp;
+    cc[rank] = me.i;
+  }
+  named_bar_sync(1, 256);
+}
+
+struct SelectSmem {  // fixed part of beam_select's shared memory
+  float best[kMaxBeam];
+  int flat[kMaxBeam];
+  float row_max[kMaxBeam];
+  float row_lse[kMaxBeam];
+  float row_lp[kMaxBeam];
+  int fallback_rows[kMaxBeam];
+  int n_fallback;
+  float tau[kSelectThreads / 32];
+  unsigned hist[256];
+  unsigned warp_tot[8];
+  unsigned sel[2];
+  int counts[2];
+  float cval[kMaxBeam];
+  int cidx[kMaxBeam];
+  int eqidx[kMaxBeam];
+};
+constexpr int kWarpScratchFloats = 2 * kSelectCandCap + kSelectMaxGroups;  // cand values | cand ids | group maxima
+
+__global__ void __launch_bounds__(kSelectThreads) beam_select_kernel(const BeamSelectArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SelectSmem& S = *reinterpret_cast<SelectSmem*>(smem_raw);
+  float* val_s = reinterpret_cast<float*>(smem_raw + sizeof(SelectSmem));  // [in_rows][beam] candidate scores
+  int* cls_s = reinterpret_cast<int*>(val_s + a.in_rows * a.beam);          // [in_rows][beam] candidate classes
+  float* scratch = reinterpret_cast<float*>(cls_s + a.in_rows * a.beam);    // per-warp scratch, or one staged row
+  const int nrn = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+
+  if (*a.done_flag != 0) {
+    // every beam of every neuron has ended: the reference has left its loop; the beams stay as they are
+    for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
+      const int out = nrn * a.beam + j;
+      a.next_tokens[out] = a.stop_index;
+      a.next_lp[out] = a.cur_lp[out];
+      a.backptr[out] = out;
+      a.hist_tok[out] = static_cast<int>(a.stop_index);
+      a.hist_bp[out] = j;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) S.n_fallback = 0;
+  __syncthreads();
+
+  const int row_base = nrn * a.in_rows;
+  const int V4 = static_cast<int>(a.ld >> 2);
+  // ---- per row (one warp each): finish the log-softmax, prefilter, rank
+  for (int rl = warp; rl < a.in_rows; rl += n_warps) {
+    const long long r = row_base + rl;
+    float* cv = val_s + rl * a.beam;
+    int* cc = cls_s + rl * a.beam;
+    const float lp = a.last_lp != nullptr ? a.last_lp[r] : 0.0f;
+    if (a.last_tokens[r] == a.stop_index) {
+      // finished beam: only <stop> at cost 0 survives (allennlp log_probs_after_end); the other per-node candidates
+      // carry min_value_of_dtype there and are never selected while >= beam finite candidates exist
+      for (int j = lane; j < a.beam; j += 32) {
+        cv[j] = j == 0 ? lp + 0.0f : -INFINITY;
+        cc[j] = static_cast<int>(a.stop_index);
+      }
+      continue;
+    }
+    const float2* pr = a.partials + r * a.n_seg;
+    float m = -INFINITY;
+    for (int i = lane; i < a.n_seg; i += 32) m = fmaxf(m, pr[i].x);
+    const float M = warp_max(m);
+    float s = 0.f;
+    for (int i = lane; i < a.n_seg; i += 32) {
+      const float2 q = pr[i];
+      if (q.y > 0.f) s += q.y * expf(q.x - M);
+    }
+    const float lse = logf(warp_sum(s));
+    float* cand_v = scratch + warp * kWarpScratchFloats;
+    int* cand_i = reinterpret_cast<int*>(cand_v + kSelectCandCap);
+    float* gm = cand_v + 2 * kSelectCandCap;
+    // The beam-th largest of G disjoint segment maxima bounds the beam-th largest value of the row from below.
+    const int per = (a.n_seg + kSelectMaxGroups - 1) / kSelectMaxGroups;
+    const int G = (a.n_seg + per - 1) / per;
+    for (int g = lane; g < G; g += 32) {
+      float x = -INFINITY;
+      for (int i = g * per; i < min(a.n_seg, (g + 1) * per); ++i) x = fmaxf(x, pr[i].x);
+      gm[g] = x;
+    }
+    if (lane == 0) S.tau[warp] = -INFINITY;
+    __syncwarp();
+    if (G >= a.beam) {
+      for (int g = lane; g < G; g += 32) {
+        const ValIdx me{gm[g], g};
+        int rank = 0;
+        for (int j = 0; j < G; ++j) rank += better(ValIdx{gm[j], j}, me) ? 1 : 0;
+        if (rank == a.beam - 1) S.tau[warp] = me.v;
+      }
+    }
+    __syncwarp();
+    // compare in the log-softmax domain: distinct logits may round to equal log-probabilities, and ties are ranked
+    // by class index
+    const float y_tau = (S.tau[warp] - M) - lse;
+    const float4* x4 = reinterpret_cast<const float4*>(a.logits + r * a.ld);
+    int count = 0;
+    for (int base = 0; base < V4; base += 32) {
+      const int idx = base + lane;
+      float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (idx < V4) q = x4[idx];
+      const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int v = 4 * idx + c;
+        const float y = (e[c] - M) - lse;
+        const bool take = idx < V4 && v < a.V && y >= y_tau;
+        const unsigned ballot = __ballot_sync(0xffffffffu, take);
+        if (take) {
+          const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+          if (pos < kSelectCandCap) { cand_v[pos] = y; cand_i[pos] = v; }
+        }
+        count += __popc(ballot);
+      }
+    }
+    __syncwarp();
+    if (count > kSelectCandCap) {  // warp-uniform
+      if (lane == 0) {
+        const int slot = atomicAdd(&S.n_fallback, 1);
+        S.fallback_rows[slot] = rl;
+        S.row_max[rl] = M;
+        S.row_lse[rl] = lse;
+        S.row_lp[rl] = lp;
+      }
+      continue;
+    }
+    for (int j = count + lane; j < a.beam; j += 32) {  // fewer candidates than beams (NaN rows): pad
+      cv[j] = -INFINITY;
+      cc[j] = 0;
+    }
+    for (int i = lane; i < count; i += 32) {
+      const ValIdx me{cand_v[i], cand_i[i]};
+      int rank = 0;
+      for (int j = 0; j < count; ++j) rank += better(ValIdx{cand_v[j], cand_i[j]}, me) ? 1 : 0;
+      if (rank < a.beam) {
+        cv[rank] = me.v + lp;
+        cc[rank] = me.i;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- rows the prefilter could not bound: exact radix select on the staged row, first 256 threads
+  const int n_fallback = S.n_fallback;
+  if (n_fallback > 0 && threadIdx.x < 256) {
+    float* pred_s = scratch;
+    for (int f = 0; f < n_fallback; ++f) {
+      const int rl = S.fallback_rows[f];
+      const float* x = a.logits + static_cast<long long>(row_base + rl) * a.ld;
+      const float M = S.row_max[rl], lse = S.row_lse[rl];
+      for (int v = threadIdx.x; v < a.V; v += 256) pred_s[v] = (x[v] - M) - lse;
+      named_bar_sync(1, 256);
+      exact_topk_256(pred_s, a.V, a.beam, S.row_lp[rl], val_s + rl * a.beam, cls_s + rl * a.beam, S.hist, S.warp_tot,
+                     S.sel, S.counts, S.cval, S.cidx, S.eqidx);
+    }
+  }
+  __syncthreads();
+  // ---- merge: the next beam = the `beam` best of the in_rows sorted lists (one warp, two list heads per lane)
+  if (warp == 0) {
+    int ptr0 = 0, ptr1 = 0;
+    const int r0 = lane, r1 = lane + 32;
+    for (int j = 0; j < a.beam; ++j) {
+      ValIdx c0{-INFINITY, 0x7fffffff}, c1{-INFINITY, 0x7fffffff};
+      if (r0 < a.in_rows && ptr0 < a.beam) c0 = ValIdx{val_s[r0 * a.beam + ptr0], r0 * a.beam + ptr0};
+      if (r1 < a.in_rows && ptr1 < a.beam) c1 = ValIdx{val_s[r1 * a.beam + ptr1], r1 * a.beam + ptr1};
+      ValIdx best = better(c1, c0) ? c1 : c0;
+      best = warp_argmax(best);
+      int flat = best.i;
+      if (flat == 0x7fffffff) flat = 0;  // degenerate (fewer finite candidates than beams)
+      const int src = flat / a.beam;
+      if (src == r0) ++ptr0;
+      if (src == r1) ++ptr1;
+      if (lane == 0) {
+        S.flat[j] = flat;
+        S.best[j] = best.v;
+      }
+    }
+  }
+  __syncthreads();
+  int ended = 1;
+  for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
+    const int out = nrn * a.beam + j;
+    const int flat = S.flat[j];
+    const int src = flat / a.beam;
+    const int cls = cls_s[flat];
+    a.next_tokens[out] = cls;
+    a.next_lp[out] = S.best[j];
+    a.backptr[out] = row_base + src;
+    a.hist_tok[out] = cls;
+    a.hist_bp[out] = src;
+    if (cls != a.stop_index) ended = 0;
+  }
+  // allennlp: `if (last_predictions == end).all(): break` — the last CTA to finish publishes it for the next step
+  ended = __syncthreads_and(ended);
+  if (threadIdx.x == 0) {
+    if (ended) atomicAdd(&a.counters[0], 1);
+    __threadfence();
+    const int ticket = atomicAdd(&a.counters[1], 1);
+    if (ticket == a.n_neurons - 1) {
+      __threadfence();
+      const int all = atomicAdd(&a.counters[0], 0);
+      *a.done_flag = all == a.n_neurons ? 1 : 0;
+      a.counters[0] = 0;
+      a.counters[1] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LM rerank read-out
+__global__ void __launch_bounds__(256) lm_finalize_kernel(const LmFinalizeArgs a) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= a.M) return;
+  const int T = a.group_T[(m / a.beam) / a.group_size];
+  const long long* seq = a.seqs + static_cast<long long>(m) * a.length;
+  // inputs = [<start>, seq...]; target t (= seq[t]) is kept iff no <stop> among inputs[0..t-1], i.e. the first <stop>
+  // in seq sits at index >= t-1: the token AFTER the first <stop> is still counted (lms.py:93-96).
+  int first_stop = a.length + 8;
+  for (int i = 0; i < T; ++i)
+    if (seq[i] == a.stop_index) { first_stop = i; break; }
+  float score = 0.f;
+  for (int t = 0; t < T && t <= first_stop + 1; ++t) {
+    const float2* pr = a.partials + (static_cast<long long>(t) * a.M + m) * a.n_seg;
+    float mx = -INFINITY;
+    for (int i = lane; i < a.n_seg; i += 32) mx = fmaxf(mx, pr[i].x);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < a.n_seg; i += 32) {
+      const float2 q = pr[i];
+      if (q.y > 0.f) s += q.y * expf(q.x - mx);
+    }
+    s = warp_sum(s);
+    score += (a.tgt_logit[static_cast<long long>(t) * a.M + m] - mx) - logf(s);
+  }
+  if (lane == 0) a.lm_scores[m] = score;
+}
+
+__global__ void __launch_bounds__(256) lm_input_table_kernel(const float* __restrict__ w_ih,
+                                                             const float* __restrict__ emb, int E, int H,
+                                                             float* __restrict__ table) {
+  extern __shared__ float e_s[];  // [E]
+  const int v = blockIdx.x;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) e_s[i] = emb[static_cast<long long>(v) * E + i];
+  __syncthreads();
+  for (int col = threadIdx.x; col < 4 * H; col += blockDim.x) {
+    const int u = col >> 2, g = col & 3;
+    const float* w = w_ih + static_cast<long long>(g * H + u) * E;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = fmaf(w[e], e_s[e], acc);
+    table[static_cast<long long>(v) * 4 * H + col] = acc;
+  }
+}
+
+inline int last_err() {
+  note_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// cudaFuncSetAttribute is per device: remember what each device has been configured for
+template <class K>
+int ensure_dynamic_smem(K kernel, size_t bytes, size_t (&configured)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
+  if (bytes > configured[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured[dev] = bytes;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int launch_attend_fused(const AttendFusedArgs& a, cudaStream_t stream) {
+  if (a.R == 0) return 0;
+  if (a.n_keys > kFusedMaxKeys || a.rows_per_feature < 1 || a.R % a.rows_per_feature != 0 || (a.F & 1) || (a.E & 1) ||
+      (a.H & 7))
+    return static_cast<int>(cudaErrorInvalidValue);
+  const size_t smem = (a.A + kFusedMaxKeys + static_cast<size_t>(a.rows_per_feature) * a.n_keys) * sizeof(float) +
+                      a.rows_per_feature * sizeof(int);
+  if (smem > 48 * 1024) return static_cast<int>(cudaErrorInvalidValue);
+  const int sets = a.R / a.rows_per_feature;
+  attend_fused_kernel<<<sets * kAttendCluster, 256, smem, stream>>>(a);
+  return last_err();
+}
+
+size_t beam_select_smem_bytes(int in_rows, int beam, int V) {
+  const size_t lists = static_cast<size_t>(in_rows) * beam * (sizeof(float) + sizeof(int));
+  const size_t warps = static_cast<size_t>(kSelectThreads / 32) * kWarpScratchFloats * sizeof(float);
+  const size_t staged = static_cast<size_t>(V) * sizeof(float);
+  return sizeof(SelectSmem) + lists + (warps > staged ? warps : staged) + 16;
+}
+
+int launch_beam_select(const BeamSelectArgs& a, cudaStream_t stream) {
+  if (a.n_neurons == 0) return 0;
+  if (a.beam < 1 || a.beam > kMaxBeam || a.in_rows < 1 || a.in_rows > 64 || a.n_seg < 1 || (a.ld & 3))
+    return static_cast<int>(cudaErrorInvalidValue);
+  const size_t smem = beam_select_smem_bytes(a.in_rows, a.beam, a.V);
+  if (smem > 227 * 1024) return static_cast<int>(cudaErrorInvalidValue);
+  static size_t configured[64] = {};
+  if (int rc = ensure_dynamic_smem(beam_select_kernel, smem, configured)) return rc;
+  beam_select_kernel<<<a.n_neurons, kSelectThreads, smem, stream>>>(a);
+  return last_err();
+}
+
+int launch_lm_finalize(const LmFinalizeArgs& a, cudaStream_t stream) {
+  if (a.M == 0) return 0;
+  lm_finalize_kernel<<<(a.M + 7) / 8, 256, 0, stream>>>(a);
+  return last_err();
+}
+
+int launch_lm_input_table(const float* w_ih, const float* emb, int V, int E, int H, float* table, cudaStream_t stream) {
+  lm_input_table_kernel<<<V, 256, E * sizeof(float), stream>>>(w_ih, emb, E, H, table);
+  return last_err();
+}
+
+}  // namespace milan

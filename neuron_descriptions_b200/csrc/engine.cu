@@ -3,6 +3,7 @@
 #include "milan_b200.h"
 
 #include "conv_gemm.h"
+#include "decode_fused.h"
 #include "decoder.h"
 #include "encoder.h"
 
@@ -178,6 +179,17 @@ struct MilanEngine {
   float* emb = nullptr;
   float* lm_emb = nullptr;
   int ldv = 0;
+  // ---- fused beam step / LM rerank (decode_fused.h): gate-interleaved LSTM weights, the concatenated head
+  SplitMat W2p, Whead, L0h, L1p;
+  float *b2p = nullptr, *bhead = nullptr, *bl0p = nullptr, *bl1p = nullptr;
+  float* lm_table = nullptr;  // [V][4 Hl]: LM embedding folded through weight_ih_l0
+  int vocab_tiles = 0, q_tiles = 0, n_seg = 0;
+  bool fused_decode = true;   // MILAN_FUSED_DECODE=0: the round-1 step (one kernel per op) for A/B runs
+  bool fused_ready = false, fused_lm_ready = false;
+  float2 *partials = nullptr, *lm_partials = nullptr;
+  float* lm_tgt = nullptr;
+  int* beam_counters = nullptr;
+  __nv_bfloat16 *lm_h0[2][2] = {}, *lm_h1[2][2] = {};  // [ping-pong][hi|lo]
   // ---- decoder workspace
   int Rmax = 0, Bmax = 0;
   size_t FRcap = 0;
@@ -297,6 +309,15 @@ struct MilanEngine {
                   float temperature, long long* d_beam_tokens, float* d_beam_scores, int* d_group_steps,
                   long long* d_tokens_out, float* d_scores_out, float* d_lm_scores_out, cudaStream_t st);
   int lm_score_seqs(const long long* d_seqs, int M, int length, int beam, int group_size, cudaStream_t st);
+  // fused path
+  bool use_fused_beam(int n_keys, int mi, int beam) const;
+  int fused_gemm(int which, long long M, const ConvGemmParams** out, int K, const SplitMat& W, const float* bias,
+                 const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, long long a_pitch,
+                 const __nv_bfloat16* a1_hi = nullptr, const __nv_bfloat16* a1_lo = nullptr, long long a1_pitch = 0,
+                 int K1 = 0);
+  int run_fused(const ConvGemmParams& p, int epilogue, cudaStream_t st, const int* skip);
+  int beam_steps_fused(const float* d_features, int B, int n_keys, int length, int beam, cudaStream_t st);
+  int lm_score_seqs_fused(const long long* d_seqs, int M, int length, int beam, int group_size, cudaStream_t st);
 };
 
 // ============================================================================ weight ingestion
@@ -589,6 +610,32 @@ int MilanEngine::finalize_decoder() {
     for (int i = 0; i < 4 * H; ++i) b[i] = bih->data[i] + bhh->data[i];
     if (upload_split(&W2, w, 4 * H, K, true)) return 1;
     if (upload_f32(&b2, b)) return 1;
+    // fused step: rows interleaved so that row 4u + g is gate g (i, f, g, o) of hidden unit u (conv_gemm.h, EPI_LSTM)
+    std::vector<float> wp(w.size()), bp(b.size());
+    for (int u = 0; u < H; ++u)
+      for (int g = 0; g < 4; ++g) {
+        memcpy(&wp[static_cast<size_t>(4 * u + g) * K], &w[static_cast<size_t>(g * H + u) * K], sizeof(float) * K);
+        bp[4 * u + g] = b[g * H + u];
+      }
+    if (upload_split(&W2p, wp, 4 * H, K, true)) return 1;
+    if (upload_f32(&b2p, bp)) return 1;
+  }
+  {  // Whead = [W_out; 0 ...; W_q; 0 ...; W_g]: every linear applied to h', each section starting on a 128-row tile
+    vocab_tiles = (V + 127) / 128;
+    q_tiles = (A + 127) / 128;
+    n_seg = 2 * vocab_tiles;
+    const size_t rows = static_cast<size_t>(vocab_tiles + q_tiles) * 128 + F;
+    const size_t padded = (rows + 127) / 128 * 128;
+    std::vector<float> w(rows * H, 0.f), b(padded, 0.f);
+    memcpy(&w[0], wout->data.data(), sizeof(float) * V * H);
+    memcpy(&b[0], bout->data.data(), sizeof(float) * V);
+    const size_t q0 = static_cast<size_t>(vocab_tiles) * 128, g0 = q0 + static_cast<size_t>(q_tiles) * 128;
+    memcpy(&w[q0 * H], wq->data.data(), sizeof(float) * A * H);
+    memcpy(&b[q0], bq->data.data(), sizeof(float) * A);
+    memcpy(&w[g0 * H], wg->data.data(), sizeof(float) * F * H);
+    memcpy(&b[g0], bg->data.data(), sizeof(float) * F);
+    if (upload_split(&Whead, w, static_cast<int>(rows), H, true)) return 1;
+    if (upload_f32(&bhead, b)) return 1;
   }
   if (upload_split(&W3, wout->data, V, H, true)) return 1;
   if (upload_f32(&b3, bout->data, (V + 127) / 128 * 128)) return 1;
@@ -628,6 +675,28 @@ int MilanEngine::finalize_decoder() {
     if (upload_split(&Lout, lo->data, V, Hl, true)) return 1;
     if (upload_f32(&blout, lb->data, (V + 127) / 128 * 128)) return 1;
     if (upload_f32(&lm_emb, le->data)) return 1;
+    {  // fused LM: gate-interleaved rows; layer 0 sees its input through lm_table (gathered add in the epilogue)
+      std::vector<float> w0(static_cast<size_t>(4) * Hl * Hl), w1(static_cast<size_t>(4) * Hl * 2 * Hl), p0(4 * Hl),
+          p1(4 * Hl);
+      for (int u = 0; u < Hl; ++u)
+        for (int g = 0; g < 4; ++g) {
+          const size_t dst = 4 * u + g, src = static_cast<size_t>(g) * Hl + u;
+          memcpy(&w0[dst * Hl], &h0->data[src * Hl], sizeof(float) * Hl);
+          memcpy(&w1[dst * 2 * Hl], &i1->data[src * Hl], sizeof(float) * Hl);
+          memcpy(&w1[dst * 2 * Hl + Hl], &h1->data[src * Hl], sizeof(float) * Hl);
+          p0[dst] = b0[src];
+          p1[dst] = b1v[src];
+        }
+      if (upload_split(&L0h, w0, 4 * Hl, Hl, true)) return 1;
+      if (upload_split(&L1p, w1, 4 * Hl, 2 * Hl, true)) return 1;
+      if (upload_f32(&bl0p, p0)) return 1;
+      if (upload_f32(&bl1p, p1)) return 1;
+      float* d_wih = nullptr;
+      if (upload_f32(&d_wih, i0->data)) return 1;
+      if (dalloc(&lm_table, static_cast<size_t>(V) * 4 * Hl)) return 1;
+      RC(launch_lm_input_table(d_wih, lm_emb, V, El, Hl, lm_table, nullptr));
+      CU(cudaDeviceSynchronize());
+    }
   }
   return 0;
 }
@@ -700,6 +769,11 @@ int MilanEngine::alloc_workspace() {
   if (dalloc(&lm_skip, L + 1)) return 1;
   CU(cudaMemset(d_done, 0, 4 * sizeof(int)));
   CU(cudaMemset(lm_skip, 0, (L + 1) * sizeof(int)));
+  if (dalloc(&partials, R * std::max(n_seg, 1))) return 1;
+  if (dalloc(&beam_counters, 4)) return 1;
+  CU(cudaMemset(beam_counters, 0, 4 * sizeof(int)));
+  fused_ready = split && A % 128 == 0 && H % 64 == 0 && F % 2 == 0 && E % 2 == 0 &&
+                beam_select_smem_bytes(cfg.max_beam, cfg.max_beam, V) <= 227 * 1024;
   if (dalloc(&tok_cur, R)) return 1;
   if (dalloc(&tok_next, R)) return 1;
   if (dalloc(&seqs, R * (L + 1))) return 1;
@@ -721,6 +795,13 @@ int MilanEngine::alloc_workspace() {
     if (dalloc(&lm_c1n, R * Hl)) return 1;
     if (dalloc(&lm_inputs, R)) return 1;
     if (dalloc(&lm_h_f32, R * Hl * 2)) return 1;
+    for (int pp = 0; pp < 2; ++pp) {
+      if (dalloc2(lm_h0[pp], R * Hl)) return 1;
+      if (dalloc2(lm_h1[pp], R * Hl)) return 1;
+    }
+    if (dalloc(&lm_partials, R * L * std::max(n_seg, 1))) return 1;
+    if (dalloc(&lm_tgt, R * L)) return 1;
+    fused_lm_ready = split && Hl % 64 == 0;
   }
   return 0;
 }
@@ -1060,6 +1141,7 @@ int MilanEngine::decode_greedy(const float* d_features, int B, int n_keys, int l
 }
 
 int MilanEngine::lm_score_seqs(const long long* d_seqs, int M, int length, int beam, int group_size, cudaStream_t st) {
+  if (fused_decode && fused_lm_ready) return lm_score_seqs_fused(d_seqs, M, length, beam, group_size, st);
   const int V = cfg.vocab_size;
   if (lm_reset(M, st)) return 1;
   RC(launch_fill_f32(lm_scores, 0.f, M, st));
@@ -1098,7 +1180,9 @@ int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int len
   CU(cudaMemsetAsync(d_done, 0, sizeof(int), st));
   if (mi && lm_reset(R, st)) return 1;
   const int Hl = cfg.lm_hidden_size, El = cfg.lm_embedding_size;
-  for (int t = 0; t < length; ++t) {
+  const bool fused = use_fused_beam(n_keys, mi, beam);
+  if (fused && beam_steps_fused(d_features, B, n_keys, length, beam, st)) return 1;
+  for (int t = 0; t < length && !fused; ++t) {
     const int rows = t == 0 ? B : R;
     const int rpf = t == 0 ? 1 : beam;
     if (step_core(rows, rpf, n_keys, d_features, tok_cur, nullptr, 0, st, d_done)) return 1;
@@ -1169,6 +1253,168 @@ int MilanEngine::decode_beam(const float* d_features, int B, int n_keys, int len
   return 0;
 }
 
+
+// ============================================================================ fused beam step / LM rerank
+enum FusedGemmId { F_HEAD0 = 100, F_LSTM, F_HEAD, F_LM0_A, F_LM0_B, F_LM1_A, F_LM1_B, F_LMOUT_A, F_LMOUT_B };
+
+bool MilanEngine::use_fused_beam(int n_keys, int mi, int beam) const {
+  return fused_decode && fused_ready && !mi && n_keys <= kFusedMaxKeys && beam <= kMaxBeam;
+}
+
+// Cached tensor maps / tiling of a flat GEMM whose epilogue is patched per launch (A = [a | a1] when K1 > 0).
+int MilanEngine::fused_gemm(int which, long long M, const ConvGemmParams** out, int K, const SplitMat& W,
+                            const float* bias, const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, long long a_pitch,
+                            const __nv_bfloat16* a1_hi, const __nv_bfloat16* a1_lo, long long a1_pitch, int K1) {
+  auto key = std::make_pair(which, M);
+  auto it = gemm_plans.find(key);
+  if (it == gemm_plans.end()) {
+    Plan pl;
+    pl.block_n = 128;
+    int rc;
+    if (K1 > 0)
+      rc = build_gemm2_params(&pl.p, M, K, K1, W.rows, a_hi, a_lo, a_pitch, a1_hi, a1_lo, a1_pitch, W.hi, W.lo, bias, 1, 1);
+    else
+      rc = build_gemm_params(&pl.p, M, K, W.rows, a_hi, a_lo, a_pitch, W.hi, W.lo, bias, nullptr, W.rows, 1, 1);
+    if (rc) return fail("fused gemm plan %d (M=%lld K=%d+%d N=%d): %s", which, M, K, K1, W.rows, tmap_last_error());
+    it = gemm_plans.emplace(key, pl).first;
+  }
+  *out = &it->second.p;
+  return 0;
+}
+
+int MilanEngine::run_fused(const ConvGemmParams& p, int epilogue, cudaStream_t st, const int* skip) {
+  RC(launch_conv_gemm(p, 128, 1, epilogue, num_sms, st, skip));
+  return 0;
+}
+
+// The beam loop of decode_beam as four launches per step (decode_fused.h). On return tok_cur / last_lp hold the
+// final beam, hist_tok / hist_bp the history; state lives in Alstm / hnew / c / cnew like the unfused path.
+int MilanEngine::beam_steps_fused(const float* d_features, int B, int n_keys, int length, int beam, cudaStream_t st) {
+  const int V = cfg.vocab_size, H = cfg.hidden_size, E = cfg.embedding_size, F = cfg.feature_size,
+            A = cfg.attention_size;
+  const int R = B * beam;
+  const long long xp = E + F + H, qgp = A + F;
+  const __nv_bfloat16* h0_hi = Alstm[0] + E + F;
+  const __nv_bfloat16* h0_lo = Alstm[1] + E + F;
+  {  // attention query and feature gate of the initial state (the head GEMM's q / gate sections only)
+    const ConvGemmParams* base = nullptr;
+    if (fused_gemm(F_HEAD0, B, &base, H, W1, b1, h0_hi, h0_lo, xp)) return 1;
+    ConvGemmParams p = *base;
+    p.fe.vocab_tiles = 0; p.fe.q_tiles = q_tiles;
+    p.fe.q_out = qg; p.fe.q_pitch = qgp; p.fe.q_cols = A;
+    p.fe.g_out = qg + A; p.fe.g_pitch = qgp; p.fe.gate_cols = F;
+    if (run_fused(p, EPI_HEAD, st, nullptr)) return 1;
+  }
+  float* c_cur = c;
+  float* c_nxt = cnew;
+  for (int t = 0; t < length; ++t) {
+    const int rows = t == 0 ? B : R;
+    const int rpf = t == 0 ? 1 : beam;
+    const int* parents = t == 0 ? nullptr : backptr;
+    AttendFusedArgs aa{};
+    aa.q = qg; aa.q_pitch = qgp; aa.gate = qg + A; aa.gate_pitch = qgp;
+    aa.src_row = parents;
+    aa.kh = kh; aa.features = d_features; aa.w_o = w_o; aa.b_o = b_o;
+    aa.embedding = emb; aa.tokens = tok_cur;
+    if (t > 0) { aa.h_src_hi = hnew[0]; aa.h_src_lo = hnew[1]; aa.h_src_pitch = H; }
+    aa.R = rows; aa.rows_per_feature = rpf; aa.n_keys = n_keys; aa.A = A; aa.F = F; aa.E = E; aa.H = H;
+    aa.x_hi = Alstm[0]; aa.x_lo = Alstm[1]; aa.x_pitch = xp;
+    aa.attn_ws = attn_ws; aa.skip = d_done;
+    RC(launch_attend_fused(aa, st));
+    {
+      const ConvGemmParams* base = nullptr;
+      if (fused_gemm(F_LSTM, rows, &base, static_cast<int>(xp), W2p, b2p, Alstm[0], Alstm[1], xp)) return 1;
+      ConvGemmParams p = *base;
+      p.fe.hidden = H; p.fe.c_in = c_cur; p.fe.c_out = c_nxt; p.fe.src_row = parents;
+      p.fe.h_hi = hnew[0]; p.fe.h_lo = hnew[1]; p.fe.h_pitch = H;
+      if (run_fused(p, EPI_LSTM, st, d_done)) return 1;
+    }
+    {
+      const ConvGemmParams* base = nullptr;
+      if (fused_gemm(F_HEAD, rows, &base, H, Whead, bhead, hnew[0], hnew[1], H)) return 1;
+      ConvGemmParams p = *base;
+      p.fe.vocab_tiles = vocab_tiles; p.fe.q_tiles = q_tiles; p.fe.vocab = V;
+      p.fe.logits = logits; p.fe.ld_logits = ldv; p.fe.partials = partials;
+      p.fe.q_out = qg; p.fe.q_pitch = qgp; p.fe.q_cols = A;
+      p.fe.g_out = qg + A; p.fe.g_pitch = qgp; p.fe.gate_cols = F;
+      if (t == length - 1) {  // nothing reads the query / gate of the last step
+        p.n_tiles = vocab_tiles;
+        p.cout = std::min(p.cout, vocab_tiles * 128);
+      }
+      if (run_fused(p, EPI_HEAD, st, d_done)) return 1;
+    }
+    BeamSelectArgs sa{};
+    sa.logits = logits; sa.ld = ldv; sa.partials = partials; sa.n_seg = n_seg; sa.V = V;
+    sa.last_tokens = tok_cur; sa.last_lp = t == 0 ? nullptr : last_lp;
+    sa.n_neurons = B; sa.in_rows = rpf; sa.beam = beam; sa.stop_index = cfg.stop_index;
+    sa.next_tokens = tok_next; sa.next_lp = next_lp; sa.backptr = backptr;
+    sa.hist_tok = hist_tok + static_cast<size_t>(t) * R; sa.hist_bp = hist_bp + static_cast<size_t>(t) * R;
+    sa.cur_lp = last_lp; sa.done_flag = d_done; sa.counters = beam_counters;
+    RC(launch_beam_select(sa, st));
+    std::swap(tok_cur, tok_next);
+    std::swap(last_lp, next_lp);
+    std::swap(c_cur, c_nxt);
+  }
+  return 0;
+}
+
+// lm_score_seqs with three launches per position: both LSTM cells finish in their GEMM's epilogue (layer 0 reads its
+// input through lm_table), the vocabulary GEMM leaves softmax partials + the target logit, one read-out at the end.
+int MilanEngine::lm_score_seqs_fused(const long long* d_seqs, int M, int length, int beam, int group_size,
+                                     cudaStream_t st) {
+  const int V = cfg.vocab_size, Hl = cfg.lm_hidden_size;
+  const size_t plane = static_cast<size_t>(M) * Hl * sizeof(__nv_bfloat16);
+  for (int hl = 0; hl < 2; ++hl) {
+    CU(cudaMemsetAsync(lm_h0[0][hl], 0, plane, st));
+    CU(cudaMemsetAsync(lm_h1[0][hl], 0, plane, st));
+  }
+  CU(cudaMemsetAsync(lm_c0, 0, static_cast<size_t>(M) * Hl * 4, st));
+  CU(cudaMemsetAsync(lm_c1, 0, static_cast<size_t>(M) * Hl * 4, st));
+  const int groups = beam > 0 && group_size < (1 << 29) ? ((M / beam) + group_size - 1) / group_size : 1;
+  RC(launch_lm_skip(group_T, groups, length, lm_skip, st));  // positions beyond every group's T are no-ops
+  for (int t = 0; t < length; ++t) {
+    const int cur = t & 1, nxt = cur ^ 1;
+    const int* skip = lm_skip + t;
+    {
+      const ConvGemmParams* base = nullptr;
+      if (fused_gemm(cur ? F_LM0_B : F_LM0_A, M, &base, Hl, L0h, bl0p, lm_h0[cur][0], lm_h0[cur][1], Hl)) return 1;
+      ConvGemmParams p = *base;
+      p.fe.hidden = Hl; p.fe.c_in = lm_c0; p.fe.c_out = lm_c0;
+      p.fe.h_hi = lm_h0[nxt][0]; p.fe.h_lo = lm_h0[nxt][1]; p.fe.h_pitch = Hl;
+      p.fe.add_table = lm_table; p.fe.add_pitch = 4LL * Hl;
+      p.fe.add_index = t == 0 ? nullptr : d_seqs + (t - 1);  // inputs = [<start>, seq...]
+      p.fe.add_stride = length; p.fe.add_const = cfg.start_index;
+      if (run_fused(p, EPI_LSTM, st, skip)) return 1;
+    }
+    {
+      const ConvGemmParams* base = nullptr;
+      if (fused_gemm(cur ? F_LM1_B : F_LM1_A, M, &base, Hl, L1p, bl1p, lm_h0[nxt][0], lm_h0[nxt][1], Hl, lm_h1[cur][0],
+                     lm_h1[cur][1], Hl, Hl))
+        return 1;
+      ConvGemmParams p = *base;
+      p.fe.hidden = Hl; p.fe.c_in = lm_c1; p.fe.c_out = lm_c1;
+      p.fe.h_hi = lm_h1[nxt][0]; p.fe.h_lo = lm_h1[nxt][1]; p.fe.h_pitch = Hl;
+      if (run_fused(p, EPI_LSTM, st, skip)) return 1;
+    }
+    {
+      const ConvGemmParams* base = nullptr;
+      if (fused_gemm(cur ? F_LMOUT_B : F_LMOUT_A, M, &base, Hl, Lout, blout, lm_h1[nxt][0], lm_h1[nxt][1], Hl)) return 1;
+      ConvGemmParams p = *base;
+      p.fe.vocab_tiles = vocab_tiles; p.fe.q_tiles = 0; p.fe.vocab = V;
+      p.fe.partials = lm_partials + static_cast<size_t>(t) * M * n_seg;
+      p.fe.target = d_seqs + t; p.fe.target_stride = length;
+      p.fe.tgt_logit = lm_tgt + static_cast<size_t>(t) * M;
+      if (run_fused(p, EPI_HEAD, st, skip)) return 1;
+    }
+  }
+  LmFinalizeArgs fa{};
+  fa.partials = lm_partials; fa.tgt_logit = lm_tgt; fa.n_seg = n_seg; fa.M = M; fa.length = length; fa.beam = beam;
+  fa.group_size = group_size; fa.seqs = d_seqs; fa.group_T = group_T; fa.stop_index = cfg.stop_index;
+  fa.lm_scores = lm_scores;
+  RC(launch_lm_finalize(fa, st));
+  return 0;
+}
+
 // ============================================================================ C ABI
 extern "C" {
 
@@ -1214,6 +1460,7 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   eng->alexnet = alexnet;
   if (const char* env = getenv("MILAN_FUSE_DOWNSAMPLE")) eng->fuse_downsample = atoi(env) != 0;
   if (const char* env = getenv("MILAN_OVERLAP_DECODE")) eng->overlap_decode = atoi(env) != 0;
+  if (const char* env = getenv("MILAN_FUSED_DECODE")) eng->fused_decode = atoi(env) != 0;
   eng->enc_out_per_image = (spatial ? kSpatialKeys : 1) * config->feature_size;
   *out = eng;
   return 0;
