@@ -59,8 +59,6 @@ struct SmemLayout {
   static_assert(kTotalBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ float fused_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }  // as decoder.cu's
-
 // byte offset of 16-byte chunk j of row r inside a [128][128 B] tile with the TMA/UMMA 128-byte swizzle
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
 
@@ -442,8 +440,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float gi = v[c][4 * j], gf = v[c][4 * j + 1], gg = v[c][4 * j + 2], go = v[c][4 * j + 3];
-                c_new[j] = fused_sigmoid(gf) * c_prev[j] + fused_sigmoid(gi) * tanhf(gg);
-                h_new[j] = fused_sigmoid(go) * tanhf(c_new[j]);
+                c_new[j] = sigmoid_fast(gf) * c_prev[j] + sigmoid_fast(gi) * tanh_fast(gg);
+                h_new[j] = sigmoid_fast(go) * tanh_fast(c_new[j]);
               }
               float4* co = reinterpret_cast<float4*>(fe.c_out + r * fe.hidden + u0);
               co[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
@@ -538,7 +536,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             if (col0 + 32 <= limit) {  // sections are multiples of 32 columns wide
               if (!is_q) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[c][j] = fused_sigmoid(v[c][j]);
+                for (int j = 0; j < 32; ++j) v[c][j] = sigmoid_fast(v[c][j]);
               }
               float4* o4 = reinterpret_cast<float4*>(dst + col0);
 #pragma unroll

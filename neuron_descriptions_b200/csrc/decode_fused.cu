@@ -6,6 +6,7 @@
 #include "decoder.h"    // kMaxBeam
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -19,14 +20,6 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16* hi, __nv_bfloat16* l
   split_fp16x2(v0, v1, h, l);
   *reinterpret_cast<uint32_t*>(hi + off) = h;
   if (lo != nullptr) *reinterpret_cast<uint32_t*>(lo + off) = l;
-}
-
-// tanh through one ex2 and one rcp: |error| < 2e-7 absolute on the clamped range (tanh(15) rounds to 1.0f). The
-// attention scores sum 512 of these against |w_o| ~ 0.04: far below the 1e-5 the split-fp16 GEMMs leave.
-__device__ __forceinline__ float tanh_fast(float x) {
-  x = fminf(fmaxf(x, -15.0f), 15.0f);
-  const float t = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, t + 1.0f);
 }
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -66,17 +59,17 @@ __device__ __forceinline__ unsigned float_key(float x) {  // order-preserving fl
 }
 
 // ------------------------------------------------------------------ attention + gating + operand assembly
-// Cluster of kAttendCluster CTAs per feature set (neuron). Phase A: the neuron's rows are dealt round-robin to the
-// CTAs; each computes its rows' attention weights (one warp per key), writes the token embedding and copies the
-// parent's h' into the operand row. Cluster barrier. Phase B: each CTA owns a column slice of the features, reads it
-// ONCE into registers and produces that slice of `attenuated * gate` for every row of the neuron.
+// Cluster of kAttendCluster CTAs per feature set (neuron). Phase A: the neuron's rows are dealt to the (CTA, warp)
+// pairs of the cluster, one row per warp, all in flight at once: attention weights (15 warp reductions over A),
+// the token embedding, and the parent's h' copied into the operand row. Cluster barrier. Phase B: each CTA owns a
+// column slice of the features, reads it ONCE into registers and produces that slice of `attenuated * gate` for
+// every row of the neuron.
 __global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
     attend_fused_kernel(const AttendFusedArgs a) {
   if (a.skip != nullptr && *a.skip) return;  // uniform over the grid
   extern __shared__ float sm[];
-  float* q_s = sm;                         // [A]
-  float* sc_s = q_s + a.A;                 // [kFusedMaxKeys]
-  float* w_s = sc_s + kFusedMaxKeys;       // [rpf][n_keys]
+  float* q_s = sm;                                     // [8 warps][A]
+  float* w_s = q_s + 8 * a.A;                          // [rpf][n_keys]
   int* src_s = reinterpret_cast<int*>(w_s + a.rows_per_feature * a.n_keys);  // [rpf]
   const int fidx = blockIdx.x / kAttendCluster;
   const int crank = blockIdx.x % kAttendCluster;
@@ -84,44 +77,44 @@ __global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
   const long long row0 = static_cast<long long>(fidx) * rpf;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  for (int rl = crank; rl < rpf; rl += kAttendCluster) {
+  for (int rl = crank + kAttendCluster * warp; rl < rpf; rl += kAttendCluster * 8) {
     const long long r = row0 + rl;
     const long long src = a.src_row != nullptr ? a.src_row[r] : r;
+    float* q = q_s + warp * a.A;
     const float* qrow = a.q + src * a.q_pitch;
-    for (int i = threadIdx.x; i < a.A; i += blockDim.x) q_s[i] = qrow[i];
-    __syncthreads();
-    for (int k = warp; k < a.n_keys; k += 8) {
+    for (int i = lane; i < a.A; i += 32) q[i] = qrow[i];
+    __syncwarp();
+    float score = -INFINITY;  // lane k keeps the score of key k
+    for (int k = 0; k < a.n_keys; ++k) {
       const float* khr = a.kh + (static_cast<long long>(fidx) * a.n_keys + k) * a.A;
       float s = 0.f;
-      for (int i = lane; i < a.A; i += 32) s += __ldg(a.w_o + i) * tanh_fast(q_s[i] + __ldg(khr + i));
+      for (int i = lane; i < a.A; i += 32) s += __ldg(a.w_o + i) * tanh_fast(q[i] + __ldg(khr + i));
       s = warp_sum(s);
-      if (lane == 0) sc_s[k] = s + a.b_o;
+      if (lane == k) score = s + a.b_o;
     }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int k = 0; k < a.n_keys; ++k) mx = fmaxf(mx, sc_s[k]);
-    float den = 0.f;
-    for (int k = 0; k < a.n_keys; ++k) den += expf(sc_s[k] - mx);
-    if (threadIdx.x < a.n_keys) {
-      const float w = expf(sc_s[threadIdx.x] - mx) / den;
-      a.attn_ws[r * a.n_keys + threadIdx.x] = w;
-      if (a.attn_out != nullptr) a.attn_out[r * a.attn_pitch + threadIdx.x] = w;
+    const float mx = warp_max(score);
+    const float e = lane < a.n_keys ? expf(score - mx) : 0.f;
+    const float den = warp_sum(e);
+    if (lane < a.n_keys) {
+      const float w = e / den;
+      a.attn_ws[r * a.n_keys + lane] = w;
+      if (a.attn_out != nullptr) a.attn_out[r * a.attn_pitch + lane] = w;
     }
     const long long xoff = r * a.x_pitch;
     const float* erow = a.embedding + a.tokens[r] * a.E;
-    for (int e2 = threadIdx.x; e2 < a.E / 2; e2 += blockDim.x) {
+    for (int e2 = lane; e2 < a.E / 2; e2 += 32) {
       const float2 v = __ldg(reinterpret_cast<const float2*>(erow + 2 * e2));
       store_split2(a.x_hi, a.x_lo, xoff + 2 * e2, v.x, v.y);
     }
     if (a.h_src_hi != nullptr) {  // the recurrent state follows the backpointer
       const long long dst = xoff + a.E + a.F, from = src * a.h_src_pitch;
-      for (int j = threadIdx.x; j < a.H / 8; j += blockDim.x) {
+      for (int j = lane; j < a.H / 8; j += 32) {
         *reinterpret_cast<uint4*>(a.x_hi + dst + 8 * j) = *reinterpret_cast<const uint4*>(a.h_src_hi + from + 8 * j);
         if (a.x_lo != nullptr)
           *reinterpret_cast<uint4*>(a.x_lo + dst + 8 * j) = *reinterpret_cast<const uint4*>(a.h_src_lo + from + 8 * j);
       }
     }
-    __syncthreads();  // q_s / sc_s are reused by the next row
+    __syncwarp();
   }
   __threadfence();
   cluster_sync_all();
@@ -142,7 +135,9 @@ __global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
     for (int k = 0; k < kFusedMaxKeys; ++k)
       f[k] = k < a.n_keys ? __ldg(reinterpret_cast<const float2*>(fb + static_cast<long long>(k) * a.F + 2 * j2))
                           : make_float2(0.f, 0.f);
+#pragma unroll 4
     for (int rl = 0; rl < rpf; ++rl) {
+      const float2 g = *reinterpret_cast<const float2*>(a.gate + static_cast<long long>(src_s[rl]) * a.gate_pitch + 2 * j2);
       const float* w = w_s + rl * a.n_keys;
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -152,15 +147,14 @@ __global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
           s1 += w[k] * f[k].y;
         }
       }
-      const float2 g = *reinterpret_cast<const float2*>(a.gate + static_cast<long long>(src_s[rl]) * a.gate_pitch + 2 * j2);
       store_split2(a.x_hi, a.x_lo, (row0 + rl) * a.x_pitch + a.E + 2 * j2, s0 * g.x, s1 * g.y);
     }
   }
 }
 
 // ------------------------------------------------------------------ per-neuron top-k + beam merge
-// Exact top-`beam` of one row by MSB radix select (the fallback of decoder.cu's row_kernel, run here by the first 256
-// threads of the CTA on a row staged in shared memory): only reached when more than kSelectCandCap values pass the
+// Exact top-`beam` of one row by MSB radix select (the fallback of decoder.cu's row_kernel, run here by the 256
+// threads of a CTA on a row staged in shared memory): only reached when more than kSelectCandCap values pass the
 // prefilter, e.g. masses of tied logits.
 __device__ void exact_topk_256(const float* pred_s, int V, int beam, float lp, float* cv, int* cc, unsigned* hist,
                                unsigned* warp_tot, unsigned* sel, int* counts, float* cval, int* cidx, int* eqidx) {
@@ -242,12 +236,11 @@ __device__ void exact_topk_256(const float* pred_s, int V, int beam, float lp, f
 struct SelectSmem {  // fixed part of beam_select's shared memory
   float best[kMaxBeam];
   int flat[kMaxBeam];
-  float row_max[kMaxBeam];
-  float row_lse[kMaxBeam];
-  float row_lp[kMaxBeam];
-  int fallback_rows[kMaxBeam];
-  int n_fallback;
-  float tau[kSelectThreads / 32];
+  float row_max[8];  // per warp: the row it owns, when that row needs the exact fallback
+  float row_lse[8];
+  float row_lp[8];
+  int row_fallback[8];
+  float tau[8];
   unsigned hist[256];
   unsigned warp_tot[8];
   unsigned sel[2];
@@ -257,39 +250,44 @@ struct SelectSmem {  // fixed part of beam_select's shared memory
   int eqidx[kMaxBeam];
 };
 constexpr int kWarpScratchFloats = 2 * kSelectCandCap + kSelectMaxGroups;  // cand values | cand ids | group maxima
+constexpr int kSelectWarps = kSelectThreads / 32;
 
-__global__ void __launch_bounds__(kSelectThreads) beam_select_kernel(const BeamSelectArgs a) {
+// Cluster of kSelectCluster CTAs per neuron, one source row per warp (in_rows <= 64 = 8 CTAs x 8 warps): finish the
+// row's log-softmax from the GEMM's partials, prefilter, rank exactly, write the sorted top-`beam` list to global
+// memory. Cluster barrier. CTA 0 of the cluster merges the lists into the next beam and publishes the early-exit flag.
+__global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelectThreads)
+    beam_select_kernel(const BeamSelectArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SelectSmem& S = *reinterpret_cast<SelectSmem*>(smem_raw);
-  float* val_s = reinterpret_cast<float*>(smem_raw + sizeof(SelectSmem));  // [in_rows][beam] candidate scores
-  int* cls_s = reinterpret_cast<int*>(val_s + a.in_rows * a.beam);          // [in_rows][beam] candidate classes
-  float* scratch = reinterpret_cast<float*>(cls_s + a.in_rows * a.beam);    // per-warp scratch, or one staged row
-  const int nrn = blockIdx.x;
+  float* scratch = reinterpret_cast<float*>(smem_raw + sizeof(SelectSmem));  // per-warp scratch | staged row | lists
+  const int nrn = blockIdx.x / kSelectCluster;
+  const int crank = blockIdx.x % kSelectCluster;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_warps = blockDim.x >> 5;
 
   if (*a.done_flag != 0) {
     // every beam of every neuron has ended: the reference has left its loop; the beams stay as they are
-    for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
-      const int out = nrn * a.beam + j;
-      a.next_tokens[out] = a.stop_index;
-      a.next_lp[out] = a.cur_lp[out];
-      a.backptr[out] = out;
-      a.hist_tok[out] = static_cast<int>(a.stop_index);
-      a.hist_bp[out] = j;
+    if (crank == 0) {
+      for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
+        const int out = nrn * a.beam + j;
+        a.next_tokens[out] = a.stop_index;
+        a.next_lp[out] = a.cur_lp[out];
+        a.backptr[out] = out;
+        a.hist_tok[out] = static_cast<int>(a.stop_index);
+        a.hist_bp[out] = j;
+      }
     }
-    return;
+    return;  // uniform over the grid: nobody reaches the cluster barrier
   }
-  if (threadIdx.x == 0) S.n_fallback = 0;
+  if (threadIdx.x < 8) S.row_fallback[threadIdx.x] = -1;
   __syncthreads();
 
   const int row_base = nrn * a.in_rows;
   const int V4 = static_cast<int>(a.ld >> 2);
-  // ---- per row (one warp each): finish the log-softmax, prefilter, rank
-  for (int rl = warp; rl < a.in_rows; rl += n_warps) {
+  const int rl = crank + kSelectCluster * warp;  // this warp's source row
+  if (rl < a.in_rows) {
     const long long r = row_base + rl;
-    float* cv = val_s + rl * a.beam;
-    int* cc = cls_s + rl * a.beam;
+    float* cv = a.cand_val + r * a.beam;
+    int* cc = a.cand_cls + r * a.beam;
     const float lp = a.last_lp != nullptr ? a.last_lp[r] : 0.0f;
     if (a.last_tokens[r] == a.stop_index) {
       // finished beam: only <stop> at cost 0 survives (allennlp log_probs_after_end); the other per-node candidates
@@ -298,106 +296,134 @@ __global__ void __launch_bounds__(kSelectThreads) beam_select_kernel(const BeamS
         cv[j] = j == 0 ? lp + 0.0f : -INFINITY;
         cc[j] = static_cast<int>(a.stop_index);
       }
-      continue;
-    }
-    const float2* pr = a.partials + r * a.n_seg;
-    float m = -INFINITY;
-    for (int i = lane; i < a.n_seg; i += 32) m = fmaxf(m, pr[i].x);
-    const float M = warp_max(m);
-    float s = 0.f;
-    for (int i = lane; i < a.n_seg; i += 32) {
-      const float2 q = pr[i];
-      if (q.y > 0.f) s += q.y * expf(q.x - M);
-    }
-    const float lse = logf(warp_sum(s));
-    float* cand_v = scratch + warp * kWarpScratchFloats;
-    int* cand_i = reinterpret_cast<int*>(cand_v + kSelectCandCap);
-    float* gm = cand_v + 2 * kSelectCandCap;
-    // The beam-th largest of G disjoint segment maxima bounds the beam-th largest value of the row from below.
-    const int per = (a.n_seg + kSelectMaxGroups - 1) / kSelectMaxGroups;
-    const int G = (a.n_seg + per - 1) / per;
-    for (int g = lane; g < G; g += 32) {
-      float x = -INFINITY;
-      for (int i = g * per; i < min(a.n_seg, (g + 1) * per); ++i) x = fmaxf(x, pr[i].x);
-      gm[g] = x;
-    }
-    if (lane == 0) S.tau[warp] = -INFINITY;
-    __syncwarp();
-    if (G >= a.beam) {
+    } else {
+      const float2* pr = a.partials + r * a.n_seg;
+      float m = -INFINITY;
+      for (int i = lane; i < a.n_seg; i += 32) m = fmaxf(m, pr[i].x);
+      const float M = warp_max(m);
+      float s = 0.f;
+      for (int i = lane; i < a.n_seg; i += 32) {
+        const float2 q = pr[i];
+        if (q.y > 0.f) s += q.y * expf(q.x - M);
+      }
+      const float lse = logf(warp_sum(s));
+      float* cand_v = scratch + warp * kWarpScratchFloats;
+      int* cand_i = reinterpret_cast<int*>(cand_v + kSelectCandCap);
+      float* gm = cand_v + 2 * kSelectCandCap;
+      // The beam-th largest of G disjoint segment maxima bounds the beam-th largest value of the row from below.
+      const int per = (a.n_seg + kSelectMaxGroups - 1) / kSelectMaxGroups;
+      const int G = (a.n_seg + per - 1) / per;
       for (int g = lane; g < G; g += 32) {
-        const ValIdx me{gm[g], g};
-        int rank = 0;
-        for (int j = 0; j < G; ++j) rank += better(ValIdx{gm[j], j}, me) ? 1 : 0;
-        if (rank == a.beam - 1) S.tau[warp] = me.v;
+        float x = -INFINITY;
+        for (int i = g * per; i < min(a.n_seg, (g + 1) * per); ++i) x = fmaxf(x, pr[i].x);
+        gm[g] = x;
       }
-    }
-    __syncwarp();
-    // compare in the log-softmax domain: distinct logits may round to equal log-probabilities, and ties are ranked
-    // by class index
-    const float y_tau = (S.tau[warp] - M) - lse;
-    const float4* x4 = reinterpret_cast<const float4*>(a.logits + r * a.ld);
-    int count = 0;
-    for (int base = 0; base < V4; base += 32) {
-      const int idx = base + lane;
-      float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (idx < V4) q = x4[idx];
-      const float e[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int v = 4 * idx + c;
-        const float y = (e[c] - M) - lse;
-        const bool take = idx < V4 && v < a.V && y >= y_tau;
-        const unsigned ballot = __ballot_sync(0xffffffffu, take);
-        if (take) {
-          const int pos = count + __popc(ballot & ((1u << lane) - 1u));
-          if (pos < kSelectCandCap) { cand_v[pos] = y; cand_i[pos] = v; }
+      if (lane == 0) S.tau[warp] = -INFINITY;
+      __syncwarp();
+      if (G >= a.beam) {
+        for (int g = lane; g < G; g += 32) {
+          const ValIdx me{gm[g], g};
+          int rank = 0;
+          for (int j = 0; j < G; ++j) rank += better(ValIdx{gm[j], j}, me) ? 1 : 0;
+          if (rank == a.beam - 1) S.tau[warp] = me.v;
         }
-        count += __popc(ballot);
       }
-    }
-    __syncwarp();
-    if (count > kSelectCandCap) {  // warp-uniform
-      if (lane == 0) {
-        const int slot = atomicAdd(&S.n_fallback, 1);
-        S.fallback_rows[slot] = rl;
-        S.row_max[rl] = M;
-        S.row_lse[rl] = lse;
-        S.row_lp[rl] = lp;
+      __syncwarp();
+      // compare in the log-softmax domain: distinct logits may round to equal log-probabilities, and ties are
+      // ranked by class index
+      const float y_tau = (S.tau[warp] - M) - lse;
+      const float4* x4 = reinterpret_cast<const float4*>(a.logits + r * a.ld);
+      int count = 0;
+      constexpr int kBatch = 4;  // independent 16-byte loads in flight per lane
+      for (int base = 0; base < V4; base += 32 * kBatch) {
+        float4 q[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int idx = base + u * 32 + lane;
+          q[u] = idx < V4 ? x4[idx] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          const int idx = base + u * 32 + lane;
+          const float e[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+          float y[4];
+          bool take[4];
+          bool any = false;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            y[c] = (e[c] - M) - lse;
+            take[c] = idx < V4 && 4 * idx + c < a.V && y[c] >= y_tau;
+            any |= take[c];
+          }
+          if (__any_sync(0xffffffffu, any)) {  // ~1.5 % of the values pass: most groups of 128 hold none
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const unsigned ballot = __ballot_sync(0xffffffffu, take[c]);
+              if (take[c]) {
+                const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+                if (pos < kSelectCandCap) { cand_v[pos] = y[c]; cand_i[pos] = 4 * idx + c; }
+              }
+              count += __popc(ballot);
+            }
+          }
+        }
       }
-      continue;
-    }
-    for (int j = count + lane; j < a.beam; j += 32) {  // fewer candidates than beams (NaN rows): pad
-      cv[j] = -INFINITY;
-      cc[j] = 0;
-    }
-    for (int i = lane; i < count; i += 32) {
-      const ValIdx me{cand_v[i], cand_i[i]};
-      int rank = 0;
-      for (int j = 0; j < count; ++j) rank += better(ValIdx{cand_v[j], cand_i[j]}, me) ? 1 : 0;
-      if (rank < a.beam) {
-        cv[rank] = me.v + lp;
-        cc[rank] = me.i;
+      __syncwarp();
+      if (count > kSelectCandCap) {  // warp-uniform: more ties than the prefilter holds -> exact fallback below
+        if (lane == 0) {
+          S.row_fallback[warp] = rl;
+          S.row_max[warp] = M;
+          S.row_lse[warp] = lse;
+          S.row_lp[warp] = lp;
+        }
+      } else {
+        for (int j = count + lane; j < a.beam; j += 32) {  // fewer candidates than beams (NaN rows): pad
+          cv[j] = -INFINITY;
+          cc[j] = 0;
+        }
+        for (int i = lane; i < count; i += 32) {
+          const ValIdx me{cand_v[i], cand_i[i]};
+          int rank = 0;
+          for (int j = 0; j < count; ++j) rank += better(ValIdx{cand_v[j], cand_i[j]}, me) ? 1 : 0;
+          if (rank < a.beam) {
+            cv[rank] = me.v + lp;
+            cc[rank] = me.i;
+          }
+        }
       }
     }
   }
   __syncthreads();
-  // ---- rows the prefilter could not bound: exact radix select on the staged row, first 256 threads
-  const int n_fallback = S.n_fallback;
-  if (n_fallback > 0 && threadIdx.x < 256) {
+  // ---- rows the prefilter could not bound: exact radix select on the staged row, whole CTA, one row at a time
+  for (int w = 0; w < kSelectWarps; ++w) {
+    const int frl = S.row_fallback[w];
+    if (frl < 0) continue;  // uniform (shared memory)
     float* pred_s = scratch;
-    for (int f = 0; f < n_fallback; ++f) {
-      const int rl = S.fallback_rows[f];
-      const float* x = a.logits + static_cast<long long>(row_base + rl) * a.ld;
-      const float M = S.row_max[rl], lse = S.row_lse[rl];
-      for (int v = threadIdx.x; v < a.V; v += 256) pred_s[v] = (x[v] - M) - lse;
-      named_bar_sync(1, 256);
-      exact_topk_256(pred_s, a.V, a.beam, S.row_lp[rl], val_s + rl * a.beam, cls_s + rl * a.beam, S.hist, S.warp_tot,
-                     S.sel, S.counts, S.cval, S.cidx, S.eqidx);
-    }
+    const long long r = row_base + frl;
+    const float* x = a.logits + r * a.ld;
+    const float M = S.row_max[w], lse = S.row_lse[w];
+    for (int v = threadIdx.x; v < a.V; v += kSelectThreads) pred_s[v] = (x[v] - M) - lse;
+    named_bar_sync(1, 256);
+    exact_topk_256(pred_s, a.V, a.beam, S.row_lp[w], a.cand_val + r * a.beam, a.cand_cls + r * a.beam, S.hist,
+                   S.warp_tot, S.sel, S.counts, S.cval, S.cidx, S.eqidx);
+  }
+  __threadfence();
+  cluster_sync_all();
+  if (crank != 0) return;
+
+  // ---- merge (CTA 0): the next beam = the `beam` best of the in_rows sorted lists. The lists were written by other
+  // CTAs of this cluster during this kernel: coherent loads only.
+  float* val_s = scratch;
+  int* cls_s = reinterpret_cast<int*>(val_s + a.in_rows * a.beam);
+  const int n_cand = a.in_rows * a.beam;
+  const volatile float* gv = a.cand_val + static_cast<long long>(row_base) * a.beam;
+  const volatile int* gc = a.cand_cls + static_cast<long long>(row_base) * a.beam;
+  for (int i = threadIdx.x; i < n_cand; i += blockDim.x) {
+    val_s[i] = gv[i];
+    cls_s[i] = gc[i];
   }
   __syncthreads();
-  // ---- merge: the next beam = the `beam` best of the in_rows sorted lists (one warp, two list heads per lane)
-  if (warp == 0) {
+  if (warp == 0) {  // one warp, two list heads per lane
     int ptr0 = 0, ptr1 = 0;
     const int r0 = lane, r1 = lane + 32;
     for (int j = 0; j < a.beam; ++j) {
@@ -431,7 +457,7 @@ __global__ void __launch_bounds__(kSelectThreads) beam_select_kernel(const BeamS
     a.hist_bp[out] = src;
     if (cls != a.stop_index) ended = 0;
   }
-  // allennlp: `if (last_predictions == end).all(): break` — the last CTA to finish publishes it for the next step
+  // allennlp: `if (last_predictions == end).all(): break` — the last neuron to finish publishes it for the next step
   ended = __syncthreads_and(ended);
   if (threadIdx.x == 0) {
     if (ended) atomicAdd(&a.counters[0], 1);
@@ -519,7 +545,7 @@ int launch_attend_fused(const AttendFusedArgs& a, cudaStream_t stream) {
   if (a.n_keys > kFusedMaxKeys || a.rows_per_feature < 1 || a.R % a.rows_per_feature != 0 || (a.F & 1) || (a.E & 1) ||
       (a.H & 7))
     return static_cast<int>(cudaErrorInvalidValue);
-  const size_t smem = (a.A + kFusedMaxKeys + static_cast<size_t>(a.rows_per_feature) * a.n_keys) * sizeof(float) +
+  const size_t smem = (8 * static_cast<size_t>(a.A) + static_cast<size_t>(a.rows_per_feature) * a.n_keys) * sizeof(float) +
                       a.rows_per_feature * sizeof(int);
   if (smem > 48 * 1024) return static_cast<int>(cudaErrorInvalidValue);
   const int sets = a.R / a.rows_per_feature;
@@ -529,20 +555,21 @@ int launch_attend_fused(const AttendFusedArgs& a, cudaStream_t stream) {
 
 size_t beam_select_smem_bytes(int in_rows, int beam, int V) {
   const size_t lists = static_cast<size_t>(in_rows) * beam * (sizeof(float) + sizeof(int));
-  const size_t warps = static_cast<size_t>(kSelectThreads / 32) * kWarpScratchFloats * sizeof(float);
+  const size_t warps = static_cast<size_t>(kSelectWarps) * kWarpScratchFloats * sizeof(float);
   const size_t staged = static_cast<size_t>(V) * sizeof(float);
-  return sizeof(SelectSmem) + lists + (warps > staged ? warps : staged) + 16;
+  return sizeof(SelectSmem) + std::max(lists, std::max(warps, staged)) + 16;
 }
 
 int launch_beam_select(const BeamSelectArgs& a, cudaStream_t stream) {
   if (a.n_neurons == 0) return 0;
-  if (a.beam < 1 || a.beam > kMaxBeam || a.in_rows < 1 || a.in_rows > 64 || a.n_seg < 1 || (a.ld & 3))
+  if (a.beam < 1 || a.beam > kMaxBeam || a.in_rows < 1 || a.in_rows > kSelectCluster * kSelectWarps || a.n_seg < 1 ||
+      (a.ld & 3))
     return static_cast<int>(cudaErrorInvalidValue);
   const size_t smem = beam_select_smem_bytes(a.in_rows, a.beam, a.V);
   if (smem > 227 * 1024) return static_cast<int>(cudaErrorInvalidValue);
   static size_t configured[64] = {};
   if (int rc = ensure_dynamic_smem(beam_select_kernel, smem, configured)) return rc;
-  beam_select_kernel<<<a.n_neurons, kSelectThreads, smem, stream>>>(a);
+  beam_select_kernel<<<a.n_neurons * kSelectCluster, kSelectThreads, smem, stream>>>(a);
   return last_err();
 }
 

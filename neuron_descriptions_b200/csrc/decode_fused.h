@@ -9,8 +9,9 @@
 //   2. LSTM GEMM         conv_gemm_kernel<EPI_LSTM>: gates -> c', h' in the epilogue
 //   3. head GEMM         conv_gemm_kernel<EPI_HEAD>: [W_out; W_q; W_g] h' -> logits + softmax partials, next step's
 //                        attention query and feature gate
-//   4. beam_select       one CTA per neuron: log-softmax normaliser from the partials, exact per-row top-`beam`,
-//                        the `beam x beam` merge, backpointers / history, and allennlp's all-ended early-exit flag
+//   4. beam_select       cluster of 8 CTAs per neuron, one source row per warp: log-softmax normaliser from the
+//                        partials, exact per-row top-`beam`; then CTA 0 of the cluster does the `beam x beam` merge,
+//                        backpointers / history, and allennlp's all-ended early-exit flag
 // Everything that depends on the parent row only (query, gate, h', c') is produced in the parent's row order and read
 // through the backpointers by the consumer, so no state tensor is ever reordered in memory.
 #pragma once
@@ -22,7 +23,8 @@ namespace milan {
 
 constexpr int kAttendCluster = 8;      // CTAs per neuron in attend_fused
 constexpr int kFusedMaxKeys = 16;      // keys held in registers (k = 15 exemplars)
-constexpr int kSelectThreads = 1024;
+constexpr int kSelectThreads = 256;
+constexpr int kSelectCluster = 8;      // CTAs per neuron in beam_select: one source row per warp
 constexpr int kSelectCandCap = 256;    // candidates per row kept by the fast path
 constexpr int kSelectMaxGroups = 128;  // segment maxima ranked per row
 
@@ -62,6 +64,8 @@ struct BeamSelectArgs {
   const float* last_lp;          // [rows] or nullptr (first step: 0)
   int n_neurons, in_rows, beam;  // rows = n_neurons * in_rows; in_rows = 1 (first step) or beam
   long long stop_index;
+  float* cand_val;           // workspace [rows][beam]: each row's sorted top-`beam` (score incl. last_lp)
+  int* cand_cls;             // workspace [rows][beam]
   long long* next_tokens;    // [n_neurons * beam]
   float* next_lp;            // [n_neurons * beam]
   int* backptr;              // [n_neurons * beam] global parent row

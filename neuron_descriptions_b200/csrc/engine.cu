@@ -1347,6 +1347,7 @@ int MilanEngine::beam_steps_fused(const float* d_features, int B, int n_keys, in
     sa.logits = logits; sa.ld = ldv; sa.partials = partials; sa.n_seg = n_seg; sa.V = V;
     sa.last_tokens = tok_cur; sa.last_lp = t == 0 ? nullptr : last_lp;
     sa.n_neurons = B; sa.in_rows = rpf; sa.beam = beam; sa.stop_index = cfg.stop_index;
+    sa.cand_val = cand_val; sa.cand_cls = cand_cls;
     sa.next_tokens = tok_next; sa.next_lp = next_lp; sa.backptr = backptr;
     sa.hist_tok = hist_tok + static_cast<size_t>(t) * R; sa.hist_bp = hist_bp + static_cast<size_t>(t) * R;
     sa.cur_lp = last_lp; sa.done_flag = d_done; sa.counters = beam_counters;

@@ -283,6 +283,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 __device__ __forceinline__ float bf16_lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 
+// tanh / sigmoid through one ex2.approx and one rcp.approx: |error| < 2e-7 ABSOLUTE (tanh(15) rounds to 1.0f, so the
+// clamp loses nothing), i.e. far below what the split-fp16 GEMMs around them leave (~1e-5). Used where the
+// transcendental sits on a critical path: the epilogues of the LSTM / head GEMMs and the attention scores.
+__device__ __forceinline__ float tanh_fast(float x) {
+  x = fminf(fmaxf(x, -15.0f), 15.0f);
+  const float t = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, t + 1.0f);
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  x = fminf(fmaxf(x, -30.0f), 30.0f);
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= v to ~16 mantissa bits.
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
