@@ -36,6 +36,7 @@ CONV_FLOP_PER_NEURON = 2.0 * 7.79935744e9 * K_EXEMPLARS  # SURVEY.md section 8(d
 # every conv input / residual / output tensor touched once as (hi, lo) bf16 planes; the four
 # downsample tensors are never materialised (conv3 + downsample run as one GEMM): 157.5 - 11.6 + 2.1 GB per 64 neurons
 CONV_BYTES_PER_NEURON = 148.0e9 / 64
+SURVEY_BYTES_PER_NEURON = 0.97e9  # every conv tensor once as ONE bf16 NHWC plane
 WORKLOAD = ('alexnet/imagenet 1k neurons, k=15, beam=50 + PMI rerank (synthetic exemplars of that shape, '
             'random-init MILAN resnet101 encoder + attention-LSTM decoder + LSTM LM, V=5004)')
 
@@ -105,21 +106,39 @@ class ClockSampler:
                 'samples': len(clocks)}
 
 
-def cpu_oracle_neurons_per_s(n_neurons, threads):
-    """The reference's CPU path (oracle port, torch fp32) on a bounded sample of the same workload."""
+def shared_config():
+    """The `config` both arms print (identical dicts: the driver compares them); arm-specific detail goes in `arm`."""
+    return {'workload': WORKLOAD, 'k': K_EXEMPLARS, 'beam': BEAM, 'length': LENGTH, 'strategy': 'rerank',
+            'temperature': 0.2, 'decode_batch': GROUP}
+
+
+def bench_exemplars(nb, rank, index):
+    """Synthetic uint8 exemplars of bench batch `index` of `rank` — the SAME bytes for our arm, the reference arm and
+    the in-run parity check."""
+    from neuron_descriptions_b200 import synthetic
+    return synthetic.synthetic_exemplars(nb, K_EXEMPLARS, seed=1000 * rank + index)
+
+
+def cpu_oracle_describe(images_u8, masks_u8, threads):
+    """The reference's CPU path (oracle port, torch fp32) on the given exemplars: (tokens, scores, seconds)."""
     from neuron_descriptions_b200 import synthetic
     from oracle import milan_oracle as O
     torch.set_num_threads(threads)
     vocab = synthetic.synthetic_vocab(5000)
     sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=0.0)
-    images_u8, masks_u8 = synthetic.synthetic_exemplars(n_neurons, K_EXEMPLARS, seed=123)
     images, masks = O.to_float_inputs(images_u8, masks_u8)
+    tokens, scores = [], []
     start = time.perf_counter()
     with torch.no_grad():
-        O.describe(images, masks, sd, vocab, batch_size=GROUP, strategy='rerank', beam_size=BEAM, length=LENGTH,
-                   temperature=0.2)
+        for lo in range(0, len(images), GROUP):  # Decoder.predict's batches, src/milan/decoders.py:809-871
+            feats = O.encode(images[lo:lo + GROUP], masks[lo:lo + GROUP], sd)
+            out = O.decode(feats, sd, vocab, strategy='rerank', beam_size=BEAM, length=LENGTH, temperature=0.2)
+            pad = out.tokens.new_full((len(out.tokens), LENGTH), len(vocab) + 1)  # early exit: <stop> padding
+            pad[:, :out.tokens.shape[1]] = out.tokens
+            tokens.append(pad)
+            scores.append(out.scores)
     elapsed = time.perf_counter() - start
-    return n_neurons / elapsed, elapsed
+    return torch.cat(tokens), torch.cat(scores), elapsed
 
 
 def run_reference(args):
@@ -128,11 +147,14 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     sample = GROUP  # one reference batch (16 neurons, ~6 s of CPU work) per step
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_oracle_neurons_per_s(1, threads)
+    images_u8, masks_u8 = bench_exemplars(4 * GROUP, 0, 0)  # our arm's batch 0 of rank 0
+    warm_sample = 2
+    for _ in range(args.warmup):
+        cpu_oracle_describe(images_u8[:warm_sample], masks_u8[:warm_sample], threads)
     times = []
-    for _ in range(args.steps):
-        nps, elapsed = cpu_oracle_neurons_per_s(sample, threads)
+    for i in range(args.steps):
+        lo = (i % 4) * GROUP
+        _, _, elapsed = cpu_oracle_describe(images_u8[lo:lo + sample], masks_u8[lo:lo + sample], threads)
         times.append(elapsed)
     total = sum(times)
     value = sample * len(times) / total
@@ -140,7 +162,9 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'neurons_per_step': sample, 'device': 'cpu'},
+        'config': shared_config(),
+        'arm': {'neurons_per_step': sample, 'device': 'cpu', 'threads': threads,
+                'warmup_sample': f'{warm_sample} neurons per warm-up step'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': f'{sample} neurons per step x {len(times)} steps, oracle port of the reference '
                                    f'PyTorch path (torch fp32, {threads} threads), batch 16, rerank beam 50'},
@@ -192,7 +216,7 @@ def main():
     # nb*15*(3+1)*224*224 B (193 MB at nb=64) of inputs and GBs of activations: far beyond the 126 MB L2.
     host = []
     for i in range(2):
-        images_u8, masks_u8 = synthetic.synthetic_exemplars(nb, K_EXEMPLARS, seed=1000 * rank + i)
+        images_u8, masks_u8 = bench_exemplars(nb, rank, i)
         host.append((images_u8.pin_memory(), masks_u8.pin_memory()))
     dev = [(im.to(device), mk.to(device)) for im, mk in host]
     gathered_tokens = torch.empty(world, nb, LENGTH, dtype=torch.long, device=device) if world > 1 else None
@@ -236,12 +260,15 @@ def main():
             gather(tokens, scores)
         return tokens
 
+    e2e_first = {}
+
     def e2e_all(engine_):
         for n_steps in call_steps:
             n = nb * n_steps
             tokens, scores, _ = engine_.describe_host(host_all[0][:n], host_all[1][:n], strategy='rerank', length=LENGTH,
                                                       beam=BEAM, group_size=GROUP, temperature=0.2)
             gather(tokens, scores)
+            e2e_first.setdefault('out', (tokens, scores))  # kept for the in-run parity check (first call, batch 0 first)
         return tokens
 
     def barrier():
@@ -322,9 +349,9 @@ def main():
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
         'ms_per_step': ms_res / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16x3' if args.precision == 'split' else 'bf16', 'data': 'synthetic',
-        'config': {
-            'workload': WORKLOAD, 'neurons_per_step_per_gpu': nb, 'k': K_EXEMPLARS, 'beam': BEAM, 'length': LENGTH,
-            'strategy': 'rerank', 'reference_batch_size': GROUP, 'parallelism': f'neuron-sharded x{world}',
+        'config': shared_config(),
+        'arm': {
+            'neurons_per_step_per_gpu': nb, 'parallelism': f'neuron-sharded x{world}',
             'precision': ('bf16 hi/lo split operands (3 products per K step, issued as 2 or 3 tcgen05 MMAs), fp32 TMEM '
                           'accumulation (fp32-class results; parity-tested)' if args.precision == 'split'
                           else 'plain bf16 operands'),
@@ -342,7 +369,10 @@ def main():
                         f'off ({ms_prof / steps:.2f} ms per step, SM clock {clocks_prof["sm_mhz"] if clocks_prof else None} MHz)',
             'mma_flop_multiplier': 3 if args.precision == 'split' else 1,
             'tensor_pipe_frac_incl_split': achieved * (3 if args.precision == 'split' else 1) / peak,
-            'algorithmic_bytes_per_launch': CONV_BYTES_PER_NEURON * nb * steps / conv_launches,
+            # bytes THIS implementation has to move (activations as hi + lo bf16 planes = fp32 bytes, each touched once)
+            'implementation_bytes_per_launch': CONV_BYTES_PER_NEURON * nb * steps / conv_launches,
+            # 0.97 GB per neuron with single-plane bf16 NHWC activations
+            'survey_algorithmic_bytes_per_launch': SURVEY_BYTES_PER_NEURON * nb * steps / conv_launches,
             'hbm_gbs_while_convs_run': CONV_BYTES_PER_NEURON * nb * steps / (conv_ms / 1e3) / 1e9,
             'hbm_peak_gbs': peaks['hbm_gbs'],
         },
@@ -359,12 +389,26 @@ def main():
     if fast is not None:
         line['fast_mode'] = fast
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # cpu_baseline AND in-run parity check: the oracle describes the first two reference batches of the timed
+        # run's own exemplars (batch 0 of this rank); its token ids / scores are compared with what the timed
+        # `milan_describe_host` call returned for those neurons.
         threads = os.cpu_count() or 1
-        sample = 2 * GROUP  # two reference batches: ~10-15 s of CPU work
-        nps, elapsed = cpu_oracle_neurons_per_s(sample, threads)
-        line['cpu_baseline'] = {'value': nps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                'sample': f'{sample} neurons ({sample * K_EXEMPLARS} exemplars) through the oracle port of the reference '
-                                          f'PyTorch CPU path, rerank beam 50, {elapsed:.1f} s'}
+        sample = min(2 * GROUP, nb)  # ~10-15 s of CPU work
+        ref_tokens, ref_scores, elapsed = cpu_oracle_describe(host[0][0][:sample], host[0][1][:sample], threads)
+        line['cpu_baseline'] = {'value': sample / elapsed, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': f'the first {sample} neurons ({sample * K_EXEMPLARS} exemplars) of the timed run through '
+                                          f'the oracle port of the reference PyTorch CPU path, rerank beam 50, {elapsed:.1f} s'}
+        got_tokens, got_scores = (t.cpu() for t in e2e_first['out'])
+        got_tokens, got_scores = got_tokens[:sample], got_scores[:sample]
+        same = (got_tokens == ref_tokens).all(dim=1)
+        err = (got_scores - ref_scores).abs()
+        # identical ids, or (near-tie in the rerank argmax) a different sequence whose score is within tolerance
+        ok = bool((err <= 1e-3).all())
+        line['parity_check'] = {'neurons': sample, 'sequences_identical': int(same.sum()),
+                                'max_abs_score_err': float(err.max()), 'tolerance': 1e-3, 'ok': ok,
+                                'against': 'oracle port on the same exemplars, same run'}
+        if not ok:
+            raise SystemExit(f'bench.py: timed outputs differ from the oracle: {line["parity_check"]}')
     if rank == 0:
         print(json.dumps(line), flush=True)
     engine.close()

@@ -8,6 +8,7 @@
 #include "encoder.h"
 
 #include <cuda_fp16.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler injects the NVTX library
 
 #include <algorithm>
 #include <cmath>
@@ -45,6 +46,19 @@ int fail(const char* fmt, ...) {
       return fail("%s failed with code %d (%s) (%s:%d)", #expr, rc_, cudaGetErrorString((cudaError_t)rc_), \
                   __FILE__, __LINE__);                                                                   \
   } while (0)
+
+// NVTX range over a pipeline phase ("milan.encode chunk 3", ...): shows the chunk pipeline in nsys / ncu timelines
+// (tracing).
+struct NvtxRange {
+  explicit NvtxRange(const char* fmt, int a = 0, int b = 0) {
+    char name[96];
+    snprintf(name, sizeof name, fmt, a, b);
+    nvtxRangePushA(name);
+  }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Entry points run on the engine's device and leave the caller's current device as they found it (a process may hold
 // tensors on several GPUs; torch tracks its own notion of the current device).
@@ -1701,6 +1715,7 @@ int MilanEngine::describe(const uint8_t* images, const uint8_t* masks, bool host
     const int b = c & 1;
     const int done = c * chunk;
     const int nb = std::min(chunk, n_neurons - done);
+    NvtxRange range("milan.h2d chunk %d (%d neurons)", c, nb);
     if (c >= 2) CU(cudaStreamWaitEvent(copy_stream, ev_consumed[b], 0));
     CU(cudaMemcpyAsync(d_img_stage[b], images + done * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, copy_stream));
     CU(cudaMemcpyAsync(d_mask_stage[b], masks + done * msk_bytes, nb * msk_bytes, cudaMemcpyHostToDevice, copy_stream));
@@ -1720,7 +1735,10 @@ int MilanEngine::describe(const uint8_t* images, const uint8_t* masks, bool host
     }
     if (overlap && c >= 2) CU(cudaStreamWaitEvent(st, ev_feat_free[b], 0));  // decode of chunk c-2 read feats[b]
     profiling_append = profiling && c > 0;  // one conv-event list across the chunks of this call
-    if (e->encode(d_img, d_msk, nb * k, MILAN_DTYPE_U8, feats[b], st)) return 1;
+    {
+      NvtxRange range("milan.encode chunk %d (%d images)", c, nb * k);
+      if (e->encode(d_img, d_msk, nb * k, MILAN_DTYPE_U8, feats[b], st)) return 1;
+    }
     profiling_append = false;
     if (host_inputs) CU(cudaEventRecord(ev_consumed[b], st));
     if (overlap) {
@@ -1729,6 +1747,7 @@ int MilanEngine::describe(const uint8_t* images, const uint8_t* masks, bool host
     }
     long long* d_tok = d_tokens_all + static_cast<size_t>(done) * length;
     float* d_sc = d_scores_all + done;
+    NvtxRange range("milan.decode chunk %d (strategy %d)", c, strategy);
     if (strategy == 0) {
       if (decode_greedy(feats[b], nb, n_keys, length, mi, temperature, nullptr, d_tok, d_sc, nullptr, nullptr, ds)) return 1;
     } else {

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <vector>
 
 using namespace milan;
@@ -54,7 +55,7 @@ struct Case {
   int N, H, W, Cin, Cout, ks, stride, relu, residual, split, f32out;
 };
 
-static int run_case(const Case& c, int num_sms) {
+static int run_case(const Case& c, int num_sms, int reps = 5) {
   std::mt19937 rng(1234 + c.Cin * 7 + c.Cout + c.H);
   std::normal_distribution<float> nd(0.f, 1.f);
   const int Ho = c.H / c.stride, Wo = c.W / c.stride;
@@ -123,7 +124,6 @@ static int run_case(const Case& c, int num_sms) {
   if (rc) { printf("[%s] launch failed rc=%d\n", c.name, rc); return 1; }
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) { printf("[%s] kernel failed: %s\n", c.name, cudaGetErrorString(se)); return 1; }
-  const int reps = 5;
   CK(cudaEventRecord(e0));
   for (int i = 0; i < reps; ++i) launch_conv_gemm(p, block_n, c.split, c.f32out ? EPI_F32 : EPI_BF16, num_sms, 0);
   CK(cudaEventRecord(e1));
@@ -402,8 +402,29 @@ int main(int argc, char** argv) {
       {"perf_l1_c1",   240, 56,  56, 256,   64, 1, 1, 1, 0, 1, 0},
       {"perf_l3_c3f",  240, 14,  14, 256, 1024, 1, 1, 1, 1, 0, 0},
   };
-  int only = argc > 1 ? atoi(argv[1]) : -1;
   int fails = 0;
+  if (argc > 1 && std::string(argv[1]) == "l2") {
+    // L2-residency sweep: the same problems at image counts whose tensors fit the 126 MB L2 (repeated launches on
+    // one buffer set), next to the HBM-streaming sizes. Per-image time tells what a depth-first schedule could gain.
+    const int ns[] = {12, 24, 48, 96, 240};
+    const Case shapes[] = {
+        {"l3_reduce", 0, 14, 14, 1024, 256, 1, 1, 1, 0, 1, 0}, {"l3_3x3", 0, 14, 14, 256, 256, 3, 1, 1, 0, 1, 0},
+        {"l3_expand", 0, 14, 14, 256, 1024, 1, 1, 1, 1, 1, 0}, {"l2_reduce", 0, 28, 28, 512, 128, 1, 1, 1, 0, 1, 0},
+        {"l2_3x3", 0, 28, 28, 128, 128, 3, 1, 1, 0, 1, 0},     {"l2_expand", 0, 28, 28, 128, 512, 1, 1, 1, 1, 1, 0},
+        {"l1_reduce", 0, 56, 56, 256, 64, 1, 1, 1, 0, 1, 0},   {"l1_3x3", 0, 56, 56, 64, 64, 3, 1, 1, 0, 1, 0},
+        {"l1_expand", 0, 56, 56, 64, 256, 1, 1, 1, 1, 1, 0},   {"l4_reduce", 0, 7, 7, 2048, 512, 1, 1, 1, 0, 1, 0},
+        {"l4_3x3", 0, 7, 7, 512, 512, 3, 1, 1, 0, 1, 0},       {"l4_expand", 0, 7, 7, 512, 2048, 1, 1, 1, 1, 1, 0}};
+    for (const Case& sh : shapes)
+      for (int n : ns) {
+        Case c = sh;
+        c.N = n;
+        fails += run_case(c, sms, 20);
+        fflush(stdout);
+      }
+    printf("%s (%d failures)\n", fails ? "SOME FAILED" : "ALL OK", fails);
+    return fails ? 1 : 0;
+  }
+  int only = argc > 1 ? atoi(argv[1]) : -1;
   for (size_t i = 0; i < cases.size(); ++i) {
     if (only >= 0 && static_cast<int>(i) != only) continue;
     fails += run_case(cases[i], sms);

@@ -50,7 +50,7 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-from neuron_descriptions_b200.exemplars.transforms import first, identity  # noqa: E402,F401
+from neuron_descriptions_b200.exemplars.transforms import first, identities, identity  # noqa: E402,F401
 
 
 class _Tally:
@@ -148,11 +148,11 @@ def activation_masks(maps: torch.Tensor, levels: torch.Tensor, size: int) -> tor
     return masks
 
 
-def _byte_images(images: torch.Tensor, size: int, mean, std) -> torch.Tensor:
-    """`ImageVisualizer.pytorch_image` (imgviz.py:200-210): undo the dataset normalisation into bytes
-    (`renormalize.Renormalizer`, renormalize.py:118-139), nearest-neighbour resize to the output size."""
-    mul = torch.tensor(numpy.array(std) * 255.0).to(images.device, images.dtype).view(1, 3, 1, 1)
-    add = torch.tensor(numpy.array(mean) * 255.0).to(images.device, images.dtype).view(1, 3, 1, 1)
+def _byte_images(images: torch.Tensor, size: int, mul, add) -> torch.Tensor:
+    """`ImageVisualizer.pytorch_image` (imgviz.py:200-210): the renormaliser's map into bytes
+    (`Renormalizer.__call__`, renormalize.py:129-139), nearest-neighbour resize to the output size."""
+    mul = torch.tensor(mul).to(images.device, images.dtype).view(1, 3, 1, 1)
+    add = torch.tensor(add).to(images.device, images.dtype).view(1, 3, 1, 1)
     data_ = images.mul(mul).add_(add).clamp(0, 255).byte()
     return torch.nn.functional.interpolate(data_.float(), size=(size, size)).clamp(0, 255).byte()
 
@@ -174,6 +174,25 @@ def _find_normalizer(source):
     return None
 
 
+def _byte_map(normalizer):
+    """(mul, add) of `renormalize.renormalizer(source, target='byte')` (renormalize.py:53-80,118-127): data * mul +
+    add is in [0, 255]. `normalizer` is a torchvision `Normalize` / anything with the SOURCE `(mean, std)`, a NetDissect
+    `Renormalizer` that targets bytes (its own `mul` / `add` are used as they are), or None = 'pt' data in [0, 1]."""
+    if normalizer is not None and hasattr(normalizer, 'mul') and hasattr(normalizer, 'add'):
+        if not getattr(normalizer, 'tobyte', True):
+            raise ValueError('renormalizer must target bytes (renormalize.renormalizer(..., target="byte"))')
+        return (numpy.asarray(torch.as_tensor(normalizer.mul).flatten().double()),
+                numpy.asarray(torch.as_tensor(normalizer.add).flatten().double()))
+    if normalizer is None:
+        mean, std = (0., 0., 0.), (1., 1., 1.)
+    elif hasattr(normalizer, 'mean') and hasattr(normalizer, 'std'):
+        mean, std = normalizer.mean, normalizer.std
+    else:
+        mean, std = normalizer
+    byte_scale = numpy.array([1.0 / 255] * 3)
+    return numpy.array(std, dtype=numpy.float64) / byte_scale, numpy.array(mean, dtype=numpy.float64) / byte_scale
+
+
 def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
             compute_activations: Callable[..., torch.Tensor],
             dataset: data.Dataset,
@@ -192,7 +211,9 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
             **_: Any) -> ActivationStats:
     """`exemplars.compute` (`src/exemplars/compute.py:27-246`). Both callables take a dataset batch and return the
     layer's activations (B, C, H, W) on the device (the reference's first callable returns the pooled / flattened
-    pair instead; pooling and flattening happen in the tally kernels here)."""
+    pair instead; pooling and flattening happen in the tally kernels here). `compute_activations` may return an
+    `(activations, images)` pair instead (`:168-175`): the images to keep are then the model's outputs (generative
+    models), not the dataset items."""
     del image_size, num_workers, display_progress
     if units is not None and not units:
         raise ValueError('when setting `units`, must provide >= 1 unit')
@@ -239,7 +260,7 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
     needed = needed[slice(*neuron_sharding.shard_range(len(needed), rank, world))]  # this rank's share of pass 2
     owned = set(needed)
     normalizer = renormalizer if renormalizer is not None else _find_normalizer(dataset)
-    mean, std = ((normalizer.mean, normalizer.std) if normalizer is not None else ((0., 0., 0.), (1., 1., 1.)))
+    to_byte = _byte_map(normalizer)
     masks = torch.zeros(n_units, k, 1, output_size, output_size, dtype=torch.uint8)
     images = torch.zeros(n_units, k, 3, output_size, output_size, dtype=torch.uint8)
     subset = data.Subset(dataset, needed)
@@ -251,8 +272,12 @@ def compute(compute_topk_and_quantile: Callable[..., torch.Tensor],
                 wanted.setdefault(image, []).append((unit, slot))
     for batch in data.DataLoader(subset, batch_size=batch_size, shuffle=False):
         batch = batch if isinstance(batch, (list, tuple)) else [batch]
-        hiddens = select(compute_activations(*batch)).float()
-        bytes_ = _byte_images(batch[0].to(device).float(), output_size, mean, std).cpu()
+        outputs = compute_activations(*batch)
+        shown = batch[0]
+        if not torch.is_tensor(outputs):  # generative: (activations, generated images)
+            outputs, shown = outputs
+        hiddens = select(outputs).float()
+        bytes_ = _byte_images(shown.to(device).float(), output_size, *to_byte).cpu()
         pairs, maps, levels = [], [], []
         for local in range(len(hiddens)):
             image = needed[offset + local]
@@ -313,3 +338,49 @@ def discriminative(model: torch.nn.Module,
     finally:
         if handle is not None:
             handle.remove()
+
+
+def generative(model: torch.nn.Module,
+               dataset: data.Dataset,
+               layer: str,
+               device='cuda',
+               results_dir=None,
+               viz_dir=None,
+               transform_inputs: Callable[..., Any] = identities,
+               transform_hiddens: Callable[[Any], torch.Tensor] = identity,
+               transform_outputs: Callable[[Any], torch.Tensor] = identity,
+               **kwargs: Any) -> ActivationStats:
+    """`exemplars.generative` (`src/exemplars/compute.py:352-437`): exemplars of `layer` of a model for which a
+    representation goes in and an image comes out (BigGAN: `dataset` holds the z / class pairs). The unit statistics
+    are tallied over the layer's activations exactly as for a classifier; the images kept for the top-k are the
+    model's OUTPUTS (through `transform_outputs`), renormalised to bytes (`renormalizer=`; default: [0, 1] data).
+    Results go to `<results_dir>/<layer>`. The whole batch is handed to the model (`transform_inputs` default
+    `identities`), as in the reference."""
+    del viz_dir
+    model.to(device).eval()
+    if results_dir is not None:
+        results_dir = pathlib.Path(results_dir) / str(layer)
+    modules = dict(model.named_modules())
+    if str(layer) not in modules:
+        raise KeyError(f'layer "{layer}" not found in model')
+    retained = {}
+    handle = modules[str(layer)].register_forward_hook(
+        lambda _module, _inputs, output: retained.__setitem__('x', output))
+
+    def run(*args: Any):
+        inputs = transform_inputs(*[a.to(device) if torch.is_tensor(a) else a for a in args])
+        with torch.no_grad():
+            images = model(**inputs) if isinstance(inputs, dict) else model(*inputs)
+        return transform_hiddens(retained['x']), images
+
+    def tallied(*args: Any) -> torch.Tensor:
+        return run(*args)[0]
+
+    def activations_and_images(*args: Any):
+        hiddens, images = run(*args)
+        return hiddens, transform_outputs(images)
+
+    try:
+        return compute(tallied, activations_and_images, dataset, results_dir=results_dir, device=device, **kwargs)
+    finally:
+        handle.remove()

@@ -7,6 +7,7 @@ gloo in the CPU tests — after which every rank (rank 0 matters) detokenises in
 The reference has no multi-GPU path; this is new.
 """
 import os
+import pathlib
 from typing import List, Sequence, Tuple
 
 import torch
@@ -32,6 +33,14 @@ def init_distributed() -> Tuple[int, int, int]:
         else:
             dist.init_process_group('gloo')
     return world, rank, local_rank
+
+
+def barrier(device=None):
+    """All ranks (no-op for one) + a device sync, so that a host clock read after it brackets GPU work."""
+    if dist.is_initialized():
+        dist.barrier()
+    if device is not None and torch.cuda.is_available() and str(device).startswith('cuda'):
+        torch.cuda.synchronize(device)
 
 
 def finalize_distributed():
@@ -77,10 +86,20 @@ class _SliceU8(_Slice):
         return self.base.alloc_batch_u8(n)
 
 
-def predict_sharded(decoder, dataset, world: int = 1, rank: int = 0, batch_size: int = 16, **kwargs) -> Sequence[str]:
-    """`Decoder.predict` over this rank's shard + all-gather of the token ids; returns all captions."""
+def _shard_file(resume_dir, lo: int, hi: int, n: int, length: int):
+    return pathlib.Path(resume_dir) / f'shard_{lo:07d}_{hi:07d}_of_{n}_len{length}.pt'
+
+
+def predict_sharded(decoder, dataset, world: int = 1, rank: int = 0, batch_size: int = 16, resume_dir=None,
+                    **kwargs) -> Sequence[str]:
+    """`Decoder.predict` over this rank's shard + all-gather of the token ids; returns all captions.
+
+    With `resume_dir` every rank saves its finished shard (token ids, keyed by the neuron range, so the file is valid
+    for any later world size that produces the same range) and a re-run loads it instead of describing the shard
+    again: after a rank failure only the missing shards are recomputed (failure detection).
+    """
     n = len(dataset)
-    if world == 1:
+    if world == 1 and resume_dir is None:
         return decoder.predict(dataset, batch_size=batch_size, **kwargs)
     lo, hi = shard_range(n, rank, world)
     # shards start on reference-batch boundaries only if ceil(N/G) is a multiple of batch_size; the reference's
@@ -90,14 +109,25 @@ def predict_sharded(decoder, dataset, world: int = 1, rank: int = 0, batch_size:
     stop = decoder.indexer.stop_index
     tokens = torch.full((hi - lo, length), stop, dtype=torch.long)
     kwargs.setdefault('display_progress_as', None)
-    captions_local: List[str] = list(decoder.predict(shard, batch_size=batch_size, **kwargs)) if hi > lo else []
-    # captions -> token ids would need the tokenizer; gather the ids the engine produced instead
-    if hi > lo:
+    saved = _shard_file(resume_dir, lo, hi, n, length) if resume_dir is not None else None
+    if saved is not None and saved.exists():
+        ids = torch.load(saved)
+        if tuple(ids.shape) != (hi - lo, length):
+            raise RuntimeError(f'rank {rank}: {saved} holds {tuple(ids.shape)}, expected {(hi - lo, length)}')
+        tokens = ids
+    elif hi > lo:
+        captions_local: List[str] = list(decoder.predict(shard, batch_size=batch_size, **kwargs))
+        # captions -> token ids would need the tokenizer; gather the ids the engine produced instead
         ids = getattr(decoder, 'last_predict_tokens', None)
         if ids is None or len(ids) != hi - lo or len(captions_local) != hi - lo:
             raise RuntimeError(f'rank {rank}: predict() returned {len(captions_local)} captions and '
                                f'{None if ids is None else len(ids)} token rows for a shard of {hi - lo} neurons')
         tokens[:, :ids.shape[1]] = ids.cpu()
+        if saved is not None:  # write-then-rename: a killed rank never leaves a truncated shard behind
+            saved.parent.mkdir(parents=True, exist_ok=True)
+            partial = saved.with_suffix(f'.tmp{os.getpid()}')
+            torch.save(tokens, partial)
+            os.replace(partial, saved)
     device = decoder.engine.device if torch.cuda.is_available() else torch.device('cpu')
     gathered = gather_token_rows(tokens.to(device), n, world, stop)
     return tuple(decoder.indexer.reconstruct(gathered.cpu().tolist())) if n else ()

@@ -94,11 +94,19 @@ def byte_images(images: torch.Tensor, size: int, mean: Sequence[float] = (0., 0.
 
 @torch.no_grad()
 def discriminative(features_fn, images: torch.Tensor, k: int, quantile: float, output_size: int,
-                   batch_size: int = 128, mean=(0., 0., 0.), std=(1., 1., 1.)) -> Dict[str, np.ndarray]:
-    """`exemplars.compute.discriminative` for an in-memory image tensor; `features_fn(batch) -> (B,C,H,W)`."""
+                   batch_size: int = 128, mean=(0., 0., 0.), std=(1., 1., 1.), images_fn=None,
+                   units: Optional[Sequence[int]] = None) -> Dict[str, np.ndarray]:
+    """`exemplars.compute.discriminative` for an in-memory image tensor; `features_fn(batch) -> (B,C,H,W)`.
+
+    `images_fn` (generative models, `src/exemplars/compute.py:352-437`): the kept images are `images_fn(batch)` — the
+    model's outputs — instead of the dataset items. `units` (`:159-175`): statistics of those channels only."""
     pooled, samples, hiddens = [], [], []
+    shown = images if images_fn is None else torch.cat(
+        [images_fn(images[lo:lo + batch_size]) for lo in range(0, len(images), batch_size)])
     for lo in range(0, len(images), batch_size):
         h = features_fn(images[lo:lo + batch_size])
+        if units is not None:
+            h = h[:, sorted(units)]
         p, s = pooled_and_samples(h)
         pooled.append(p.numpy())
         samples.append(s.numpy())
@@ -109,7 +117,7 @@ def discriminative(features_fn, images: torch.Tensor, k: int, quantile: float, o
     units = values.shape[0]
     masks = np.zeros((units, k, 1, output_size, output_size), np.uint8)
     top_images = np.zeros((units, k, 3, output_size, output_size), np.uint8)
-    bytes_all = byte_images(images, output_size, mean, std).numpy()
+    bytes_all = byte_images(shown, output_size, mean, std).numpy()
     for u in range(units):
         for r in range(k):
             up = upsample_bilinear_zeros(hiddens[ids[u, r], u], output_size)

@@ -162,6 +162,111 @@ def make_exemplars_golden():
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'exemplars.npz'), **out)
 
 
+class FeaturesToImage(torch.nn.Module):
+    """Toy generator head, as in the reference's own `test_generative` (`tests/exemplars/compute_test.py:265-272`):
+    the first three feature channels, squashed to [0, 1], are the "generated image"."""
+
+    def forward(self, features):
+        return torch.sigmoid(features[:, :3])
+
+
+def generative_toy_model(seed: int = 0):
+    """The toy CNN with the image head appended: representation in, image out; `conv_2` is the dissected layer."""
+    import collections
+    layers = list(exemplar_toy_model(seed).named_children())
+    layers.append(('output', FeaturesToImage()))
+    return torch.nn.Sequential(collections.OrderedDict(layers)).eval()
+
+
+GENERATIVE_CASES = (('conv_2', 24, 3, None), ('conv_1', 16, 4, (0, 2, 5)))  # (layer, output_size, k, units)
+
+
+def make_generative_golden():
+    """The reference's `exemplars.compute.generative` (`src/exemplars/compute.py:352-437`) on the toy generator: the
+    top images are the model's OUTPUTS for the top-activating representations, renormalised from [0, 1] to bytes
+    (no dataset normaliser: `renormalize.renormalizer(source=dataset)` falls back to 'pt')."""
+    import tempfile
+    from torch.utils import data
+    compute = ref_import.import_reference_exemplars()
+    model, zs = generative_toy_model(), exemplar_toy_images(seed=11)
+    out = {}
+    for layer, output_size, k, units in GENERATIVE_CASES:
+        root = pathlib.Path(tempfile.mkdtemp())
+        compute.generative(model, data.TensorDataset(zs), layer, device='cpu', results_dir=root / 'res',
+                           viz_dir=root / 'viz', display_progress=False, num_workers=0, k=k, quantile=0.99,
+                           image_size=16, output_size=output_size, batch_size=8, save_results=True, save_viz=False,
+                           units=units)
+        d = root / 'res' / layer
+        out[f'{layer}_ids'] = np.loadtxt(d / 'ids.csv', delimiter=',').astype(np.int64)
+        out[f'{layer}_activations'] = np.loadtxt(d / 'activations.csv', delimiter=',').astype(np.float32)
+        out[f'{layer}_images'] = np.load(d / 'images.npy')
+        out[f'{layer}_masks'] = np.load(d / 'masks.npy')
+        if units is not None:
+            out[f'{layer}_units'] = np.load(d / 'units.npy')
+        print(f'generative golden [{layer}]: images {out[f"{layer}_images"].shape} mean {out[f"{layer}_images"].mean():.2f} '
+              f'masks mean {out[f"{layer}_masks"].mean():.4f} ids[0] {out[f"{layer}_ids"][0].tolist()}')
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'exemplars_generative.npz'), **out)
+
+
+class ToyViT(torch.nn.Module):
+    """A one-block ViT in the shape of DINO's `vit_small(patch_size=8)` blocks (`blocks.N.mlp.fc1` is what the
+    reference dissects, `src/exemplars/models.py:236-247`): patch embedding + CLS token, one pre-norm block whose MLP
+    hidden layer `mlp.fc1` yields (batch, 1 + patches, units)."""
+
+    def __init__(self, seed: int = 0, size: int = 16, patch: int = 4, dim: int = 12, units: int = 10):
+        super().__init__()
+        self.patch_embed = torch.nn.Conv2d(3, dim, patch, stride=patch)
+        self.cls_token = torch.nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = torch.nn.Parameter(torch.zeros(1, 1 + (size // patch) ** 2, dim))
+        self.norm1 = torch.nn.LayerNorm(dim)
+        self.attn = torch.nn.MultiheadAttention(dim, 2, batch_first=True)
+        self.norm2 = torch.nn.LayerNorm(dim)
+        self.mlp = torch.nn.Sequential(collections_ordered([('fc1', torch.nn.Linear(dim, units)), ('act', torch.nn.GELU()),
+                                                            ('fc2', torch.nn.Linear(units, dim))]))
+        gen = torch.Generator().manual_seed(seed + 31)
+        with torch.no_grad():
+            for param in self.parameters():
+                param.copy_(torch.randn(param.shape, generator=gen) * 0.4)
+
+    def forward(self, images):
+        tokens = self.patch_embed(images).flatten(2).transpose(1, 2)
+        tokens = torch.cat([self.cls_token.expand(len(tokens), -1, -1), tokens], dim=1) + self.pos_embed
+        normed = self.norm1(tokens)
+        tokens = tokens + self.attn(normed, normed, normed, need_weights=False)[0]
+        return tokens + self.mlp(self.norm2(tokens))
+
+
+def collections_ordered(pairs):
+    import collections
+    return collections.OrderedDict(pairs)
+
+
+VIT_CASE = ('mlp.fc1', 16, 3)  # (layer, output_size, k)
+
+
+def make_vit_exemplars_golden():
+    """The reference's `discriminative` with `transform_hiddens=spatialize_vit_mlp` (`src/exemplars/transforms.py:
+    55-81`, the DINO ViT-S/8 configuration of `src/exemplars/models.py:236-247`) on the toy ViT."""
+    import importlib
+    import tempfile
+    from torch.utils import data
+    compute = ref_import.import_reference_exemplars()
+    ref_transforms = importlib.import_module('src.exemplars.transforms')
+    model, images = ToyViT().eval(), exemplar_toy_images(seed=23)
+    layer, output_size, k = VIT_CASE
+    root = pathlib.Path(tempfile.mkdtemp())
+    compute.discriminative(model, data.TensorDataset(images), layer=layer, device='cpu', results_dir=root / 'res',
+                           viz_dir=root / 'viz', display_progress=False, num_workers=0, k=k, quantile=0.99,
+                           image_size=16, output_size=output_size, batch_size=8, save_results=True, save_viz=False,
+                           transform_hiddens=ref_transforms.spatialize_vit_mlp)
+    d = root / 'res' / layer
+    out = {'ids': np.loadtxt(d / 'ids.csv', delimiter=',').astype(np.int64),
+           'activations': np.loadtxt(d / 'activations.csv', delimiter=',').astype(np.float32),
+           'images': np.load(d / 'images.npy'), 'masks': np.load(d / 'masks.npy')}
+    print(f'vit exemplars golden: images {out["images"].shape} masks mean {out["masks"].mean():.4f} ids[0] {out["ids"][0].tolist()}')
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'exemplars_vit.npz'), **out)
+
+
 def payload_skeleton(value):
     """A checkpoint payload with every tensor replaced by ['tensor', shape, dtype] (JSON-serialisable)."""
     if isinstance(value, dict):
@@ -234,6 +339,8 @@ def main():
     if '--only-encoders' in sys.argv:
         return make_encoder_variant_goldens(milan)
     if '--only-exemplars' in sys.argv:
+        make_generative_golden()
+        make_vit_exemplars_golden()
         return make_exemplars_golden()
     if '--only-checkpoint' in sys.argv:
         return make_checkpoint_skeleton(milan, lang)

@@ -3,7 +3,8 @@
 Counterpart of the reference's `scripts/compute_exemplars.py` (same positional arguments and the flags that make
 sense offline). The reference resolves `model/dataset` through a hub of downloadable weights and datasets
 (`src/exemplars/models.py:160-403`, `src/exemplars/datasets.py:55-102`); there is no network here, so the model is
-a torchvision architecture whose weights come from `--model-file` (a `state_dict`), and the dataset is an image
+an architecture of `exemplars/models.py` (torchvision CNNs, DINO ViT-S/8) whose weights come from `--model-file` (a
+`state_dict`), and the dataset is an image
 folder at `--dataset-path` with the reference's ImageNet / Places365 transform (`datasets.py:60-75`). The results
 (`<results-root>/<model>/<dataset>/<layer>/{images,masks}.npy, ids.csv, activations.csv`) are exactly what
 `scripts/compute_milan_descriptions.py` reads; under `torchrun` the images shard over the GPUs.
@@ -22,21 +23,14 @@ import torchvision  # noqa: E402
 from torch import cuda  # noqa: E402
 
 from neuron_descriptions_b200 import exemplars, sharding  # noqa: E402
+from neuron_descriptions_b200.exemplars import models as zoo  # noqa: E402
 
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
-# default layers, as in `src/exemplars/models.py` LAYERS
-LAYERS = {
-    'alexnet': ('features.0', 'features.3', 'features.6', 'features.8', 'features.10'),
-    'resnet18': ('conv1', 'layer1', 'layer2', 'layer3', 'layer4'),
-    'resnet50': ('conv1', 'layer1', 'layer2', 'layer3', 'layer4'),
-    'resnet101': ('conv1', 'layer1', 'layer2', 'layer3', 'layer4'),
-    'resnet152': ('conv1', 'layer1', 'layer2', 'layer3', 'layer4'),
-}
 
 
 def main(argv=None):
     parser = argparse.ArgumentParser(description='compute unit exemplars')
-    parser.add_argument('model', help='model architecture', choices=sorted(LAYERS))
+    parser.add_argument('model', help='model architecture', choices=sorted(zoo.ZOO))
     parser.add_argument('dataset', help='dataset of unseen examples for model (names the results directory)')
     group = parser.add_mutually_exclusive_group()
     group.add_argument('--layer-names', nargs='+', help='layer names to compute exemplars for')
@@ -48,7 +42,7 @@ def main(argv=None):
     parser.add_argument('--dataset-path', type=pathlib.Path, required=True, help='path to an image folder')
     parser.add_argument('--k', type=int, default=15, help='top images per unit (default: 15)')
     parser.add_argument('--quantile', type=float, default=.99, help='mask activation quantile (default: .99)')
-    parser.add_argument('--batch-size', type=int, default=128)
+    parser.add_argument('--batch-size', type=int, help='images per batch (default: the model entry\'s, else 128)')
     parser.add_argument('--device', help='manually set device (default: guessed)')
     args = parser.parse_args(argv)
 
@@ -57,10 +51,8 @@ def main(argv=None):
     if not str(device).startswith('cuda'):
         raise SystemExit('milan_b200 is CUDA-only (B200, sm_100a): no CPU fallback; got device ' + str(device))
 
-    model = getattr(torchvision.models, args.model)(weights=None)
-    if args.model_file is not None:
-        model.load_state_dict(torch.load(args.model_file, map_location='cpu'))
-    elif rank == 0:
+    model, layers, config = zoo.load(args.model, args.model_file)
+    if args.model_file is None and rank == 0:
         print('warning: no --model-file given, dissecting a randomly initialised network', file=sys.stderr)
     dataset = torchvision.datasets.ImageFolder(
         str(args.dataset_path),
@@ -68,7 +60,6 @@ def main(argv=None):
             torchvision.transforms.Resize(256), torchvision.transforms.CenterCrop(224),
             torchvision.transforms.ToTensor(), torchvision.transforms.Normalize(IMAGENET_MEAN, IMAGENET_STD)]))
 
-    layers = LAYERS[args.model]
     if args.layer_names:
         layers = args.layer_names
     elif args.layer_indices:
@@ -79,9 +70,11 @@ def main(argv=None):
         results_root = (pathlib.Path(base) if base else pathlib.Path(__file__).resolve().parents[1] / 'results') / 'exemplars'
     results_dir = results_root / args.model / args.dataset
     for layer in layers:
+        kwargs = dict(config, k=args.k, quantile=args.quantile, image_size=224, output_size=224)
+        if args.batch_size:
+            kwargs['batch_size'] = args.batch_size
         exemplars.discriminative(model, dataset, layer=layer, units=range(args.units) if args.units else None,
-                                 results_dir=results_dir, device=device, k=args.k, quantile=args.quantile,
-                                 batch_size=args.batch_size, image_size=224, output_size=224)
+                                 results_dir=results_dir, device=device, **kwargs)
         if rank == 0:
             print(f'{args.model}/{args.dataset}/{layer}: exemplars written to {results_dir / str(layer)}')
     sharding.finalize_distributed()

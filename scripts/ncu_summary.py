@@ -64,7 +64,7 @@ def full(path, out):
 
 
 
-def traffic(path, out_json, kernel='conv_gemm_kernel', limit=100):
+def traffic(path, out_json, kernel='conv_gemm', limit=100):
     """ncu csv with dram__bytes_{read,write}.sum + gpu__time_duration.sum + tensor pipe % for every conv launch of a
     step -> profiles/conv_traffic.json (mean DRAM bytes per launch, consumed by bench.py's roofline.traffic)."""
     import json
@@ -106,7 +106,7 @@ def layers(path, out):
     per = collections.OrderedDict()
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     for row in csv.DictReader(lines):
-        if 'conv_gemm_kernel' not in row['Kernel Name']:
+        if 'conv_gemm' not in row['Kernel Name']:  # conv_gemm_kernel<...> and conv_gemm_pair_kernel
             continue
         value = float(row['Metric Value'].replace(',', ''))
         name = row['Metric Name']

@@ -35,3 +35,7 @@ def test_reference_arm_prints_one_contract_line():
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0,
                            'd2h_bytes_per_step': 0}
     assert line['config']['workload'] and 'model' not in line['config']
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line['config'] == bench.shared_config()  # both arms print the same dict (the driver's same_config check)
+    assert line['arm']['device'] == 'cpu'

@@ -108,6 +108,13 @@ def test_compute_exemplars_cli(tmp_path):
     assert sample.unit == 1 and sample.images.shape == (3, 3, 224, 224) and sample.masks.shape == (3, 1, 224, 224)
     ids = np.loadtxt(root / 'layer4' / 'ids.csv', delimiter=',')
     assert ids.shape == (4, 3) and ids.min() >= 0 and ids.max() < 10
+    # the DINO ViT-S/8 entry (`src/exemplars/models.py:236-247`): MLP units of a block on the 28 x 28 patch grid
+    compute_exemplars.main(['dino_vits8', 'toyset', '--dataset-path', str(tmp_path / 'images'), '--results-root',
+                            str(tmp_path / 'exemplars'), '--layer-names', 'blocks.1.mlp.fc1', '--units', '5', '--k', '2',
+                            '--device', 'cuda:0'])
+    dataset = milannotations.TopImagesDataset(tmp_path / 'exemplars' / 'dino_vits8' / 'toyset', layers=['blocks.1.mlp.fc1'])
+    assert len(dataset) == 5 and dataset.k == 2 and dataset[0].masks.shape == (2, 1, 224, 224)
+    assert 0 < float(dataset[0].masks.float().mean()) < 0.2  # 0.99-quantile masks: a few percent of the pixels
 
 
 def test_smoke_without_cta_pair_convs():

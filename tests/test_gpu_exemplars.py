@@ -9,7 +9,8 @@ import torch
 from torch.utils import data
 
 from oracle import exemplars_oracle as E
-from oracle.make_golden import EXEMPLAR_CASES, exemplar_toy_images, exemplar_toy_model
+from oracle.make_golden import (EXEMPLAR_CASES, GENERATIVE_CASES, VIT_CASE, ToyViT, exemplar_toy_images,
+                                exemplar_toy_model, generative_toy_model)
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +38,54 @@ def test_discriminative_matches_reference_golden(golden_dir, tmp_path, layer, ou
     from neuron_descriptions_b200 import milannotations
     exemplar_set = milannotations.TopImagesDataset(tmp_path, layers=[layer])
     assert len(exemplar_set) == got.shape[0] and exemplar_set.k == k
+
+
+def _check_result_dir(d, g, prefix, k, mask_slack=2):
+    np.testing.assert_array_equal(np.loadtxt(d / 'ids.csv', delimiter=',').astype(np.int64), g[f'{prefix}ids'])
+    np.testing.assert_allclose(np.loadtxt(d / 'activations.csv', delimiter=','), g[f'{prefix}activations'],
+                               rtol=2e-5, atol=2e-6)
+    got_images, ref_images = np.load(d / 'images.npy'), g[f'{prefix}images']
+    assert got_images.shape == ref_images.shape and got_images.dtype == ref_images.dtype
+    got, ref = np.load(d / 'masks.npy'), g[f'{prefix}masks']
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert int((got != ref).sum()) <= mask_slack, f'{int((got != ref).sum())} mask pixels differ'
+    return got_images, ref_images
+
+
+@pytest.mark.parametrize('layer,output_size,k,units', GENERATIVE_CASES)
+def test_generative_matches_reference_golden(golden_dir, tmp_path, layer, output_size, k, units):
+    """`exemplars.generative` vs the UNMODIFIED reference's (`src/exemplars/compute.py:352-437`): representations in,
+    the generator's own output images kept for the top-k."""
+    from neuron_descriptions_b200 import exemplars
+    g = np.load(os.path.join(golden_dir, 'exemplars_generative.npz'))
+    model, zs = generative_toy_model(), exemplar_toy_images(seed=11)
+    stats = exemplars.generative(model, data.TensorDataset(zs), layer, device='cuda:0', results_dir=tmp_path, k=k,
+                                 quantile=0.99, image_size=16, output_size=output_size, batch_size=8, units=units)
+    assert stats.exact_quantile
+    d = tmp_path / layer
+    expected = ['activations.csv', 'ids.csv', 'images.npy', 'masks.npy'] + (['units.npy'] if units else [])
+    assert sorted(p.name for p in d.iterdir()) == expected
+    got_images, ref_images = _check_result_dir(d, g, f'{layer}_', k)
+    # generated on the GPU here, on the CPU in the reference: sigmoid(x) * 255 truncated to a byte may land one off
+    diff = np.abs(got_images.astype(np.int16) - ref_images.astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    if units:
+        np.testing.assert_array_equal(np.load(d / 'units.npy'), g[f'{layer}_units'])
+
+
+def test_vit_featurizer_matches_reference_golden(golden_dir, tmp_path):
+    """The DINO ViT-S/8 configuration (`src/exemplars/models.py:236-247`): MLP activations of a ViT block, made
+    spatial by `transforms.spatialize_vit_mlp`, through the same tally / mask kernels."""
+    from neuron_descriptions_b200 import exemplars
+    g = np.load(os.path.join(golden_dir, 'exemplars_vit.npz'))
+    model, images = ToyViT().eval(), exemplar_toy_images(seed=23)
+    layer, output_size, k = VIT_CASE
+    stats = exemplars.discriminative(model, data.TensorDataset(images), layer=layer, device='cuda:0',
+                                     results_dir=tmp_path, k=k, quantile=0.99, image_size=16, output_size=output_size,
+                                     batch_size=8, transform_hiddens=exemplars.transforms.spatialize_vit_mlp)
+    assert stats.exact_quantile
+    got_images, ref_images = _check_result_dir(tmp_path / layer, g, '', k, mask_slack=4)
+    np.testing.assert_array_equal(got_images, ref_images)
 
 
 def test_tally_kernels_vs_oracle():

@@ -152,3 +152,46 @@ def test_exemplars_oracle_matches_reference_golden(golden_dir, layer, output_siz
     np.testing.assert_allclose(out['activations'], g[f'{layer}_activations'], rtol=2e-5, atol=2e-6)  # csv: %.5e
     np.testing.assert_array_equal(out['images'], g[f'{layer}_images'])
     np.testing.assert_array_equal(out['masks'], g[f'{layer}_masks'])
+
+
+@pytest.mark.parametrize('layer,output_size,k,units', [('conv_2', 24, 3, None), ('conv_1', 16, 4, (0, 2, 5))])
+def test_generative_exemplars_oracle_matches_reference_golden(golden_dir, layer, output_size, k, units):
+    """`exemplars.compute.generative` (`src/exemplars/compute.py:352-437`): kept images are the generator's outputs."""
+    from oracle import exemplars_oracle as E
+    from oracle.make_golden import exemplar_toy_images, generative_toy_model
+    g = _load(golden_dir, 'exemplars_generative.npz')
+    model, zs = generative_toy_model(), exemplar_toy_images(seed=11)
+    features = (lambda x: model.conv_1(x)) if layer == 'conv_1' else (lambda x: model.conv_2(model.conv_1(x)))
+    with torch.no_grad():
+        out = E.discriminative(features, zs, k, 0.99, output_size, batch_size=8, images_fn=model, units=units)
+    np.testing.assert_array_equal(out['ids'], g[f'{layer}_ids'])
+    np.testing.assert_allclose(out['activations'], g[f'{layer}_activations'], rtol=2e-5, atol=2e-6)
+    np.testing.assert_array_equal(out['images'], g[f'{layer}_images'])
+    np.testing.assert_array_equal(out['masks'], g[f'{layer}_masks'])
+    if units is not None:
+        np.testing.assert_array_equal(g[f'{layer}_units'], sorted(units))
+
+
+def test_vit_exemplars_oracle_matches_reference_golden(golden_dir):
+    """`discriminative(transform_hiddens=spatialize_vit_mlp)`: the DINO ViT-S/8 configuration of
+    `src/exemplars/models.py:236-247` on a toy ViT (CLS token dropped, patches arranged on their grid)."""
+    from neuron_descriptions_b200.exemplars import transforms
+    from oracle import exemplars_oracle as E
+    from oracle.make_golden import VIT_CASE, ToyViT, exemplar_toy_images
+    g = _load(golden_dir, 'exemplars_vit.npz')
+    model, images = ToyViT().eval(), exemplar_toy_images(seed=23)
+    _, output_size, k = VIT_CASE
+    retained = {}
+    model.mlp.fc1.register_forward_hook(lambda _m, _i, output: retained.__setitem__('x', output))
+
+    def features(x):
+        model(x)
+        return transforms.spatialize_vit_mlp(retained['x'])
+
+    with torch.no_grad():
+        out = E.discriminative(features, images, k, 0.99, output_size, batch_size=8)
+    assert out['masks'].shape == (10, k, 1, output_size, output_size)  # 10 MLP units on the 4 x 4 patch grid
+    np.testing.assert_array_equal(out['ids'], g['ids'])
+    np.testing.assert_allclose(out['activations'], g['activations'], rtol=2e-5, atol=2e-6)
+    np.testing.assert_array_equal(out['images'], g['images'])
+    np.testing.assert_array_equal(out['masks'], g['masks'])

@@ -47,6 +47,20 @@ WORKER = textwrap.dedent('''
     captions = sharding.predict_sharded(FakeDecoder(), dataset, world=world, rank=rank)
     expected = tuple(f'W{i % 7} w{i % 5}' for i in range(n))
     assert captions == expected, (rank, captions[:5], expected[:5])
+    resume = os.environ.get('MILAN_RESUME')
+    if resume:  # per-rank shard persistence: a re-run only recomputes the shard whose file is missing
+        assert sharding.predict_sharded(FakeDecoder(), dataset, world=world, rank=rank, resume_dir=resume) == expected
+        lo, hi = sharding.shard_range(n, rank, world)
+        saved = sharding._shard_file(resume, lo, hi, n, 4)
+        assert saved.exists()
+        class Exploding(FakeDecoder):
+            def predict(self, dataset, batch_size=16, **kwargs):
+                raise AssertionError('a finished shard was described again')
+        if rank == 1:
+            saved.unlink()  # "rank 1 died before finishing"
+        decoder = FakeDecoder() if rank == 1 else Exploding()
+        assert sharding.predict_sharded(decoder, dataset, world=world, rank=rank, resume_dir=resume) == expected
+        assert saved.exists()
     sharding.finalize_distributed()
     print('rank', rank, 'ok', len(captions))
 ''')
@@ -59,7 +73,8 @@ def test_predict_sharded_two_ranks_gloo(tmp_path, n):
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
-    env = dict(os.environ, MILAN_ROOT=ROOT, MILAN_N=str(n), CUDA_VISIBLE_DEVICES='')
+    env = dict(os.environ, MILAN_ROOT=ROOT, MILAN_N=str(n), CUDA_VISIBLE_DEVICES='',
+               MILAN_RESUME=str(tmp_path / 'shards'))
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
                           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
                          env=env, capture_output=True, text=True, timeout=300)
