@@ -121,6 +121,10 @@ int milan_decode_beam(MilanEngine* engine, const float* d_features, int32_t B, i
  * leading <start>; d_out (M). */
 int milan_lm_score(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int32_t T1, float* d_out, void* stream);
 
+/* LanguageModel.forward(inputs, reduce=False) (src/milan/lms.py:85-87): d_inputs (M, T) int64; d_out (M, T, V)
+ * float32 = log-softmax of the LM's next-token distribution after each input token. */
+int milan_lm_logprobs(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int32_t T, float* d_out, void* stream);
+
 /* End-to-end `Decoder.predict` equivalent on HOST buffers (src/milan/decoders.py:809-871 with
  * strategy='rerank' | 'beam' | 'greedy'): h_images (n,k,3,224,224) uint8, h_masks (n,k,1,224,224) uint8 (pinned
  * memory recommended). Chunks of whole reference batches flow through three streams: the exemplars of chunk i+1 are

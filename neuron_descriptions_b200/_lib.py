@@ -43,6 +43,7 @@ SIGNATURES = {
                                     c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'milan_lm_score': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    'milan_lm_logprobs': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     'milan_describe_host': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'milan_describe_device': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,

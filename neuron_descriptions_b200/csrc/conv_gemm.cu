@@ -658,6 +658,14 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
   }();
   if (pair_mode && wide && block_n == 128 && epilogue == EPI_BF16 && bk == 64 && p.has_b_half && !p.stem_mode)
     return launch_conv_gemm_pair(p, num_sms, stream, skip_flag);
+  static const bool pair_res_mode = [] {
+    // the residual (1x1 expand) convs on CTA pairs with the in-place io buffers; MILAN_PAIR_RES=0 for A/B runs
+    const char* e = getenv("MILAN_PAIR_RES");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  if (pair_mode && pair_res_mode && res && split != 0 && block_n == 128 && epilogue == EPI_BF16 && bk == 64 &&
+      p.has_b_half && !p.stem_mode && p.cout % 128 == 0)
+    return launch_conv_gemm_pair(p, num_sms, stream, skip_flag);
 #define MILAN_DISPATCH(BN, SP, EP, RS, BKV, WD)                                                          \
   if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV && wide == WD)     \
     return launch_impl<BN, SP, EP, RS, BKV, WD>(p, num_sms, stream, skip_flag);

@@ -114,7 +114,8 @@ struct alignas(64) ConvGemmParams {
 // beam-search loop to drop the GEMMs of steps after every beam has ended, without a host round trip.
 int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilogue, int num_sms,
                      cudaStream_t stream, const int* skip_flag = nullptr);
-// CTA-pair variant (conv_gemm_pair.cu): BLOCK_N = 128, split mode, bf16 output, no residual, 64-wide k-blocks.
+// CTA-pair variant (conv_gemm_pair.cu): BLOCK_N = 128, split mode, bf16 output, 64-wide k-blocks; p.has_res selects
+// the residual form (cout must be a multiple of 128).
 int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag);
 void count_conv_launch();
 // Kernel launches performed by this library since process start (for bench.py's gpu_launches).

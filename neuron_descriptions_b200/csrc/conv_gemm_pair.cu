@@ -1,6 +1,6 @@
-// CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM convolution kernel for the long-K bf16 convs:
-// BLOCK_N = 128, split (hi/lo) operands, bf16 hi/lo output through TMA stores, no residual, 64-wide k-blocks.
-// Default path for these convs (MILAN_PAIR=0 disables it, see launch_conv_gemm): DESIGN.md section 8c item 3.
+// CTA-pair (tcgen05 cta_group::2) variant of the implicit-GEMM convolution kernel for the bf16 convs with 128-wide
+// N tiles: split (hi/lo) operands, bf16 hi/lo output through TMA stores, 64-wide k-blocks; with (RES) or without a
+// residual. Default path for these convs (MILAN_PAIR=0 disables it, see launch_conv_gemm): DESIGN.md section 8c.
 //
 // A cluster of two CTAs (the two SMs of a TPC) computes two vertically adjacent M tiles of the same N tile as ONE
 // 256 x 128 MMA per K step: CTA r loads its own 128 pixels of A (hi + lo) and rows [64 r, 64 r + 64) of the B tile
@@ -13,9 +13,19 @@
 //   * each CTA drains its own 128 TMEM lanes; the epilogue threads of both CTAs arrive on the leader's tmem_empty.
 // Roles per CTA are those of conv_gemm.cu (warp 0 producer, warp 1 MMA - leader only -, warps 2..9 epilogue); all
 // issue loops are warp-uniform (elect.sync).
+//
+// RES (the 1x1 expand convs, `relu(bn3(conv3(t)) + x)`): shared-memory bandwidth bounds these too - per 128 x 128
+// tile the single-CTA kernel moves 896 KB through shared memory (operand fill 256, MMA operand reads 384, residual
+// in + out staging 256) against 3072 tensor-core cycles; the pair halves B (fill 64, reads 288). The epilogue works IN
+// PLACE on two 32 KB io buffers (one 64-column chunk as hi + lo planes each): the io warp (warp 10) TMA-loads the
+// residual chunk into a buffer, the epilogue threads add their accumulators to the elements they own, split the sum
+// back into the same bytes and arrive on `out_ready`; the io warp stores the buffer and, once that store has read it,
+// refills it with the residual two chunks ahead. No separate residual ring and no CTA-wide named barriers; the 64 KB
+// saved buy a third operand stage (the expands are bound by bytes in flight).
 #include "conv_gemm.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace milan {
@@ -28,12 +38,23 @@ constexpr int kBK = 64;
 constexpr int kABytes = kGemmBlockM * kBK * 2;        // 16 KB: one A plane
 constexpr int kBHalfBytes = (kBlockN / 2) * kBK * 2;  // 8 KB: this CTA's half of one B plane
 constexpr int kStageBytes = 2 * kABytes + 2 * kBHalfBytes;  // 48 KB
-constexpr int kStages = 4;
 constexpr int kTileBytes = kGemmBlockM * 64 * 2;  // 16 KB: one 64-column output plane
-constexpr int kStagingBytes = 2 * kTileBytes;
+constexpr int kStagingBytes = 2 * kTileBytes;     // hi + lo planes of one 64-column chunk
 constexpr int kTmemBufs = 4;
 constexpr uint32_t kTmemCols = kTmemBufs * kBlockN;  // 512
-constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 512 + 1024;
+// STAGES operand stages of 48 KB + IO buffers of 32 KB. Without a residual: 4 + 1 (store staging). With one the io
+// buffers are the in-place residual / result buffers: 3 + 2 when the main loop needs depth (K >= 256), 2 + 4 for the
+// short-K expands of layer1 / layer2 (one or two k-blocks per tile: what has to be deep there is the residual
+// prefetch - 4 chunks = two tiles ahead - not the operand ring).
+constexpr int kMaxIo = 4;
+template <bool RES, int STAGES, int IO>
+struct PairLayout {
+  static constexpr int kStages = STAGES;
+  static constexpr int kIoBufs = IO;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kIoBufs * kStagingBytes + 512 + 1024;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(IO <= kMaxIo && (RES || IO == 1), "io buffer count");
+};
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: -> the leader
 
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
@@ -108,17 +129,42 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // the lead
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// The 64-column chunks of this CTA's tiles, in the order the epilogue produces them (the io warp of the RES variant
+// walks the same sequence twice: once loading residuals two chunks ahead, once storing results).
+struct ChunkCursor {
+  int tile, c, total_tiles, num_pairs, rank;
+  __device__ ChunkCursor(int pair_id, int total_tiles_, int num_pairs_, int rank_)
+      : tile(pair_id), c(0), total_tiles(total_tiles_), num_pairs(num_pairs_), rank(rank_) {}
+  __device__ bool valid() const { return tile < total_tiles; }
+  __device__ void next() {
+    if (++c == kBlockN / 64) { c = 0; tile += num_pairs; }
+  }
+  __device__ void coords(const ConvGemmParams& p, int* col0, int* w0, int* h0, int* n0) const {
+    const int n_tile = tile % p.n_tiles;
+    const int m_tile = 2 * (tile / p.n_tiles) + rank;
+    *col0 = n_tile * kBlockN + c * 64;
+    *w0 = (m_tile % p.tiles_w) * p.box_w;
+    *h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.box_h;
+    *n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.box_n;
+  }
+};
+
+template <bool RES, int STAGES, int IO>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p,
                                                                         const int* __restrict__ skip_flag) {
   if (skip_flag != nullptr && *skip_flag != 0) return;  // uniform over the grid
+  using L = PairLayout<RES, STAGES, IO>;
+  constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + kStages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;  // RES: io buffers [2][hi | lo]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::kIoBufs * kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + kTmemBufs;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + kTmemBufs);
+  uint64_t* res_full_bar = tmem_empty_bar + kTmemBufs;  // [IO] RES: residual chunk landed in io buffer b (this CTA)
+  uint64_t* out_ready_bar = res_full_bar + kMaxIo;      // [IO] RES: every epilogue thread finished io buffer b
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(out_ready_bar + kMaxIo);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +179,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
     tma_prefetch_desc(&p.tmap_b_half[1]);
     tma_prefetch_desc(&p.tmap_out[0]);
     tma_prefetch_desc(&p.tmap_out[1]);
+    if (RES) {
+      tma_prefetch_desc(&p.tmap_res[0]);
+      tma_prefetch_desc(&p.tmap_res[1]);
+    }
+    for (int s = 0; s < IO; ++s) {
+      mbar_init(&res_full_bar[s], 1);
+      mbar_init(&out_ready_bar[s], kEpiThreads);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);   // used in the leader only: its producer's arrive + the bytes of both CTAs
       mbar_init(&empty_bar[s], 1);  // multicast commit of the leader
@@ -234,6 +288,37 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
       }
     }
     __syncwarp();
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ io warp (RES): residual in, result out
+    if (RES) {  // all lanes, uniform
+      ChunkCursor ld(pair_id, total_tiles, num_pairs, rank), st(pair_id, total_tiles, num_pairs, rank);
+      const uint32_t tx_bytes = 2u * p.a_box_bytes;  // hi + lo planes of one 64-column box
+      auto load_residual = [&](const ChunkCursor& cur, int b) {
+        int col0, w0, h0, n0;
+        cur.coords(p, &col0, &w0, &h0, &n0);
+        uint8_t* dst = staging + b * kStagingBytes;
+        mbar_arrive_expect_tx_elect(&res_full_bar[b], tx_bytes);
+        tma_load_4d_elect(dst, &p.tmap_res[0], &res_full_bar[b], col0, w0, h0, n0);
+        tma_load_4d_elect(dst + kTileBytes, &p.tmap_res[1], &res_full_bar[b], col0, w0, h0, n0);
+      };
+      for (int b = 0; b < IO && ld.valid(); ++b, ld.next()) load_residual(ld, b);
+      for (uint32_t n = 0; st.valid(); ++n, st.next()) {
+        const int b = n % IO;
+        mbar_wait(&out_ready_bar[b], (n / IO) & 1);  // the writers fenced their stores for the async proxy
+        int col0, w0, h0, n0;
+        st.coords(p, &col0, &w0, &h0, &n0);
+        tma_store_4d_elect(&p.tmap_out[0], staging + b * kStagingBytes, col0, w0, h0, n0);
+        tma_store_4d_elect(&p.tmap_out[1], staging + b * kStagingBytes + kTileBytes, col0, w0, h0, n0);
+        tma_store_commit_elect();
+        if (ld.valid()) {  // refill this buffer as soon as the store has read it; the epilogue is on another one
+          tma_store_wait_read_elect<0>();
+          load_residual(ld, b);
+          ld.next();
+        }
+      }
+      tma_store_wait_all_elect<0>();
+    }
+    __syncwarp();
   } else if (warp >= 2 && warp < 10) {
     // ------------------------------------------------------------ epilogue (both CTAs, own M tile)
     const int quarter = warp & 3;
@@ -241,6 +326,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
     const int row = quarter * 32 + lane;
     const bool leader = warp == 2;
     uint32_t cc = 0;
+    uint32_t io_count = 0;  // RES: chunks this CTA has produced (io buffer = count % IO, barrier phase = count / IO)
     for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = 2 * (tile / p.n_tiles) + rank;
@@ -269,6 +355,51 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
         }
         tcgen05_fence_before();
         mbar_arrive_leader(&tmem_empty_bar[as]);  // the leader's MMA warp waits for both CTAs' drains
+      }
+      if (RES) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c, ++io_count) {
+          const int col0 = n_tile * kBlockN + c * 64;  // cout is a multiple of 128 here (checked at launch)
+          const int b = io_count % IO;
+          uint8_t* io = staging + b * kStagingBytes;
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + group * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              v[c][4 * j + 0] += bb.x; v[c][4 * j + 1] += bb.y; v[c][4 * j + 2] += bb.z; v[c][4 * j + 3] += bb.w;
+            }
+          }
+          mbar_wait(&res_full_bar[b], (io_count / IO) & 1);
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = *reinterpret_cast<const uint4*>(io + pl * kTileBytes + swz(row, group * 4 + j));
+              v[c][8 * j + 0] += bf16_lo_to_f32(r.x); v[c][8 * j + 1] += bf16_hi_to_f32(r.x);
+              v[c][8 * j + 2] += bf16_lo_to_f32(r.y); v[c][8 * j + 3] += bf16_hi_to_f32(r.y);
+              v[c][8 * j + 4] += bf16_lo_to_f32(r.z); v[c][8 * j + 5] += bf16_hi_to_f32(r.z);
+              v[c][8 * j + 6] += bf16_lo_to_f32(r.w); v[c][8 * j + 7] += bf16_hi_to_f32(r.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[c][j] = fmaxf(v[c][j], 0.0f);
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_bf16x2(v[c][2 * j], v[c][2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // the very bytes this thread just read: in place
+            *reinterpret_cast<uint4*>(io + swz(row, group * 4 + j)) =
+                make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4*>(io + kTileBytes + swz(row, group * 4 + j)) =
+                make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the TMA store the io warp issues
+          mbar_arrive(&out_ready_bar[b]);
+        }
+        continue;
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -309,7 +440,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
         }
       }
     }
-    if (leader) tma_store_wait_all_elect<0>();
+    if (!RES && leader) tma_store_wait_all_elect<0>();
   }
 
   tcgen05_fence_before();
@@ -323,16 +454,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
 
 }  // namespace
 
-int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
-  static bool configured = false;
+namespace {
+template <bool RES, int STAGES, int IO>
+int launch_pair_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
+  using L = PairLayout<RES, STAGES, IO>;
+  static bool configured[64] = {};  // cudaFuncSetAttribute is per device
   static std::mutex mu;
   {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (dev < 0 || dev >= 64) return static_cast<int>(cudaErrorInvalidDevice);
     std::lock_guard<std::mutex> lock(mu);
-    if (!configured) {
-      cudaError_t e =
-          cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (!configured[dev]) {
+      e = cudaFuncSetAttribute(conv_gemm_pair_kernel<RES, STAGES, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes);
       if (e != cudaSuccess) return static_cast<int>(e);
-      configured = true;
+      configured[dev] = true;
     }
   }
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -343,7 +480,7 @@ int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t str
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.dynamicSmemBytes = L::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -352,9 +489,25 @@ int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t str
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel, p, skip_flag);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<RES, STAGES, IO>, p, skip_flag);
   count_conv_launch();
   return static_cast<int>(e);
+}
+}  // namespace
+
+int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
+  if (p.has_res) {
+    if (p.cout % kBlockN != 0) return static_cast<int>(cudaErrorInvalidValue);  // whole 64-column chunks only
+    static const int deep_io_max_k = [] {
+      const char* e = getenv("MILAN_PAIR_RES_DEEP_IO_MAX_K");  // experiment knob: K up to this uses 2 stages + 4 io
+      return e != nullptr ? atoi(e) : 128;
+    }();
+    int k_total = 0;
+    for (int t = 0; t < p.num_taps; ++t) k_total += (p.tap_cb[t] > 0 ? p.tap_cb[t] : p.cin / kBK) * kBK;
+    if (k_total <= deep_io_max_k) return launch_pair_impl<true, 2, 4>(p, num_sms, stream, skip_flag);
+    return launch_pair_impl<true, 3, 2>(p, num_sms, stream, skip_flag);
+  }
+  return launch_pair_impl<false, 4, 1>(p, num_sms, stream, skip_flag);
 }
 
 }  // namespace milan

@@ -1655,6 +1655,30 @@ int milan_lm_score(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int3
   return 0;
 }
 
+int milan_lm_logprobs(MilanEngine* engine, const int64_t* d_inputs, int32_t M, int32_t T, float* d_out, void* stream) {
+  CHECK_READY(engine);
+  CHECK_DECODER(engine);
+  MilanEngine* e = engine;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!e->cfg.has_lm) return fail("engine has no LM");
+  if (M < 1 || M > e->Rmax) return fail("milan_lm_logprobs: M=%d outside [1, capacity %d]", M, e->Rmax);
+  if (T < 1) return fail("milan_lm_logprobs: T=%d", T);
+  const int V = e->cfg.vocab_size;
+  if (e->lm_reset(M, st)) return 1;
+  for (int t = 0; t < T; ++t) {
+    // column t of the (M, T) inputs -> the contiguous token vector the embedding kernel reads
+    CU(cudaMemcpy2DAsync(e->tok_cur, sizeof(long long), d_inputs + t, sizeof(long long) * T, sizeof(long long), M,
+                         cudaMemcpyDeviceToDevice, st));
+    if (e->lm_step_core(M, e->tok_cur, false, st)) return 1;
+    RowArgs ra{};
+    ra.logits = e->logits_lm; ra.ld = e->ldv; ra.R = M; ra.V = V; ra.temperature = 0.0f;
+    ra.pred_out = d_out + static_cast<long long>(t) * V; ra.pred_pitch = static_cast<long long>(T) * V;
+    ra.stop_index = e->cfg.stop_index;
+    RC(launch_row_logsoftmax(ra, st));
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 // Shared body of milan_describe_host / milan_describe_device: chunks of whole reference batches through

@@ -92,6 +92,11 @@ class Engine:
         except Exception:
             pass
 
+    @property
+    def max_rows(self) -> int:
+        """Decoder / LM rows one call may carry (the engine's workspace holds max_neurons x max_beam beam rows)."""
+        return int(self.cfg.max_neurons) * int(self.cfg.max_beam)
+
     # ------------------------------------------------------------------ helpers
     def _f32(self, tensor: torch.Tensor) -> torch.Tensor:
         return tensor.to(self.device, torch.float32).contiguous()
@@ -182,6 +187,14 @@ class Engine:
         M, T1 = inputs.shape
         out = self._new(M)
         _lib.check(self.lib.milan_lm_score(self.handle, _ptr(inputs), M, T1, _ptr(out), _stream(self.device)))
+        return out
+
+    def lm_logprobs(self, inputs: torch.Tensor) -> torch.Tensor:
+        """(M, T) token ids -> (M, T, V) log-probabilities of the next token (`LanguageModel.forward(reduce=False)`)."""
+        inputs = inputs.to(self.device, torch.long).contiguous()
+        M, T = inputs.shape
+        out = self._new(M, T, self.cfg.vocab_size)
+        _lib.check(self.lib.milan_lm_logprobs(self.handle, _ptr(inputs), M, T, _ptr(out), _stream(self.device)))
         return out
 
     def describe_host(self, images_u8: torch.Tensor, masks_u8: torch.Tensor, strategy: str = 'rerank', mi=False,

@@ -174,11 +174,30 @@ class Decoder:
                               lm_hidden_size=self.lm.hidden_size if self.lm else 512, precision=self.precision,
                               max_neurons=self.max_neurons, encoder_arch=getattr(self.encoder, 'config', 'resnet101'),
                               encoder_kind=getattr(self.encoder, 'KIND', 'pyramid'), **self._capacity)
+        self._start_staging_allocation()
         if hasattr(self.encoder, 'bind'):
             self.encoder.bind(self._engine)
         if self.lm is not None:
             self.lm.bind(self._engine)
         return self
+
+    def _start_staging_allocation(self, k: int = 15, size: int = 224):
+        """Allocate `predict`'s two pinned host slabs (2 x 385 MB at the default capacity; page-locking them takes
+        ~0.5 s) on a worker thread as soon as the engine exists, so that it overlaps the rest of the start-up
+        (dataset opening, the other ranks' barrier) instead of delaying the first exemplar."""
+        engine = self._engine
+        if engine is None or engine.keys_per_image != 1 or getattr(self, '_predict_staging', None) is not None:
+            return
+        slab = 2 * max(16, (engine.cfg.max_neurons // 16) * 16)
+
+        def allocate():
+            return [(torch.empty((slab, k, 3, size, size), dtype=torch.uint8, pin_memory=True),
+                     torch.empty((slab, k, 1, size, size), dtype=torch.uint8, pin_memory=True)) for _ in range(2)]
+
+        import concurrent.futures
+        pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        self._staging_future = pool.submit(allocate)
+        pool.shutdown(wait=False)
 
     def _ensure_capacity(self, length: int, beam_size: int, n_keys: int):
         """Grow the engine workspace when a call asks for a longer decode, a wider beam or more exemplars per
@@ -482,8 +501,12 @@ class Decoder:
             raise ValueError('cannot set `mi=` decoding when reranking')
         if (mi or strategy == STRATEGY_RERANK) and self.lm is None:
             raise ValueError('cannot use MI/rerank decoding without an LM')
+        import time
+        clock = time.perf_counter
+        t0 = clock()
         self._ensure_capacity(length, beam_size if strategy != STRATEGY_GREEDY else 1, getattr(dataset, 'k', 15))
         engine = self.engine
+        t_capacity = clock()
         import concurrent.futures
         total = len(dataset)
         chunk = (engine.cfg.max_neurons // batch_size) * batch_size
@@ -491,12 +514,21 @@ class Decoder:
         bounds = [(lo, min(lo + slab, total)) for lo in range(0, total, slab)]
         # pinned staging slabs are expensive to allocate: keep them on the decoder between calls
         cached = getattr(self, '_predict_staging', None)
+        future = getattr(self, '_staging_future', None)
+        if cached is None and future is not None:
+            self._staging_future = None
+            try:
+                cached = future.result()
+            except RuntimeError:  # pinned allocation failed in the background: fall through to a fresh (smaller) one
+                cached = None
         want = min(slab, total)
         if cached is None or cached[0][0].shape[0] < want or cached[0][0].shape[1:] != dataset.alloc_batch_u8(0)[0].shape[1:]:
             cached = [dataset.alloc_batch_u8(want) for _ in range(2)]
             self._predict_staging = cached
         staging = cached
+        t_staging = clock()
         pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        wait_s, call_s = [], []
 
         def load(i):
             lo, hi = bounds[i]
@@ -512,13 +544,17 @@ class Decoder:
                 pass
         token_rows = []
         for i in iterator:
+            t_wait = clock()
             images, masks = pending.result()
             if i + 1 < len(bounds):
                 pending = pool.submit(load, i + 1)
+            t_call = clock()
             with torch.no_grad():
                 tokens, _, steps = engine.describe_host(images, masks, strategy=strategy, mi=mi, length=length,
                                                         beam=beam_size, group_size=batch_size,
                                                         temperature=temperature)
+            wait_s.append(t_call - t_wait)
+            call_s.append(clock() - t_call)
             if strategy != STRATEGY_GREEDY:
                 # the reference returns only the T <= length columns decoded before its per-batch early exit; pad
                 # the rest with <stop> (reconstruct cuts at the first <stop> anyway)
@@ -527,7 +563,14 @@ class Decoder:
             token_rows.append(tokens)
         pool.shutdown(wait=True)
         self.last_predict_tokens = torch.cat(token_rows)
-        return tuple(self.indexer.reconstruct(self.last_predict_tokens.tolist()))
+        t_described = clock()
+        captions = tuple(self.indexer.reconstruct(self.last_predict_tokens.tolist()))
+        # where the wall-clock of this call went (seconds): read by scripts/compute_milan_descriptions.py's timing dump
+        self.last_predict_timing = {
+            'neurons': total, 'slabs': len(bounds), 'ensure_capacity_s': t_capacity - t0,
+            'staging_alloc_s': t_staging - t_capacity, 'feed_wait_s': sum(wait_s), 'first_feed_wait_s': wait_s[0],
+            'describe_calls_s': sum(call_s), 'first_describe_call_s': call_s[0], 'detokenise_s': clock() - t_described}
+        return captions
 
     def fit(self, *args, **kwargs):
         raise NotImplementedError('training (src/milan/decoders.py:873-1070) is out of scope for this engine')

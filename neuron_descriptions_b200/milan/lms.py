@@ -25,12 +25,24 @@ class LanguageModel:
         return self
 
     def forward(self, inputs: torch.Tensor, reduce: bool = False, masks: Optional[torch.Tensor] = None):
-        """`LanguageModel.forward(reduce=True)`, `src/milan/lms.py:58-101` (default stop mask)."""
+        """`LanguageModel.forward`, `src/milan/lms.py:58-101`.
+
+        reduce=True with the default mask (everything after the first <stop>, off by one as in `:93-96`) is the rerank
+        hot path: one fused scoring call. reduce=False returns the (batch, length, vocab) log-probabilities; a
+        caller-supplied mask is applied to the per-token log-probabilities gathered from them, exactly as `:97-100`.
+        """
         if self._engine is None:
             raise RuntimeError('language model is not bound to a CUDA engine: call Decoder.to("cuda") first')
-        if not reduce or masks is not None:
-            raise NotImplementedError('only forward(inputs, reduce=True) with the default mask is on the hot path')
-        return self._engine.lm_score(inputs)
+        if reduce and masks is None:
+            return self._engine.lm_score(inputs)
+        inputs = inputs.to(self._engine.device, torch.long)
+        rows = max(1, self._engine.max_rows)
+        lps = torch.cat([self._engine.lm_logprobs(inputs[lo:lo + rows]) for lo in range(0, len(inputs), rows)])
+        if not reduce:
+            return lps
+        batch_size, length = inputs.shape
+        picked = lps[:, :-1].gather(2, inputs[:, 1:].unsqueeze(-1)).squeeze(-1)
+        return picked.mul(masks.to(picked.device)).sum(dim=-1)
 
     __call__ = forward
 

@@ -86,7 +86,8 @@ def main(argv=None):
             with open(timing_path, 'w') as handle:
                 json.dump({'neurons': len(dataset), 'world': world, 'load_s': t_loaded - t_start,
                            'describe_s': t_described - t_describe, 'csv_s': clock() - t_described,
-                           'total_s': clock() - t_start}, handle)
+                           'total_s': clock() - t_start,
+                           'rank0_predict': getattr(decoder, 'last_predict_timing', None)}, handle)
     sharding.finalize_distributed()
 
 

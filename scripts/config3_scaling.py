@@ -122,7 +122,7 @@ def main():
     parser.add_argument('--scale', type=float, default=1.0, help='prepare: fraction of the 3904 units (tests use less)')
     parser.add_argument('--gpus', type=int, default=1)
     parser.add_argument('--tag', default='')
-    args = parser.parse_args()
+    args = parser.parse_intermixed_args()
     if args.command == 'prepare':
         prepare(args.root, args.scale)
     elif args.command == 'run':

@@ -205,6 +205,25 @@ def test_lm_score_matches_oracle(variant):
     torch.testing.assert_close(got, ref, atol=LOGP_TOL, rtol=0)
 
 
+def test_lm_logprobs_and_custom_masks_match_oracle(variant):
+    """`LanguageModel.forward(reduce=False)` and `forward(reduce=True, masks=...)` (`src/milan/lms.py:58-101`)."""
+    from neuron_descriptions_b200.milan import lms
+    name, sd, engine, g = variant
+    gen = torch.Generator().manual_seed(5)
+    inputs = torch.randint(0, len(VOCAB), (9, 7), generator=gen)
+    inputs[:, 0] = len(VOCAB)
+    inputs[2, 3] = STOP
+    ref = O.lm_forward(inputs, sd, STOP, reduce=False)
+    lm = lms.LanguageModel(None).bind(engine)
+    got = lm(inputs).cpu()
+    assert got.shape == ref.shape == (9, 7, len(VOCAB) + 4)
+    torch.testing.assert_close(got, ref, atol=2e-4, rtol=0)
+    masks = (torch.rand(9, 6, generator=gen) > 0.3).long()
+    want = ref[:, :-1].gather(2, inputs[:, 1:].unsqueeze(-1)).squeeze(-1).mul(masks).sum(-1)
+    torch.testing.assert_close(lm(inputs, reduce=True, masks=masks).cpu(), want, atol=LOGP_TOL, rtol=0)
+    torch.testing.assert_close(lm(inputs, reduce=True).cpu(), O.lm_forward(inputs, sd, STOP), atol=LOGP_TOL, rtol=0)
+
+
 def test_beam_properties_full_size():
     """Size-independent properties at BASELINE size (16 neurons x beam 50 x 15 steps, V = 5004)."""
     sd = synthetic.synthetic_state_dict(seed=1, sharpen=12.0, stop_bias=2.0, with_encoder=False)
