@@ -663,8 +663,11 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     const char* e = getenv("MILAN_PAIR_RES");
     return e == nullptr || atoi(e) != 0;
   }();
+  // K >= 256 only (layer3 / layer4): same box, 240 images, single CTA -> pair: K = 512 82 -> 69 us, K = 256 97 -> 92 us,
+  // but K = 128 151 -> 159 us and K = 64 278 -> 293 us - the short-K expands are HBM-bound (6.3 of 6.55 TB/s) and only
+  // pay for the pair's extra synchronisation (gpurun_out/r02h_res_ab.txt -> profiles/r02h_expand_pair_ab.txt)
   if (pair_mode && pair_res_mode && res && split != 0 && block_n == 128 && epilogue == EPI_BF16 && bk == 64 &&
-      p.has_b_half && !p.stem_mode && p.cout % 128 == 0)
+      p.has_b_half && !p.stem_mode && p.cout % 128 == 0 && p.num_taps == 1 && p.cin >= 256)
     return launch_conv_gemm_pair(p, num_sms, stream, skip_flag);
 #define MILAN_DISPATCH(BN, SP, EP, RS, BKV, WD)                                                          \
   if (block_n == BN && (split != 0) == SP && epilogue == EP && res == RS && bk == BKV && wide == WD)     \

@@ -43,9 +43,10 @@ constexpr int kStagingBytes = 2 * kTileBytes;     // hi + lo planes of one 64-co
 constexpr int kTmemBufs = 4;
 constexpr uint32_t kTmemCols = kTmemBufs * kBlockN;  // 512
 // STAGES operand stages of 48 KB + IO buffers of 32 KB. Without a residual: 4 + 1 (store staging). With one the io
-// buffers are the in-place residual / result buffers: 3 + 2 when the main loop needs depth (K >= 256), 2 + 4 for the
-// short-K expands of layer1 / layer2 (one or two k-blocks per tile: what has to be deep there is the residual
-// prefetch - 4 chunks = two tiles ahead - not the operand ring).
+// buffers are the in-place residual / result buffers: 3 + 2. (Measured and rejected, same box, 240 images: 2 + 4 -
+// deeper residual prefetch, shallower operand ring - is 4-25 % slower on every expand conv, and pulling residual
+// chunks into L2 ahead of the io buffers with cp.async.bulk.prefetch.tensor is neutral at 4 chunks and 10-35 % slower
+// at 8: these convs already keep HBM as busy as their 128-byte-wide boxes allow.)
 constexpr int kMaxIo = 4;
 template <bool RES, int STAGES, int IO>
 struct PairLayout {
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
         tcgen05_fence_before();
         mbar_arrive_leader(&tmem_empty_bar[as]);  // the leader's MMA warp waits for both CTAs' drains
       }
-      if (RES) {
+      if constexpr (RES) {
 #pragma unroll
         for (int c = 0; c < 2; ++c, ++io_count) {
           const int col0 = n_tile * kBlockN + c * 64;  // cout is a multiple of 128 here (checked at launch)
@@ -399,8 +400,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
           fence_proxy_async();  // generic-proxy writes -> visible to the TMA store the io warp issues
           mbar_arrive(&out_ready_bar[b]);
         }
-        continue;
-      }
+      } else {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = n_tile * kBlockN + c * 64;
@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_pair_kernel(const __
           tma_store_4d_elect(&p.tmap_out[1], staging + kTileBytes, col0, tw * p.box_w, th * p.box_h, tn * p.box_n);
           tma_store_commit_elect();
         }
+      }
       }
     }
     if (!RES && leader) tma_store_wait_all_elect<0>();
@@ -498,13 +499,6 @@ int launch_pair_impl(const ConvGemmParams& p, int num_sms, cudaStream_t stream, 
 int launch_conv_gemm_pair(const ConvGemmParams& p, int num_sms, cudaStream_t stream, const int* skip_flag) {
   if (p.has_res) {
     if (p.cout % kBlockN != 0) return static_cast<int>(cudaErrorInvalidValue);  // whole 64-column chunks only
-    static const int deep_io_max_k = [] {
-      const char* e = getenv("MILAN_PAIR_RES_DEEP_IO_MAX_K");  // experiment knob: K up to this uses 2 stages + 4 io
-      return e != nullptr ? atoi(e) : 128;
-    }();
-    int k_total = 0;
-    for (int t = 0; t < p.num_taps; ++t) k_total += (p.tap_cb[t] > 0 ? p.tap_cb[t] : p.cin / kBK) * kBK;
-    if (k_total <= deep_io_max_k) return launch_pair_impl<true, 2, 4>(p, num_sms, stream, skip_flag);
     return launch_pair_impl<true, 3, 2>(p, num_sms, stream, skip_flag);
   }
   return launch_pair_impl<false, 4, 1>(p, num_sms, stream, skip_flag);

@@ -424,6 +424,22 @@ int main(int argc, char** argv) {
     printf("%s (%d failures)\n", fails ? "SOME FAILED" : "ALL OK", fails);
     return fails ? 1 : 0;
   }
+  if (argc > 1 && std::string(argv[1]) == "res") {  // the residual (expand) convs alone, for A/B runs of their kernel
+    const Case shapes[] = {
+        {"l1_expand", 240, 56, 56, 64, 256, 1, 1, 1, 1, 1, 0},  {"l2_expand", 240, 28, 28, 128, 512, 1, 1, 1, 1, 1, 0},
+        {"l3_expand", 240, 14, 14, 256, 1024, 1, 1, 1, 1, 1, 0}, {"l3_expand", 960, 14, 14, 256, 1024, 1, 1, 1, 1, 1, 0},
+        {"l4_expand", 240, 7, 7, 512, 2048, 1, 1, 1, 1, 1, 0},   {"l4_expand", 960, 7, 7, 512, 2048, 1, 1, 1, 1, 1, 0},
+        {"ragged_res", 1, 1, 333, 256, 384, 1, 1, 1, 1, 1, 0},   {"odd_tiles", 1, 1, 128 * 5 + 7, 64, 128, 1, 1, 1, 1, 1, 0}};
+    const int pick = argc > 2 ? atoi(argv[2]) : -1;  // `res 3`: one case only (ncu captures)
+    int index = 0;
+    for (const Case& c : shapes) {
+      if (pick >= 0 && index++ != pick) continue;
+      fails += run_case(c, sms, pick >= 0 ? 2 : 10);
+      fflush(stdout);
+    }
+    printf("%s (%d failures)\n", fails ? "SOME FAILED" : "ALL OK", fails);
+    return fails ? 1 : 0;
+  }
   int only = argc > 1 ? atoi(argv[1]) : -1;
   for (size_t i = 0; i < cases.size(); ++i) {
     if (only >= 0 && static_cast<int>(i) != only) continue;

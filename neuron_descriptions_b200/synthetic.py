@@ -10,7 +10,7 @@ this engine, which is how parity is checked.
 `images.npy` / `masks.npy` (`src/exemplars/compute.py:217-227`).
 """
 import math
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -171,7 +171,8 @@ def synthetic_exemplars(n_neurons: int,
                         k: int = 15,
                         size: int = 224,
                         seed: int = 0,
-                        zero_mask_fraction: float = 0.02) -> Tuple[torch.Tensor, torch.Tensor]:
+                        zero_mask_fraction: float = 0.02,
+                        images: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
     """uint8 images (n, k, 3, size, size) and binary uint8 masks (n, k, 1, size, size).
 
     Masks look like thresholded upsampled activation maps (a few connected blobs covering a few percent of the
@@ -179,7 +180,9 @@ def synthetic_exemplars(n_neurons: int,
     exercise `src/milan/encoders.py:311-314`.
     """
     gen = torch.Generator().manual_seed(seed + 77)
-    images = torch.randint(0, 256, (n_neurons, k, 3, size, size), generator=gen, dtype=torch.uint8)
+    # (images=False: masks only, drawn from a generator of their own — callers that make the image bytes themselves)
+    images = (torch.randint(0, 256, (n_neurons, k, 3, size, size), generator=gen, dtype=torch.uint8) if images
+              else None)
     low = torch.rand(n_neurons * k, 1, 14, 14, generator=gen)
     up = torch.nn.functional.interpolate(low, size=(size, size), mode='bilinear', align_corners=False)
     masks = (up > 0.8).to(torch.uint8).view(n_neurons, k, 1, size, size)

@@ -61,7 +61,9 @@ def main(argv=None):
     results_dir.mkdir(exist_ok=True, parents=True)
 
     decoder = milan_loaders.pretrained(args.milan, path=args.milan_path)
+    t_checkpoint = clock()
     decoder.to(device)
+    t_engine = clock()
     dataset = milannotations.load(key, path=data_root)
 
     t_loaded = clock()
@@ -85,6 +87,8 @@ def main(argv=None):
         if timing_path:
             with open(timing_path, 'w') as handle:
                 json.dump({'neurons': len(dataset), 'world': world, 'load_s': t_loaded - t_start,
+                           'load_checkpoint_s': t_checkpoint - t_start, 'build_engine_s': t_engine - t_checkpoint,
+                           'open_dataset_s': t_loaded - t_engine,
                            'describe_s': t_described - t_describe, 'csv_s': clock() - t_described,
                            'total_s': clock() - t_start,
                            'rank0_predict': getattr(decoder, 'last_predict_timing', None)}, handle)

@@ -17,6 +17,7 @@ describe, all-gather, detokenise, CSV), and the describe phase alone (rank 0's `
 all-gather every rank joins, so it is the max over ranks), as neurons/s and neurons/hour.
 """
 import argparse
+import concurrent.futures
 import json
 import os
 import pathlib
@@ -53,11 +54,17 @@ def prepare(root: pathlib.Path, scale: float):
         folder.mkdir(parents=True, exist_ok=True)
         images = np.lib.format.open_memmap(folder / 'images.npy', mode='w+', dtype=np.uint8, shape=(units, K, 3, 224, 224))
         masks = np.lib.format.open_memmap(folder / 'masks.npy', mode='w+', dtype=np.uint8, shape=(units, K, 1, 224, 224))
-        for lo in range(0, units, 64):
+        def fill(lo, li=li, units=units, images=images, masks=masks):
             n = min(64, units - lo)
-            im, mk = synthetic.synthetic_exemplars(n, K, seed=5000 + 100 * li + lo // 64)
-            images[lo:lo + n] = im.numpy()
+            # masks as `synthetic.synthetic_exemplars` makes them (thresholded upsampled blobs, a few all-zero); image
+            # bytes straight from numpy's generator, one generator per chunk so that the chunks can be made in parallel
+            _, mk = synthetic.synthetic_exemplars(n, K, seed=5000 + 100 * li + lo // 64, images=False)
+            rng = np.random.default_rng(7000 + 100 * li + lo // 64)
+            images[lo:lo + n] = np.frombuffer(rng.bytes(n * K * 3 * 224 * 224), dtype=np.uint8).reshape(n, K, 3, 224, 224)
             masks[lo:lo + n] = mk.numpy()
+
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+            list(pool.map(fill, range(0, units, 64)))
         images.flush()
         masks.flush()
         del images, masks
