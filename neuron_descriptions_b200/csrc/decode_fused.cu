@@ -53,9 +53,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// k-th largest (k >= 1) of the keys a warp holds KMAX per lane (unused slots = 0, below every float_key): the answer is
+// built bit by bit from the top, one warp-wide count per bit - 32 x (KMAX compares + one redux), no shared memory.
+template <int KMAX>
+__device__ __forceinline__ unsigned warp_kth_largest(const unsigned (&key)[KMAX], int k) {
+  unsigned ans = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned trial = ans | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) c += key[j] >= trial ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, c) >= k) ans = trial;
+  }
+  return ans;
+}
 __device__ __forceinline__ unsigned float_key(float x) {  // order-preserving float -> uint
   const unsigned u = __float_as_uint(x);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_key(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 // ------------------------------------------------------------------ attention + gating + operand assembly
@@ -64,10 +82,7 @@ __device__ __forceinline__ unsigned float_key(float x) {  // order-preserving fl
 // the token embedding, and the parent's h' copied into the operand row. Cluster barrier. Phase B: each CTA owns a
 // column slice of the features, reads it ONCE into registers and produces that slice of `attenuated * gate` for
 // every row of the neuron.
-__global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
-    attend_fused_kernel(const AttendFusedArgs a) {
-  if (a.skip != nullptr && *a.skip) return;  // uniform over the grid
-  extern __shared__ float sm[];
+__device__ __forceinline__ void attend_phase(const AttendFusedArgs& a, float* sm) {
   float* q_s = sm;                                     // [8 warps][A]
   float* w_s = q_s + 8 * a.A;                          // [rpf][n_keys]
   int* src_s = reinterpret_cast<int*>(w_s + a.rows_per_feature * a.n_keys);  // [rpf]
@@ -150,6 +165,13 @@ __global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
       store_split2(a.x_hi, a.x_lo, (row0 + rl) * a.x_pitch + a.E + 2 * j2, s0 * g.x, s1 * g.y);
     }
   }
+}
+
+__global__ void __cluster_dims__(kAttendCluster, 1, 1) __launch_bounds__(256)
+    attend_fused_kernel(const AttendFusedArgs a) {
+  if (a.skip != nullptr && *a.skip) return;  // uniform over the grid
+  extern __shared__ float sm[];
+  attend_phase(a, sm);
 }
 
 // ------------------------------------------------------------------ per-neuron top-k + beam merge
@@ -240,7 +262,6 @@ struct SelectSmem {  // fixed part of beam_select's shared memory
   float row_lse[8];
   float row_lp[8];
   int row_fallback[8];
-  float tau[8];
   unsigned hist[256];
   unsigned warp_tot[8];
   unsigned sel[2];
@@ -255,29 +276,28 @@ constexpr int kSelectWarps = kSelectThreads / 32;
 // Cluster of kSelectCluster CTAs per neuron, one source row per warp (in_rows <= 64 = 8 CTAs x 8 warps): finish the
 // row's log-softmax from the GEMM's partials, prefilter, rank exactly, write the sorted top-`beam` list to global
 // memory. Cluster barrier. CTA 0 of the cluster merges the lists into the next beam and publishes the early-exit flag.
-__global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelectThreads)
-    beam_select_kernel(const BeamSelectArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+// Every beam of every neuron has ended: the reference has left its loop; the beams stay as they are.
+__device__ __forceinline__ void select_done_phase(const BeamSelectArgs& a) {
+  const int nrn = blockIdx.x / kSelectCluster;
+  if (blockIdx.x % kSelectCluster == 0) {
+    for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
+      const int out = nrn * a.beam + j;
+      a.next_tokens[out] = a.stop_index;
+      a.next_lp[out] = a.cur_lp[out];
+      a.backptr[out] = out;
+      a.hist_tok[out] = static_cast<int>(a.stop_index);
+      a.hist_bp[out] = j;
+    }
+  }
+}
+
+// Rows phase (all CTAs of the cluster): each warp ranks its source row and writes the sorted top-`beam` list.
+__device__ __forceinline__ void select_rows_phase(const BeamSelectArgs& a, uint8_t* smem_raw) {
   SelectSmem& S = *reinterpret_cast<SelectSmem*>(smem_raw);
   float* scratch = reinterpret_cast<float*>(smem_raw + sizeof(SelectSmem));  // per-warp scratch | staged row | lists
   const int nrn = blockIdx.x / kSelectCluster;
   const int crank = blockIdx.x % kSelectCluster;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  if (*a.done_flag != 0) {
-    // every beam of every neuron has ended: the reference has left its loop; the beams stay as they are
-    if (crank == 0) {
-      for (int j = threadIdx.x; j < a.beam; j += blockDim.x) {
-        const int out = nrn * a.beam + j;
-        a.next_tokens[out] = a.stop_index;
-        a.next_lp[out] = a.cur_lp[out];
-        a.backptr[out] = out;
-        a.hist_tok[out] = static_cast<int>(a.stop_index);
-        a.hist_bp[out] = j;
-      }
-    }
-    return;  // uniform over the grid: nobody reaches the cluster barrier
-  }
   if (threadIdx.x < 8) S.row_fallback[threadIdx.x] = -1;
   __syncthreads();
 
@@ -318,20 +338,18 @@ __global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelect
         for (int i = g * per; i < min(a.n_seg, (g + 1) * per); ++i) x = fmaxf(x, pr[i].x);
         gm[g] = x;
       }
-      if (lane == 0) S.tau[warp] = -INFINITY;
       __syncwarp();
-      if (G >= a.beam) {
-        for (int g = lane; g < G; g += 32) {
-          const ValIdx me{gm[g], g};
-          int rank = 0;
-          for (int j = 0; j < G; ++j) rank += better(ValIdx{gm[j], j}, me) ? 1 : 0;
-          if (rank == a.beam - 1) S.tau[warp] = me.v;
-        }
+      float tau = -INFINITY;
+      if (G >= a.beam) {  // (G <= kSelectMaxGroups = 4 x 32)
+        unsigned gkey[kSelectMaxGroups / 32];
+#pragma unroll
+        for (int j = 0; j < kSelectMaxGroups / 32; ++j) gkey[j] = lane + 32 * j < G ? float_key(gm[lane + 32 * j]) : 0u;
+        const unsigned kth = warp_kth_largest(gkey, a.beam);
+        tau = float_from_key(kth);
       }
-      __syncwarp();
       // compare in the log-softmax domain: distinct logits may round to equal log-probabilities, and ties are
       // ranked by class index
-      const float y_tau = (S.tau[warp] - M) - lse;
+      const float y_tau = (tau - M) - lse;
       const float4* x4 = reinterpret_cast<const float4*>(a.logits + r * a.ld);
       int count = 0;
       constexpr int kBatch = 4;  // independent 16-byte loads in flight per lane
@@ -381,10 +399,42 @@ __global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelect
           cv[j] = -INFINITY;
           cc[j] = 0;
         }
-        for (int i = lane; i < count; i += 32) {
+        // The prefilter passes 1.5-5x `beam` candidates. Rank only those at or above the beam-th largest VALUE
+        // (found by a bitwise search over the keys, held 8 per lane), not every candidate against every other.
+        int n_rank = count;
+        if (count > a.beam) {
+          constexpr int kPerLane = kSelectCandCap / 32;
+          float v[kPerLane];
+          int ix[kPerLane];
+          unsigned key[kPerLane];
+#pragma unroll
+          for (int j = 0; j < kPerLane; ++j) {
+            const int i = lane + 32 * j;
+            v[j] = i < count ? cand_v[i] : 0.f;
+            ix[j] = i < count ? cand_i[i] : 0;
+            key[j] = i < count ? float_key(v[j]) : 0u;
+          }
+          const unsigned kth = warp_kth_largest(key, a.beam);
+          __syncwarp();  // every lane holds its candidates in registers: the lists can be compacted in place
+          int kept = 0;
+#pragma unroll
+          for (int j = 0; j < kPerLane; ++j) {
+            const bool keep = lane + 32 * j < count && key[j] >= kth;
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+              const int pos = kept + __popc(ballot & ((1u << lane) - 1u));
+              cand_v[pos] = v[j];
+              cand_i[pos] = ix[j];
+            }
+            kept += __popc(ballot);
+          }
+          n_rank = kept;  // >= beam; more only when values tie at the threshold (ranked by class index below)
+          __syncwarp();
+        }
+        for (int i = lane; i < n_rank; i += 32) {
           const ValIdx me{cand_v[i], cand_i[i]};
           int rank = 0;
-          for (int j = 0; j < count; ++j) rank += better(ValIdx{cand_v[j], cand_i[j]}, me) ? 1 : 0;
+          for (int j = 0; j < n_rank; ++j) rank += better(ValIdx{cand_v[j], cand_i[j]}, me) ? 1 : 0;
           if (rank < a.beam) {
             cv[rank] = me.v + lp;
             cc[rank] = me.i;
@@ -407,12 +457,16 @@ __global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelect
     exact_topk_256(pred_s, a.V, a.beam, S.row_lp[w], a.cand_val + r * a.beam, a.cand_cls + r * a.beam, S.hist,
                    S.warp_tot, S.sel, S.counts, S.cval, S.cidx, S.eqidx);
   }
-  __threadfence();
-  cluster_sync_all();
-  if (crank != 0) return;
+}
 
-  // ---- merge (CTA 0): the next beam = the `beam` best of the in_rows sorted lists. The lists were written by other
-  // CTAs of this cluster during this kernel: coherent loads only.
+// Merge phase (CTA 0 of the cluster, after a cluster barrier): the next beam = the `beam` best of the in_rows sorted
+// lists. The lists were written by other CTAs of this cluster during this kernel: coherent loads only.
+__device__ __forceinline__ void select_merge_phase(const BeamSelectArgs& a, uint8_t* smem_raw) {
+  SelectSmem& S = *reinterpret_cast<SelectSmem*>(smem_raw);
+  float* scratch = reinterpret_cast<float*>(smem_raw + sizeof(SelectSmem));
+  const int nrn = blockIdx.x / kSelectCluster;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row_base = nrn * a.in_rows;
   float* val_s = scratch;
   int* cls_s = reinterpret_cast<int*>(val_s + a.in_rows * a.beam);
   const int n_cand = a.in_rows * a.beam;
@@ -471,6 +525,48 @@ __global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelect
       a.counters[1] = 0;
     }
   }
+}
+
+__global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelectThreads)
+    beam_select_kernel(const BeamSelectArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (*a.done_flag != 0) {
+    select_done_phase(a);
+    return;  // uniform over the grid: nobody reaches the cluster barrier
+  }
+  select_rows_phase(a, smem_raw);
+  __threadfence();
+  cluster_sync_all();
+  if (blockIdx.x % kSelectCluster == 0) select_merge_phase(a, smem_raw);
+}
+
+// Step t's selection and step t + 1's attention as ONE launch: both are per-neuron work on the same cluster shape, and
+// the attention of the new beam needs nothing but what this neuron's merge has just produced (tokens, backpointers)
+// and what the head GEMM left in the PARENT rows (query, gate, h'). A beam step is then three launches - this kernel,
+// the LSTM GEMM, the head GEMM - each boundary a grid-wide dependency (every output tile of a GEMM needs whole rows
+// of the previous one).
+// The early-exit flag is read ONCE, at kernel start (it was published by the previous step's launch): the merge of
+// another cluster may publish it for the next step while this kernel runs, and a second read could differ between
+// the CTAs of a cluster. The attention of a beam that has just ended everywhere is computed once for nothing.
+static_assert(kSelectCluster == kAttendCluster && kSelectThreads == 256, "select + attend share one cluster shape");
+// (4 CTAs per SM: 64 neurons x 8 CTAs must be resident at once - at 78 registers the 512 CTAs took two waves and the
+// merged launch was slower than the two it replaces)
+__global__ void __cluster_dims__(kSelectCluster, 1, 1) __launch_bounds__(kSelectThreads, 4)
+    select_attend_kernel(const BeamSelectArgs s, const AttendFusedArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (*s.done_flag != 0) {
+    select_done_phase(s);
+    return;  // uniform over the grid
+  }
+  select_rows_phase(s, smem_raw);
+  __threadfence();
+  cluster_sync_all();
+  if (blockIdx.x % kSelectCluster == 0) {
+    select_merge_phase(s, smem_raw);
+    __threadfence();  // next_tokens / backptr: read by every CTA of the cluster below
+  }
+  cluster_sync_all();
+  attend_phase(a, reinterpret_cast<float*>(smem_raw));
 }
 
 // ------------------------------------------------------------------ LM rerank read-out
@@ -570,6 +666,24 @@ int launch_beam_select(const BeamSelectArgs& a, cudaStream_t stream) {
   static size_t configured[64] = {};
   if (int rc = ensure_dynamic_smem(beam_select_kernel, smem, configured)) return rc;
   beam_select_kernel<<<a.n_neurons * kSelectCluster, kSelectThreads, smem, stream>>>(a);
+  return last_err();
+}
+
+int launch_select_attend(const BeamSelectArgs& s, const AttendFusedArgs& a, cudaStream_t stream) {
+  if (s.n_neurons == 0) return 0;
+  if (s.beam < 1 || s.beam > kMaxBeam || s.in_rows < 1 || s.in_rows > kSelectCluster * kSelectWarps || s.n_seg < 1 ||
+      (s.ld & 3))
+    return static_cast<int>(cudaErrorInvalidValue);
+  if (a.n_keys > kFusedMaxKeys || a.rows_per_feature != s.beam || a.R != s.n_neurons * s.beam || (a.F & 1) ||
+      (a.E & 1) || (a.H & 7) || a.tokens != s.next_tokens || a.src_row != s.backptr)
+    return static_cast<int>(cudaErrorInvalidValue);
+  const size_t attend = (8 * static_cast<size_t>(a.A) + static_cast<size_t>(a.rows_per_feature) * a.n_keys) * sizeof(float) +
+                        a.rows_per_feature * sizeof(int);
+  const size_t smem = std::max(beam_select_smem_bytes(s.in_rows, s.beam, s.V), attend);
+  if (smem > 227 * 1024) return static_cast<int>(cudaErrorInvalidValue);
+  static size_t configured[64] = {};
+  if (int rc = ensure_dynamic_smem(select_attend_kernel, smem, configured)) return rc;
+  select_attend_kernel<<<s.n_neurons * kSelectCluster, kSelectThreads, smem, stream>>>(s, a);
   return last_err();
 }
 

@@ -12,6 +12,7 @@
 //   4. beam_select       cluster of 8 CTAs per neuron, one source row per warp: log-softmax normaliser from the
 //                        partials, exact per-row top-`beam`; then CTA 0 of the cluster does the `beam x beam` merge,
 //                        backpointers / history, and allennlp's all-ended early-exit flag
+// Steps 4 (of step t) and 1 (of step t + 1) run as ONE launch, select_attend: a beam step costs three launches.
 // Everything that depends on the parent row only (query, gate, h', c') is produced in the parent's row order and read
 // through the backpointers by the consumer, so no state tensor is ever reordered in memory.
 #pragma once
@@ -76,6 +77,9 @@ struct BeamSelectArgs {
   int* counters;             // [2], zero before the first step; left zero by every launch
 };
 int launch_beam_select(const BeamSelectArgs& a, cudaStream_t stream);
+// beam_select of step t and attend_fused of step t + 1 in one launch (a.tokens / a.src_row must be s.next_tokens /
+// s.backptr; a.skip is ignored: the early-exit flag is read once, through s.done_flag).
+int launch_select_attend(const BeamSelectArgs& s, const AttendFusedArgs& a, cudaStream_t stream);
 size_t beam_select_smem_bytes(int in_rows, int beam, int V);
 
 // LM rerank: lm_scores[m] = sum over kept positions t of log p(seq[m][t] | ...) from the per-position softmax

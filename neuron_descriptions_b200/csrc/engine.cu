@@ -1301,7 +1301,7 @@ int MilanEngine::run_fused(const ConvGemmParams& p, int epilogue, cudaStream_t s
   return 0;
 }
 
-// The beam loop of decode_beam as four launches per step (decode_fused.h). On return tok_cur / last_lp hold the
+// The beam loop of decode_beam as three launches per step (decode_fused.h): LSTM GEMM, head GEMM, select + attend. On return tok_cur / last_lp hold the
 // final beam, hist_tok / hist_bp the history; state lives in Alstm / hnew / c / cnew like the unfused path.
 int MilanEngine::beam_steps_fused(const float* d_features, int B, int n_keys, int length, int beam, cudaStream_t st) {
   const int V = cfg.vocab_size, H = cfg.hidden_size, E = cfg.embedding_size, F = cfg.feature_size,
@@ -1321,20 +1321,25 @@ int MilanEngine::beam_steps_fused(const float* d_features, int B, int n_keys, in
   }
   float* c_cur = c;
   float* c_nxt = cnew;
+  // attention + gating + operand assembly of step t, from the tokens / backpointers / parent state as they are then
+  auto attend_args = [&](int t, const long long* tokens) {
+    AttendFusedArgs aa{};
+    aa.q = qg; aa.q_pitch = qgp; aa.gate = qg + A; aa.gate_pitch = qgp;
+    aa.src_row = t == 0 ? nullptr : backptr;
+    aa.kh = kh; aa.features = d_features; aa.w_o = w_o; aa.b_o = b_o;
+    aa.embedding = emb; aa.tokens = tokens;
+    if (t > 0) { aa.h_src_hi = hnew[0]; aa.h_src_lo = hnew[1]; aa.h_src_pitch = H; }
+    aa.R = t == 0 ? B : R; aa.rows_per_feature = t == 0 ? 1 : beam;
+    aa.n_keys = n_keys; aa.A = A; aa.F = F; aa.E = E; aa.H = H;
+    aa.x_hi = Alstm[0]; aa.x_lo = Alstm[1]; aa.x_pitch = xp;
+    aa.attn_ws = attn_ws; aa.skip = d_done;
+    return aa;
+  };
+  RC(launch_attend_fused(attend_args(0, tok_cur), st));
   for (int t = 0; t < length; ++t) {
     const int rows = t == 0 ? B : R;
     const int rpf = t == 0 ? 1 : beam;
     const int* parents = t == 0 ? nullptr : backptr;
-    AttendFusedArgs aa{};
-    aa.q = qg; aa.q_pitch = qgp; aa.gate = qg + A; aa.gate_pitch = qgp;
-    aa.src_row = parents;
-    aa.kh = kh; aa.features = d_features; aa.w_o = w_o; aa.b_o = b_o;
-    aa.embedding = emb; aa.tokens = tok_cur;
-    if (t > 0) { aa.h_src_hi = hnew[0]; aa.h_src_lo = hnew[1]; aa.h_src_pitch = H; }
-    aa.R = rows; aa.rows_per_feature = rpf; aa.n_keys = n_keys; aa.A = A; aa.F = F; aa.E = E; aa.H = H;
-    aa.x_hi = Alstm[0]; aa.x_lo = Alstm[1]; aa.x_pitch = xp;
-    aa.attn_ws = attn_ws; aa.skip = d_done;
-    RC(launch_attend_fused(aa, st));
     {
       const ConvGemmParams* base = nullptr;
       if (fused_gemm(F_LSTM, rows, &base, static_cast<int>(xp), W2p, b2p, Alstm[0], Alstm[1], xp)) return 1;
@@ -1365,7 +1370,12 @@ int MilanEngine::beam_steps_fused(const float* d_features, int B, int n_keys, in
     sa.next_tokens = tok_next; sa.next_lp = next_lp; sa.backptr = backptr;
     sa.hist_tok = hist_tok + static_cast<size_t>(t) * R; sa.hist_bp = hist_bp + static_cast<size_t>(t) * R;
     sa.cur_lp = last_lp; sa.done_flag = d_done; sa.counters = beam_counters;
-    RC(launch_beam_select(sa, st));
+    if (t + 1 < length) {
+      // this step's selection + the next step's attention (which reads the beam the selection has just written)
+      RC(launch_select_attend(sa, attend_args(t + 1, tok_next), st));
+    } else {
+      RC(launch_beam_select(sa, st));
+    }
     std::swap(tok_cur, tok_next);
     std::swap(last_lp, next_lp);
     std::swap(c_cur, c_nxt);

@@ -167,6 +167,7 @@ class Decoder:
             raise RuntimeError('Decoder has no weights: load a checkpoint or call load_state_dict first')
         if self._engine is not None:
             self._engine.close()
+        self._start_staging_allocation(index)  # overlaps the engine build below (weight folding + upload, ~1.5 s)
         self._engine = Engine(self._state_dict, vocab_size=self.vocab_size, device=torch.device('cuda', index),
                               embedding_size=self.embedding_size, hidden_size=self.hidden_size,
                               attention_size=self.attention_hidden_size, feature_size=self.feature_size,
@@ -174,25 +175,24 @@ class Decoder:
                               lm_hidden_size=self.lm.hidden_size if self.lm else 512, precision=self.precision,
                               max_neurons=self.max_neurons, encoder_arch=getattr(self.encoder, 'config', 'resnet101'),
                               encoder_kind=getattr(self.encoder, 'KIND', 'pyramid'), **self._capacity)
-        self._start_staging_allocation()
         if hasattr(self.encoder, 'bind'):
             self.encoder.bind(self._engine)
         if self.lm is not None:
             self.lm.bind(self._engine)
         return self
 
-    def _start_staging_allocation(self, k: int = 15, size: int = 224):
+    def _start_staging_allocation(self, device_index: int, k: int = 15, size: int = 224):
         """Allocate `predict`'s two pinned host slabs (2 x 385 MB at the default capacity; page-locking them takes
-        ~0.5 s) on a worker thread as soon as the engine exists, so that it overlaps the rest of the start-up
-        (dataset opening, the other ranks' barrier) instead of delaying the first exemplar."""
-        engine = self._engine
-        if engine is None or engine.keys_per_image != 1 or getattr(self, '_predict_staging', None) is not None:
+        ~0.5 s) on a worker thread while the engine is being built, so that the first exemplar does not wait for it."""
+        if getattr(self.encoder, 'KIND', 'pyramid') != 'pyramid' or getattr(self, '_predict_staging', None) is not None \
+                or getattr(self, '_staging_future', None) is not None:
             return
-        slab = 2 * max(16, (engine.cfg.max_neurons // 16) * 16)
+        slab = 2 * max(16, (self.max_neurons // 16) * 16)
 
         def allocate():
-            return [(torch.empty((slab, k, 3, size, size), dtype=torch.uint8, pin_memory=True),
-                     torch.empty((slab, k, 1, size, size), dtype=torch.uint8, pin_memory=True)) for _ in range(2)]
+            with torch.cuda.device(device_index):
+                return [(torch.empty((slab, k, 3, size, size), dtype=torch.uint8, pin_memory=True),
+                         torch.empty((slab, k, 1, size, size), dtype=torch.uint8, pin_memory=True)) for _ in range(2)]
 
         import concurrent.futures
         pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
