@@ -35,7 +35,10 @@ constexpr int kSmemBudget = 224 * 1024;
 
 template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK>
 struct SmemLayout {
-  static constexpr int kABytes = kGemmBlockM * BK * 2;  // one A plane per stage (BK = 64: 16 KiB, SW128; 32: SW64)
+  // one A plane per stage. BK = 64: a 16 KiB SW128 tile per k-block. BK = 32 is the stem: ONE stage per TILE holding
+  // the 38 raw padded-row segments (176 B each, 6688 B) that all seven filter rows of the tile read through
+  // overlapping-window descriptors (filter row r starts r segments in; image rows are two segments apart).
+  static constexpr int kABytes = BK == 32 ? 7168 : kGemmBlockM * BK * 2;
   static constexpr int kBBytes = BLOCK_N * BK * 2;
   static constexpr int kPlanes = SPLIT ? 2 : 1;
   // The 64-byte-k-block variant is the 7x7 stem: its whole weight matrix (7 k-blocks x 64 rows, 56 KB as hi + lo)
@@ -166,6 +169,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int th = (m_tile / p.tiles_w) % p.tiles_h;
         const int tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.box_w, h0 = th * p.box_h, n0 = tn * p.box_n;
+        if (BK == 32) {
+          // stem: the tile's raw input once - padded rows 2 h0 .. 2 h0 + 37 (both parities of 19 row pairs), the 22
+          // pixels its 8 output columns read. One box per plane instead of one per filter row: the filter rows overlap
+          // (row 2h + r serves (h, r) and (h + 1, r - 2)), so this is a third of the bytes and of the narrow 176-byte
+          // row requests, which is what bounded the stem (ncu: MMA warp starved, profiles/r02o_stem_full_summary.txt).
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * L::kStageBytes;
+          mbar_arrive_expect_tx_elect(&full_bar[stage], L::kPlanes * p.a_box_bytes);
+          tma_load_4d_elect(st, &p.tmap_a[0][0], &full_bar[stage], 8 * w0, 0, h0, n0);
+          if (SPLIT) tma_load_4d_elect(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 8 * w0, 0, h0, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         int kcoord = 0;  // running K coordinate into the weight matrix
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int plane = p.tap_plane[tap];
@@ -185,12 +201,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             constexpr bool probe_b = true;
             mbar_arrive_expect_tx_elect(&full_bar[stage], tx_bytes);
 #endif
-            if (p.stem_mode) {
-              // filter row `tap`: the raw 22-pixel segments of padded rows 2*(h + tap/2) + (tap & 1), h = h0..h0+15,
-              // that the tile's 8 output columns read; coords (element of the row, parity, row pair, n)
-              tma_load_4d_elect(st, &p.tmap_a[0][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
-              if (SPLIT) tma_load_4d_elect(st + kABytes, &p.tmap_a[1][0], &full_bar[stage], 8 * w0, p.tap_dw[tap], ch, n0);
-            } else {
+            {
               tma_load_4d_elect(st, &p.tmap_a[0][plane], &full_bar[stage], cb * BK, cw, ch, n0);
               if (SPLIT)
                 tma_load_4d_elect(st + kABytes, &p.tmap_a[1][plane], &full_bar[stage], cb * BK, cw, ch, n0);
@@ -228,17 +239,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const int kb_end = (kb + kb_per_chunk < num_kb) ? kb + kb_per_chunk : num_kb;
           const int kb_first = kb;
           for (; kb < kb_end; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes);
+            if (BK != 32 || kb == 0) {  // (stem: one stage per tile, filter row kb starts kb segments into it)
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+            }
+            const uint32_t a_hi = smem_u32(smem + stage * L::kStageBytes) + (BK == 32 ? kb * kStemSegBytes : 0);
             const uint32_t b_hi = L::kResidentB ? smem_u32(resident_b + kb * (L::kPlanes * L::kBBytes))
                                                 : a_hi + L::kPlanes * kABytes;
             // BK == 32 is the stem: A is not an im2col tile but the raw input rows, addressed as overlapping windows
-            const uint64_t da_hi = BK == 32 ? make_smem_desc_stem_rows(a_hi) : make_smem_desc_k<BK>(a_hi);
+            const uint64_t da_hi = BK == 32 ? make_smem_desc_stem_tile(a_hi) : make_smem_desc_k<BK>(a_hi);
             const uint64_t db_hi = make_smem_desc_k<BK>(b_hi);
             const uint64_t db_lo = make_smem_desc_k<BK>(b_hi + L::kBBytes);
             const uint64_t da_lo =
-                BK == 32 ? make_smem_desc_stem_rows(a_hi + kABytes) : make_smem_desc_k<BK>(a_hi + kABytes);
+                BK == 32 ? make_smem_desc_stem_tile(a_hi + kABytes) : make_smem_desc_k<BK>(a_hi + kABytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t koff = 2 * k;  // 16 bf16 = 32 B = 2 x 16-byte units
@@ -254,9 +267,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 }
               }
             }
-            umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            const bool stage_done = BK != 32 || kb == num_kb - 1;
+            if (stage_done) umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             if (kb == kb_end - 1) umma_commit_elect(&tmem_full_bar[as]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (stage_done && ++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -648,7 +662,11 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int split, int epilog
     // fp32-output GEMMs (decoder / LM) store 4 bytes per element from the epilogue: only the K = 4544 LSTM input GEMM is
     // main-loop-bound (ncu, one decode step: K = 512 GEMMs 53 -> 62 us with the wide form, K = 4544 172 -> 160 us)
     const int need_k = epilogue != EPI_BF16 ? 8 * min_k : min_k;
-    wide = min_k > 0 && num_kb * bk >= need_k;  // (the stem, K = 224, stays on three MMAs: 0.370 vs 0.382 ms)
+    // The stem (K = 224) too, since its A operand comes as one box per tile: it is bound by how fast one warp can
+    // issue N = 64 MMAs (~70 cycles of descriptor arithmetic each against 48 of tensor time), and the wide form
+    // issues 28 instead of 42 per tile: 0.334 -> 0.309 ms per 240 images (with per-filter-row boxes it was TMA-bound
+    // and three MMAs were marginally better, 0.370 vs 0.382).
+    wide = min_k > 0 && (num_kb * bk >= need_k || p.stem_mode);
   }
   static const bool pair_mode = [] {
     // cta_group::2 pairs for the long-K bf16 convs (conv_gemm_pair.cu): default since round 2 (full parity suite green,

@@ -255,7 +255,10 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
   p->tiles_w = (O + bw - 1) / bw; p->tiles_h = (O + bh - 1) / bh; p->tiles_n = (N + bn - 1) / bn;
   p->out_w = O; p->out_h = O; p->out_n = N;
   const uint32_t seg_elems = (2 * bw + 6) * 4;  // 88 bf16 = 176 B
-  p->a_box_bytes = seg_elems * 2 * bh;
+  // one box per tile and plane: both parities of the bh + 3 row pairs the seven filter rows reach = padded rows
+  // 2 h0 .. 2 h0 + 37 in order (the kernel's descriptors start filter row r at segment r, image rows 2 segments apart)
+  const uint32_t row_pairs = bh + 3;
+  p->a_box_bytes = seg_elems * 2 * 2 * row_pairs;
   const uint64_t P = static_cast<uint64_t>(kStemPadW) * 4 * 2;  // padded row pitch in bytes
   const __nv_bfloat16* imgs[2] = {img_hi, img_lo};
   const __nv_bfloat16* ws[2] = {w_hi, w_lo};
@@ -266,7 +269,7 @@ int build_stem_params(ConvGemmParams* p, int N, const __nv_bfloat16* img_hi, con
     const uint64_t dims[4] = {static_cast<uint64_t>(kStemPadW) * 4, 2, static_cast<uint64_t>(kStemPadH / 2),
                               static_cast<uint64_t>(N)};
     const uint64_t strides[3] = {P, 2 * P, static_cast<uint64_t>(kStemPadH) * P};
-    const uint32_t box[4] = {seg_elems, 1, static_cast<uint32_t>(bh), static_cast<uint32_t>(bn)};
+    const uint32_t box[4] = {seg_elems, 2, row_pairs, static_cast<uint32_t>(bn)};
     int rc = make_tmap_nd(&p->tmap_a[hl][0], imgs[hl], 4, dims, strides, box, 0);
     if (rc) return rc;
     for (int pl = 1; pl < 4; ++pl) p->tmap_a[hl][pl] = p->tmap_a[hl][0];

@@ -267,6 +267,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_stem_rows(uint32_t smem_addr)
   d |= static_cast<uint64_t>(1) << 46;
   return d;                                              // swizzle mode 0
 }
+// The conv kernel keeps ALL the padded rows a stem tile reads (2 h0 .. 2 h0 + 37, one 176-byte segment each) in one
+// stage: consecutive image rows of a filter row are then TWO segments apart (stride 2), and filter row r starts r
+// segments into the stage.
+__device__ __forceinline__ uint64_t make_smem_desc_stem_tile(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(16 >> 4) << 16;                   // leading byte offset
+  d |= static_cast<uint64_t>((2 * kStemSegBytes) >> 4) << 32;  // stride byte offset: the next image row
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;                                                    // swizzle mode 0
+}
 template <int BK>
 __device__ __forceinline__ uint64_t make_smem_desc_k(uint32_t smem_addr) {
   return BK == 64 ? make_smem_desc_sw128(smem_addr) : make_smem_desc_sw64(smem_addr);

@@ -424,6 +424,10 @@ int main(int argc, char** argv) {
     printf("%s (%d failures)\n", fails ? "SOME FAILED" : "ALL OK", fails);
     return fails ? 1 : 0;
   }
+  if (argc > 1 && std::string(argv[1]) == "stem") {  // the 240-image stem alone (ncu captures)
+    fails += run_stem(240, 1, sms);
+    return fails ? 1 : 0;
+  }
   if (argc > 1 && std::string(argv[1]) == "res") {  // the residual (expand) convs alone, for A/B runs of their kernel
     const Case shapes[] = {
         {"l1_expand", 240, 56, 56, 64, 256, 1, 1, 1, 1, 1, 0},  {"l2_expand", 240, 28, 28, 128, 512, 1, 1, 1, 1, 1, 0},
