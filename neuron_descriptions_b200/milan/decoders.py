@@ -626,6 +626,8 @@ class Decoder:
             lm = lms.LanguageModel(lm_indexer, **lm_props)
         kwargs = {key: props[key] for key in ('embedding_size', 'hidden_size', 'attention_hidden_size', 'dropout',
                                               'length', 'strategy', 'temperature', 'beam_size') if key in props}
+        if 'reranker_kwargs' in props and hasattr(cls, 'from_decoder'):  # a DecoderWithCLIP payload (`:1198-1203`)
+            kwargs['reranker_kwargs'] = props['reranker_kwargs']
         kwargs.update(overrides)
         decoder = cls(indexer, encoder, lm=lm, **kwargs)
         state_dict = payload.get('state_dict')
@@ -636,11 +638,62 @@ class Decoder:
     @classmethod
     def load(cls, file, **kwargs: Any) -> 'Decoder':
         """`SerializableModule.load`, `src/utils/serialize.py:255-269`; kwargs go to `torch.load`."""
-        overrides = {key: kwargs.pop(key) for key in ('precision', 'max_neurons') if key in kwargs}
+        overrides = {key: kwargs.pop(key) for key in ('precision', 'max_neurons', 'reranker', 'reranker_kwargs')
+                     if key in kwargs}
         kwargs.setdefault('map_location', 'cpu')
         kwargs.setdefault('weights_only', False)
         payload = torch.load(file, **kwargs)
         return cls.deserialize(payload, **overrides)
+
+
+ENGINE_MAX_BEAM = 64  # the beam kernels rank one source row per warp of an 8-CTA cluster (csrc/decode_fused.h)
+
+
+class DecoderWithCLIP(Decoder):
+    """`DecoderWithCLIP`, `src/milan/decoders.py:1115-1211`: beam-decode with MILAN, then let an image-text similarity
+    model rerank each neuron's beam against its masked and unmasked exemplars.
+
+    Differences from the reference, both forced by what is available offline:
+      * the similarity model is injected (`reranker=` a `rerankers.SimilarityReranker`, or `reranker_kwargs` with a
+        `similarity` callable) instead of being CLIP ViT-B/32 loaded by name (`rerankers.reranker`);
+      * the default beam is the engine's widest, 64, where the reference samples 1000 candidates (`:1124-1126`).
+    """
+
+    def __init__(self, *args: Any, reranker=None, reranker_kwargs: Optional[Mapping[str, Any]] = None, **kwargs: Any):
+        from neuron_descriptions_b200.milan import rerankers
+        kwargs.setdefault('strategy', STRATEGY_BEAM)
+        kwargs.setdefault('beam_size', ENGINE_MAX_BEAM)
+        kwargs.setdefault('temperature', .5)
+        super().__init__(*args, **kwargs)
+        self.reranker_kwargs = dict(reranker_kwargs) if reranker_kwargs else {}
+        self.reranker = reranker if reranker is not None else rerankers.reranker(**self.reranker_kwargs)
+
+    def forward(self, images_or_features: torch.Tensor, masks: Optional[torch.Tensor] = None,  # type: ignore[override]
+                lam: Optional[float] = None, **kwargs: Any) -> DecoderOutput:
+        """Captions / scores / tokens are those of the beam entry the reranker puts first; the remaining fields are
+        the beam decode's (`:1135-1196`). The images must be real images: the reranker sees them too."""
+        if masks is None:
+            raise ValueError('must specify masks in DecoderWithCLIP')
+        if 'strategy' in kwargs:
+            raise ValueError('cannot set "strategy" in DecoderWithCLIP')
+        images = images_or_features
+        outputs = super().forward(images, masks=masks, strategy=STRATEGY_BEAM, **kwargs)
+        assert outputs.beam_captions is not None and outputs.beam_scores is not None and outputs.beam_tokens is not None
+        reranked = self.reranker(images, masks, outputs.beam_captions, lam=lam)
+        first = torch.tensor([order[0] for order in reranked.orders], device=outputs.beam_scores.device)
+        rows = torch.arange(len(first), device=first.device)
+        return DecoderOutput(tuple(texts[0] for texts in reranked.texts), outputs.beam_scores[rows, first],
+                             outputs.beam_tokens[rows, first], *outputs[3:])
+
+    def properties(self) -> Mapping[str, Any]:
+        """`:1198-1203`. (A similarity callable inside `reranker_kwargs` is not serializable and is left out.)"""
+        kept = {key: value for key, value in self.reranker_kwargs.items() if not callable(value)}
+        return {**super().properties(), 'reranker_kwargs': kept}
+
+    @classmethod
+    def from_decoder(cls, decoder: Decoder, **kwargs: Any) -> 'DecoderWithCLIP':
+        """`:1205-1209`: a base `Decoder` with a reranker on top; `kwargs` carry `reranker=` / `reranker_kwargs=`."""
+        return cls.deserialize(decoder.serialize(), **kwargs)
 
 
 def decoder(*args, **kwargs):

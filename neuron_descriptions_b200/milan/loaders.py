@@ -26,11 +26,20 @@ def pretrained(config: str = 'base', path=None, **kwargs: Any) -> decoders.Decod
     """Return a pretrained MILAN model (`src/milan/loaders.py:28-32`)."""
     if config not in KEYS:
         raise KeyError(f'no such model in hub: {config}')
-    if config.endswith('+clip'):
-        raise NotImplementedError('CLIP reranking (DecoderWithCLIP) is out of scope (SURVEY.md #4)')
+    with_reranker = config.endswith('+clip')
+    if with_reranker:
+        # `<group>+clip` (src/milan/loaders.py:13-25): the base checkpoint of the group with the CLIP reranker on top.
+        # CLIP itself cannot be built offline, so the similarity model has to be handed in (milan/rerankers.py).
+        if 'reranker' not in kwargs and 'similarity' not in (kwargs.get('reranker_kwargs') or {}):
+            raise NotImplementedError(f'"{config}" needs CLIP ViT-B/32 (the `clip` package + weights), not available '
+                                      'offline: pass reranker=rerankers.SimilarityReranker(<similarity callable>)')
+        config = config[:-len('+clip')]
     if path is None:
         path = models_dir() / f'{config}.pth'
     path = pathlib.Path(path)
     if not path.exists():
         raise FileNotFoundError(f'model path not found: {path} (downloads are disabled: no network)')
+    if with_reranker:
+        extra = {key: kwargs.pop(key) for key in ('reranker', 'reranker_kwargs') if key in kwargs}
+        return decoders.DecoderWithCLIP.from_decoder(decoders.Decoder.load(path, **kwargs), **extra)
     return decoders.Decoder.load(path, **kwargs)

@@ -267,6 +267,48 @@ def make_vit_exemplars_golden():
     np.savez_compressed(os.path.join(GOLDEN_DIR, 'exemplars_vit.npz'), **out)
 
 
+def reranker_similarity(images, texts, masks=None):
+    """Deterministic stand-in for `CLIPWithMasks.forward` (`src/milan/rerankers.py:141-229`): (k, n) scores from the
+    exemplars, the candidate texts and, when given, the masks."""
+    per_image = images.float().mean(dim=(1, 2, 3))
+    lengths = torch.tensor([float(len(text)) for text in texts])
+    sim = torch.sin(per_image[:, None] * 7.0 + lengths[None, :] * 1.3)
+    if masks is not None:
+        sim = sim + 0.5 * torch.cos(masks.float().mean(dim=(1, 2, 3))[:, None] * 5.0 + lengths[None, :] * 0.7)
+    return sim
+
+
+def reranker_inputs():
+    gen = torch.Generator().manual_seed(41)
+    images = torch.rand(3, 4, 3, 8, 8, generator=gen)
+    masks = (torch.rand(3, 4, 1, 8, 8, generator=gen) > 0.7).float()
+    words = ('edges', 'of', 'round', 'objects', 'text', 'sky', 'animal', 'faces', 'red', 'and', 'green', 'stripes')
+    texts = []
+    for n in (5, 7, 2):
+        texts.append(tuple(' '.join(words[int(i)] for i in torch.randint(0, len(words), (int(torch.randint(1, 6, (1,), generator=gen)),),
+                                                                              generator=gen)) for _ in range(n)))
+    return images, masks, tuple(texts)
+
+
+def make_reranker_golden():
+    """The reference's `CLIPWithMasksReranker.forward` (`src/milan/rerankers.py:261-330`) around the stand-in
+    similarity: what `milan.rerankers.SimilarityReranker` has to reproduce."""
+    import importlib
+    import json
+    ref_import.import_reference()
+    ref_rerankers = importlib.import_module('src.milan.rerankers')
+    images, masks, texts = reranker_inputs()
+    out = {}
+    for name, default_lam, lam in (('default', .5, None), ('lam0.2', .5, .2), ('unmasked_only', 1., None)):
+        reranker = ref_rerankers.CLIPWithMasksReranker(reranker_similarity, lam=default_lam)
+        got = reranker(images, masks, texts, lam=lam)
+        out[name] = {'default_lam': default_lam, 'lam': lam, 'texts': [list(t) for t in got.texts],
+                     'orders': [list(o) for o in got.orders], 'scores': [list(s) for s in got.scores]}
+    with open(os.path.join(GOLDEN_DIR, 'reranker.json'), 'w') as handle:
+        json.dump(out, handle, indent=0, sort_keys=True)
+    print('reranker golden:', {k: v['orders'][0] for k, v in out.items()})
+
+
 def payload_skeleton(value):
     """A checkpoint payload with every tensor replaced by ['tensor', shape, dtype] (JSON-serialisable)."""
     if isinstance(value, dict):
@@ -338,6 +380,8 @@ def main():
         return make_score_golden(milan, lang, vocab)
     if '--only-encoders' in sys.argv:
         return make_encoder_variant_goldens(milan)
+    if '--only-reranker' in sys.argv:
+        return make_reranker_golden()
     if '--only-exemplars' in sys.argv:
         make_generative_golden()
         make_vit_exemplars_golden()

@@ -224,6 +224,41 @@ def test_lm_logprobs_and_custom_masks_match_oracle(variant):
     torch.testing.assert_close(lm(inputs, reduce=True).cpu(), O.lm_forward(inputs, sd, STOP), atol=LOGP_TOL, rtol=0)
 
 
+def test_decoder_with_reranker_contract():
+    """`DecoderWithCLIP.forward` (`src/milan/decoders.py:1135-1196`) with an injected similarity model: captions, scores
+    and tokens are those of the beam entry the reranker ranks first; everything else is the beam decode's."""
+    from neuron_descriptions_b200 import milan
+    from neuron_descriptions_b200.milan import lang, rerankers
+    from oracle.make_golden import reranker_similarity
+    sd = synthetic.synthetic_state_dict(seed=0, sharpen=12.0, stop_bias=1.0)
+    indexer = lang.Indexer(lang.Vocab(VOCAB), start=True, stop=True, pad=True, unk=True)
+    base = milan.Decoder(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False),
+                         lm=milan.LanguageModel(indexer), max_neurons=4)
+    base.load_state_dict(sd)
+    reranker = rerankers.SimilarityReranker(reranker_similarity, lam=.4)
+    decoder = milan.DecoderWithCLIP.from_decoder(base, reranker=reranker, max_neurons=4)
+    assert decoder.reranker is reranker and decoder.beam_size == base.beam_size  # properties travel with the payload
+    decoder.to('cuda:0')
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(3, 15, seed=8)
+    images, masks = O.to_float_inputs(images_u8, masks_u8)
+    with pytest.raises(ValueError, match='must specify masks'):
+        decoder(images)
+    with pytest.raises(ValueError, match='cannot set "strategy"'):
+        decoder(images, masks, strategy='greedy')
+    out = decoder(images, masks, beam_size=12, mi=False)
+    beam = milan.Decoder.forward(decoder, images, masks=masks, strategy='beam', beam_size=12, mi=False)
+    ranked = reranker(images, masks, beam.beam_captions)
+    for i in range(3):
+        first = ranked.orders[i][0]
+        assert out.captions[i] == beam.beam_captions[i][first] == ranked.texts[i][0]
+        assert torch.equal(out.tokens[i], beam.beam_tokens[i, first])
+        assert float(out.scores[i]) == float(beam.beam_scores[i, first])
+    assert torch.equal(out.beam_tokens, beam.beam_tokens) and len(out.beam_captions) == 3
+    assert 'reranker_kwargs' in decoder.properties()
+    with pytest.raises(NotImplementedError, match='clip'):
+        milan.DecoderWithCLIP(indexer, milan.PyramidConvEncoder('resnet101', pretrained=False))
+
+
 def test_beam_properties_full_size():
     """Size-independent properties at BASELINE size (16 neurons x beam 50 x 15 steps, V = 5004)."""
     sd = synthetic.synthetic_state_dict(seed=1, sharpen=12.0, stop_bias=2.0, with_encoder=False)
