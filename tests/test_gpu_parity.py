@@ -423,6 +423,33 @@ def test_edge_cases_vs_oracle():
     engine.close()
 
 
+def test_encoder_batch_invariance_full_size(full_sd):
+    """BASELINE size (64 neurons x 15 exemplars = 960 images per step), size-independent properties of the encoder:
+    an image's features do not depend on what else is in the batch (tiles of the implicit GEMM span image boundaries,
+    CTA pairs split M tiles between two SMs) - bit for bit -, all-zero masks give exactly zero features, and masked
+    pooling is invariant to the image content outside the mask's support."""
+    engine = _engine(full_sd, max_neurons=64)
+    images_u8, masks_u8 = synthetic.synthetic_exemplars(64, 15, seed=77, zero_mask_fraction=0.05)
+    images, masks = images_u8.view(-1, 3, 224, 224), masks_u8.view(-1, 1, 224, 224)
+    full = engine.encode(images, masks)
+    assert full.shape == (960, synthetic.FEATURE_SIZE) and torch.isfinite(full).all()
+    picks = torch.tensor([0, 1, 127, 128, 500, 958, 959])
+    alone = engine.encode(images[picks].contiguous(), masks[picks].contiguous())
+    assert torch.equal(full[picks], alone), 'features depend on the batch an image is encoded in'
+    empty = masks.view(960, -1).sum(dim=1) == 0
+    assert empty.any() and (full[empty.to(full.device)] == 0).all()
+    # the first retained map (raw conv1, 7x7 receptive field): pixels further than the stem's reach from every mask
+    # pixel cannot influence level 0 of the pyramid
+    i = int(picks[3])
+    keep = torch.nn.functional.max_pool2d(masks[i:i + 1].float(), kernel_size=31, stride=1, padding=15) > 0
+    scrambled = images[i:i + 1].clone()
+    noise = torch.randint(0, 256, scrambled.shape, dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    scrambled = torch.where(keep.expand_as(scrambled), scrambled, noise)
+    again = engine.encode(scrambled, masks[i:i + 1].contiguous())
+    assert torch.equal(again[0, :64], full[i, :64])
+    engine.close()
+
+
 def test_empty_inputs(full_engine):
     out = full_engine.encode(torch.zeros(0, 3, 224, 224, dtype=torch.uint8), torch.zeros(0, 1, 224, 224, dtype=torch.uint8))
     assert out.shape == (0, synthetic.FEATURE_SIZE)
