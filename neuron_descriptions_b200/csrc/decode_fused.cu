@@ -100,12 +100,29 @@ __device__ __forceinline__ void attend_phase(const AttendFusedArgs& a, float* sm
     for (int i = lane; i < a.A; i += 32) q[i] = qrow[i];
     __syncwarp();
     float score = -INFINITY;  // lane k keeps the score of key k
-    for (int k = 0; k < a.n_keys; ++k) {
-      const float* khr = a.kh + (static_cast<long long>(fidx) * a.n_keys + k) * a.A;
-      float s = 0.f;
-      for (int i = lane; i < a.A; i += 32) s += __ldg(a.w_o + i) * tanh_fast(q[i] + __ldg(khr + i));
-      s = warp_sum(s);
-      if (lane == k) score = s + a.b_o;
+    {
+      // all keys of an attention column at once: n_keys independent tanh chains per lane keep the SFU pipe full (one
+      // key at a time left every FADD waiting for its own ex2 + rcp). Per key the summation order is unchanged.
+      float acc[kFusedMaxKeys];
+#pragma unroll
+      for (int k = 0; k < kFusedMaxKeys; ++k) acc[k] = 0.f;
+      const float* khb = a.kh + static_cast<long long>(fidx) * a.n_keys * a.A;
+      const int last = a.n_keys - 1;
+      for (int i = lane; i < a.A; i += 32) {
+        const float qi = q[i], wo = __ldg(a.w_o + i);
+        float kv[kFusedMaxKeys];  // branch-free: slots past n_keys re-read the last key and are never used
+#pragma unroll
+        for (int k = 0; k < kFusedMaxKeys; ++k) kv[k] = __ldg(khb + static_cast<long long>(min(k, last)) * a.A + i);
+#pragma unroll
+        for (int k = 0; k < kFusedMaxKeys; ++k) acc[k] += wo * tanh_fast(qi + kv[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kFusedMaxKeys; ++k) {
+        if (k < a.n_keys) {
+          const float sk = warp_sum(acc[k]);
+          if (lane == k) score = sk + a.b_o;
+        }
+      }
     }
     const float mx = warp_max(score);
     const float e = lane < a.n_keys ? expf(score - mx) : 0.f;
@@ -150,7 +167,7 @@ __device__ __forceinline__ void attend_phase(const AttendFusedArgs& a, float* sm
     for (int k = 0; k < kFusedMaxKeys; ++k)
       f[k] = k < a.n_keys ? __ldg(reinterpret_cast<const float2*>(fb + static_cast<long long>(k) * a.F + 2 * j2))
                           : make_float2(0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
     for (int rl = 0; rl < rpf; ++rl) {
       const float2 g = *reinterpret_cast<const float2*>(a.gate + static_cast<long long>(src_s[rl]) * a.gate_pitch + 2 * j2);
       const float* w = w_s + rl * a.n_keys;
@@ -477,7 +494,60 @@ __device__ __forceinline__ void select_merge_phase(const BeamSelectArgs& a, uint
     cls_s[i] = gc[i];
   }
   __syncthreads();
-  if (warp == 0) {  // one warp, two list heads per lane
+  // The next beam = the `beam` best of n_cand candidates in (value desc, flat index asc) order - what a k-way merge of
+  // the sorted lists yields. In parallel: the beam-th largest VALUE by a bitwise search over the keys (CTA-wide counts,
+  // one barrier per bit), then only the candidates at or above it are ranked against each other. (The sequential
+  // k-way merge by one warp took ~25 us of the step with the other seven CTAs of the cluster waiting; it stays as the
+  // fallback for mass ties at the threshold, e.g. fewer finite candidates than beams.)
+  constexpr int kPer = (kSelectCluster * kSelectWarps * kMaxBeam + kSelectThreads - 1) / kSelectThreads;
+  constexpr int kWinCap = 128;
+  unsigned* cnt = S.hist;          // [0, 32): candidates at or above the trial key of each bit; [33]: winners
+  unsigned* win = S.hist + 64;     // [kWinCap] flat indices of the winners
+  unsigned key[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = threadIdx.x + kSelectThreads * j;
+    key[j] = i < n_cand ? float_key(val_s[i]) : 0u;
+  }
+  if (threadIdx.x < 34) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned kth = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned trial = kth | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) c += key[j] >= trial ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c > 0) atomicAdd(&cnt[bit], static_cast<unsigned>(c));
+    __syncthreads();
+    if (cnt[bit] >= static_cast<unsigned>(a.beam)) kth = trial;
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = threadIdx.x + kSelectThreads * j;
+    if (i < n_cand && key[j] >= kth) {
+      const unsigned pos = atomicAdd(&cnt[33], 1u);
+      if (pos < kWinCap) win[pos] = static_cast<unsigned>(i);
+    }
+  }
+  __syncthreads();
+  const int n_win = static_cast<int>(cnt[33]);  // >= beam; uniform
+  if (n_win <= kWinCap) {
+    for (int w = threadIdx.x; w < n_win; w += kSelectThreads) {
+      const int flat = static_cast<int>(win[w]);
+      const ValIdx me{val_s[flat], flat};
+      int rank = 0;
+      for (int u = 0; u < n_win; ++u) {
+        const int fu = static_cast<int>(win[u]);
+        rank += better(ValIdx{val_s[fu], fu}, me) ? 1 : 0;
+      }
+      if (rank < a.beam) {
+        S.flat[rank] = flat;
+        S.best[rank] = me.v;
+      }
+    }
+  } else if (warp == 0) {  // one warp, two list heads per lane
     int ptr0 = 0, ptr1 = 0;
     const int r0 = lane, r1 = lane + 32;
     for (int j = 0; j < a.beam; ++j) {
