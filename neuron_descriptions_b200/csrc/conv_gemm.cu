@@ -48,7 +48,9 @@ struct SmemLayout {
   static constexpr int kResidentKb = kResidentB ? 7 : 0;
   static constexpr int kResidentBytes = kResidentKb * kPlanes * kBBytes;
   static constexpr int kStageBytes = kPlanes * (kABytes + (kResidentB ? 0 : kBBytes));
-  static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kTileBytes : 0;            // one 64-col chunk
+  // one 64-column chunk: bf16 hi + lo planes for the TMA stores, or (EPI_HEAD) the same 32 KiB as 128 x 64 fp32 through
+  // which the epilogue transposes its thread-per-row registers into row-contiguous global stores
+  static constexpr int kStagingBytes = EPI == EPI_BF16 ? kPlanes * kTileBytes : (EPI == EPI_HEAD ? 2 * kTileBytes : 0);
   static constexpr int kResBytes = (EPI == EPI_BF16 && HAS_RES) ? 2 * kPlanes * kTileBytes : 0;  // 2-deep ring
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes - kResBytes - kResidentBytes) / kStageBytes;
 #ifndef MILAN_MAX_STAGES
@@ -64,6 +66,10 @@ struct SmemLayout {
 
 // byte offset of 16-byte chunk j of row r inside a [128][128 B] tile with the TMA/UMMA 128-byte swizzle
 __device__ __forceinline__ uint32_t swz(int r, int j) { return static_cast<uint32_t>(r) * 128u + ((j ^ (r & 7)) << 4); }
+
+// byte offset of 16-byte chunk j (0..15) of row r inside a [128][256 B] fp32 staging tile: the same XOR on the low three
+// chunk bits, so that 8 consecutive rows writing the same chunk, and one row read across a warp, are conflict-free
+__device__ __forceinline__ uint32_t swz256(int r, int j) { return static_cast<uint32_t>(r) * 256u + ((j ^ (r & 7)) << 4); }
 
 template <int BLOCK_N, bool SPLIT, int EPI, bool HAS_RES, int BK, bool WIDE>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p,
@@ -477,6 +483,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const FusedEpilogue& fe = p.fe;
         const long long r = static_cast<long long>(tw) * p.box_w + row;
         const bool valid = r < p.out_w;
+        // One 64-column chunk of the tile -> global memory, row-contiguous: every thread holds 32 columns of ITS row, so
+        // storing from registers writes 16 bytes to each of 32 different rows per instruction (120 MB of such stores per
+        // beam step made the head GEMM 57 % slower per tile than the LM head, which stores nothing). Through the
+        // staging tile instead: each warp then writes whole 256-byte row segments. All epilogue threads call this
+        // (two named barriers); rows past M and columns past `col_limit` are masked at the store.
+        auto store_rows = [&](const float (&vals)[32], float* dst, long long pitch, int col0, int col_limit) {
+          named_bar_sync(1, kEpiThreads);  // the previous chunk has been read back
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(staging + swz256(row, group * 8 + j)) =
+                make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+          named_bar_sync(1, kEpiThreads);
+          const int ew = warp - 2;  // 0..7: rows [16 ew, 16 ew + 16) of the tile
+          const int col = col0 + 2 * lane;
+          const long long row0 = static_cast<long long>(tw) * p.box_w + ew * 16;
+#pragma unroll 4
+          for (int rr = 0; rr < 16; ++rr) {
+            const int rl = ew * 16 + rr;
+            const float2 x = *reinterpret_cast<const float2*>(staging + swz256(rl, lane >> 1) + (lane & 1) * 8);
+            if (row0 + rr < p.out_w) {
+              float* o = dst + (row0 + rr) * pitch + col;
+              if (col + 1 < col_limit) *reinterpret_cast<float2*>(o) = x;
+              else if (col < col_limit) *o = x.x;
+            }
+          }
+        };
         const int tile_col0 = n_tile * BLOCK_N + group * 32;  // chunk c adds 64 c
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {  // + bias (padded to whole tiles)
@@ -508,23 +540,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           }
           if (valid) {
             fe.partials[r * (2 * fe.vocab_tiles) + n_tile * 2 + group] = make_float2(mx, sum);
-            if (fe.logits != nullptr) {
-#pragma unroll
-              for (int c = 0; c < kChunks; ++c) {
-                const int col0 = tile_col0 + c * 64;
-                float* o = fe.logits + r * fe.ld_logits + col0;
-                if (col0 + 32 <= fe.vocab) {
-                  float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    o4[j] = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (col0 + j < fe.vocab) o[j] = v[c][j];
-                }
-              }
-            }
             if (fe.target != nullptr) {
               const int rel = static_cast<int>(fe.target[r * fe.target_stride]) - tile_col0;  // column within this thread's view
               if (rel >= 0 && rel < 96 && (rel & 32) == 0) {  // [0, 32) -> chunk 0, [64, 96) -> chunk 1
@@ -538,24 +553,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               }
             }
           }
-        } else if (valid) {
+          if (fe.logits != nullptr) {  // uniform
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c)
+              store_rows(v[c], fe.logits, fe.ld_logits, n_tile * BLOCK_N + c * 64, fe.vocab);
+          }
+        } else {
           const bool is_q = n_tile < fe.vocab_tiles + fe.q_tiles;
-          const int base = is_q ? (n_tile - fe.vocab_tiles) * BLOCK_N + group * 32
-                                : (n_tile - fe.vocab_tiles - fe.q_tiles) * BLOCK_N + group * 32;
+          const int base = is_q ? (n_tile - fe.vocab_tiles) * BLOCK_N : (n_tile - fe.vocab_tiles - fe.q_tiles) * BLOCK_N;
           const int limit = is_q ? fe.q_cols : fe.gate_cols;
-          float* dst = is_q ? fe.q_out + r * fe.q_pitch : fe.g_out + r * fe.g_pitch;
 #pragma unroll
           for (int c = 0; c < kChunks; ++c) {
-            const int col0 = base + c * 64;
-            if (col0 + 32 <= limit) {  // sections are multiples of 32 columns wide
+            if (base + c * 64 < limit) {  // uniform
               if (!is_q) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[c][j] = sigmoid_fast(v[c][j]);
               }
-              float4* o4 = reinterpret_cast<float4*>(dst + col0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                o4[j] = make_float4(v[c][4 * j], v[c][4 * j + 1], v[c][4 * j + 2], v[c][4 * j + 3]);
+              store_rows(v[c], is_q ? fe.q_out : fe.g_out, is_q ? fe.q_pitch : fe.g_pitch, base + c * 64, limit);
             }
           }
         }
