@@ -117,6 +117,32 @@ def test_compute_exemplars_cli(tmp_path):
     assert 0 < float(dataset[0].masks.float().mean()) < 0.2  # 0.99-quantile masks: a few percent of the pixels
 
 
+def test_bench_line_contract():
+    """`python bench.py` (a short run): ONE JSON line with every key the driver reads, the roofline / e2e / clocks
+    sub-objects, a non-zero count of this library's kernel launches and the same `config` dict as the reference arm."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '3', '--warmup', '3',
+                          '--neurons-per-step', '16', '--no-cpu-baseline', '--no-fast-mode', '--no-strong-scaling'],
+                         env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'roofline', 'e2e', 'gpu_launches', 'clocks'):
+        assert key in line, key
+    assert line['unit'] == 'neurons/s' and line['higher_is_better'] is True and line['scaling'] == 'weak'
+    assert line['value'] > 0 and line['e2e']['value'] > 0 and line['gpu_launches'] > 0
+    assert line['e2e']['h2d_bytes_per_step'] == 16 * 15 * 4 * 224 * 224 and line['e2e']['d2h_bytes_per_step'] > 0
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in line['roofline'], key
+    assert line['roofline']['bound'] == 'tensor' and 0 < line['roofline']['frac'] < 1
+    assert abs(line['roofline']['frac'] - line['roofline']['achieved'] / line['roofline']['peak']) < 1e-9
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line['config'] == bench.shared_config() and 'model' not in line['config']
+
+
 def test_smoke_without_cta_pair_convs():
     """The cta_group::2 conv kernel is the default; MILAN_PAIR=0 (read once per process) selects the single-CTA
     kernel for the same convs. smoke() checks features, rerank scores and token ids against the oracle."""
