@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -1478,6 +1479,10 @@ int milan_engine_create(const MilanConfig* config, int device, MilanEngine** out
   eng->cfg = *config;
   eng->device = device;
   eng->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("MILAN_NUM_SMS")) {  // experiment knob: CTAs of the persistent conv / GEMM kernels (two engines can share a GPU)
+    const int n = atoi(e);
+    if (n >= 2 && n <= eng->num_sms) eng->num_sms = n & ~1;
+  }
   eng->split = config->precision == MILAN_PRECISION_SPLIT;
   eng->arch = arch;
   eng->expansion = expansion;
